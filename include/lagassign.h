@@ -1,0 +1,188 @@
+/*
+ * lagassign.h — C ABI of the B200-native lag-balancing partition assignor.
+ *
+ * This is the drop-in boundary for ONE hot path of
+ * grantneale/kafka-lag-based-assignor: the pure function
+ *
+ *     static Map<String, List<TopicPartition>> assign(
+ *         Map<String, List<TopicPartitionLag>> partitionLagPerTopic,
+ *         Map<String, List<String>> subscriptions)
+ *
+ * (reference: src/main/java/com/github/grantneale/kafka/
+ *  LagBasedPartitionAssignor.java:166-188, which drives assignTopic :204-277
+ *  and consumersPerTopic :410-426; the plugin entry that calls it is :149).
+ *
+ * The reference is a JVM class with no native code, so this header is what a
+ * JNI shim would bind. Plain C: pointers and sizes only,
+ * no C++ types, no exceptions, no torch types. All entry points return 0 on
+ * success or a negative LAGASSIGN_ERR_* code; the message is available from
+ * lagassign_last_error(). There is NO CPU fallback: without a CUDA device
+ * lagassign_create() fails with LAGASSIGN_ERR_NO_DEVICE.
+ *
+ * Flat layout ("CSR") replacing the reference's maps of boxed objects:
+ *
+ *   topics        t = 0..T-1, in the order the caller wants results grouped
+ *   topic_off     int64[T+1]  partitions of topic t are [topic_off[t], topic_off[t+1])
+ *   lag           int64[N]    TopicPartitionLag.getLag()        (Main:451-453)
+ *   partition     int32[N]    TopicPartitionLag.getPartition()  (Main:447-449);
+ *                             NULL means ids 0..P-1 in order
+ *   consumer sets s = 0..S-1: the distinct values of consumersPerTopic (Main:410-426)
+ *   cset_off      int64[S+1]
+ *   cset_rank     int32[R]    members of set s, as GLOBAL member ranks, strictly
+ *                             ascending inside each set. rank r = position of the
+ *                             member id in String.compareTo order (Main:258-259)
+ *   topic_cset    int32[T]    which consumer set subscribes topic t
+ *
+ * Result, per topic, in ASSIGNMENT ORDER (the order of the loop Main:237, i.e.
+ * lag descending / partition ascending, Main:228-235):
+ *
+ *   out_partition[topic_off[t] + k]      partition id of the k-th assigned partition
+ *   out_consumer_rank[topic_off[t] + k]  global rank of the member chosen for it
+ *                                        (Collections.min of Main:240-263)
+ *
+ * A topic whose consumer set is empty is never visited by the reference
+ * (Main:177 iterates consumersPerTopic only): its partitions come back in input
+ * order with out_consumer_rank = -1.
+ *
+ * Optional check outputs (reference: consumerTotalLags / consumerTotalPartitions
+ * at the end of assignTopic, Main:216-225, :265-266), laid out per topic then
+ * per member of the topic's consumer set (set order), at offset
+ * tc_off[t] = sum_{u<t} |cset(topic_cset[u])|:
+ *
+ *   out_total  int64[sum_t C_t]   wrapping signed 64-bit sums
+ *   out_count  int32[sum_t C_t]
+ */
+#ifndef LAGASSIGN_H
+#define LAGASSIGN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LAGASSIGN_ABI_VERSION 1
+
+#define LAGASSIGN_OK               0
+#define LAGASSIGN_ERR_ARG         -1  /* NULL pointer, non-monotone offsets, unsorted set ... */
+#define LAGASSIGN_ERR_CUDA        -2  /* a CUDA runtime call or kernel failed */
+#define LAGASSIGN_ERR_OOM         -3  /* host or device allocation failed */
+#define LAGASSIGN_ERR_STATE       -4  /* call order violated (execute before upload ...) */
+#define LAGASSIGN_ERR_NO_DEVICE   -5  /* no usable CUDA device: there is no CPU fallback */
+#define LAGASSIGN_ERR_UNSUPPORTED -6  /* shape outside what the kernels cover */
+
+typedef struct lagassign_ctx lagassign_ctx;
+
+/* Inputs of one assign() call. All pointers are HOST pointers owned by the
+ * caller; the library copies what it needs before returning. */
+typedef struct lagassign_batch {
+    int64_t        n_topics;    /* T */
+    const int64_t *topic_off;   /* [T+1], topic_off[0] == 0, non-decreasing */
+    const int64_t *lag;         /* [N], N = topic_off[T] */
+    const int32_t *partition;   /* [N] or NULL */
+    const int32_t *topic_cset;  /* [T], values in [0, n_csets) */
+    int64_t        n_csets;     /* S */
+    const int64_t *cset_off;    /* [S+1], cset_off[0] == 0, non-decreasing */
+    const int32_t *cset_rank;   /* [cset_off[S]], strictly ascending inside a set, >= 0 */
+} lagassign_batch;
+
+/* Outputs of one assign() call. HOST pointers owned by the caller. out_total
+ * and out_count may be NULL (they are only produced when enabled with
+ * lagassign_set_option(LAGASSIGN_OPT_TOTALS, 1) before upload). */
+typedef struct lagassign_result {
+    int32_t *out_partition;      /* [N] */
+    int32_t *out_consumer_rank;  /* [N] */
+    int64_t *out_total;          /* [sum_t C_t] or NULL */
+    int32_t *out_count;          /* [sum_t C_t] or NULL */
+} lagassign_result;
+
+/* Raw offsets for the fused lag computation (reference: computePartitionLag,
+ * Main:376-404, called per partition at Main:344-356). When given to
+ * lagassign_upload_offsets() the device computes
+ *   lag = max(end - (has_committed ? committed : (reset_latest ? end : begin)), 0)
+ * with wrapping int64 subtraction, in the same pass that builds the sort keys. */
+typedef struct lagassign_offsets {
+    const int64_t *begin_offset;  /* [N]  topicBeginOffsets.getOrDefault(p, 0)  Main:350 */
+    const int64_t *end_offset;    /* [N]  topicEndOffsets.getOrDefault(p, 0)    Main:351 */
+    const int64_t *committed;     /* [N]  OffsetAndMetadata.offset()            Main:386 */
+    const uint8_t *has_committed; /* [N]  partitionMetadata != null             Main:384 */
+    int32_t        reset_latest;  /* auto.offset.reset equalsIgnoreCase "latest" Main:391 */
+} lagassign_offsets;
+
+/* Counters of the last execute(), for benchmarks and tests. */
+typedef struct lagassign_stats {
+    int64_t n_partitions;        /* N */
+    int64_t n_assigned;          /* partitions that received a consumer */
+    int64_t topics_warp;         /* topics sorted+filled by one warp  (P <= 256) */
+    int64_t topics_cta;          /* topics sorted+filled by one CTA   (P <= 4096) */
+    int64_t topics_device;       /* topics sorted by the device-wide radix path */
+    int64_t topics_unassigned;   /* topics with an empty consumer set */
+    int64_t device_sort_elems;   /* elements that went through the radix path */
+    int32_t radix_passes_run;    /* digit passes that moved data (max over topics) */
+    int32_t kernel_launches;     /* kernels launched by the last execute() */
+    int64_t h2d_bytes;           /* bytes copied host->device by the last upload() */
+    int64_t d2h_bytes;           /* bytes copied device->host by the last download() */
+} lagassign_stats;
+
+#define LAGASSIGN_OPT_TOTALS 1   /* produce out_total / out_count (default 0) */
+
+int  lagassign_abi_version(void);
+
+/* Number of CUDA devices visible; 0 devices is not an error here. */
+int  lagassign_device_count(int *n_devices);
+
+/* One context = one device + one stream + reusable device workspaces.
+ * Mirrors one LagBasedPartitionAssignor instance (Main:83-89). Not re-entrant:
+ * like the reference's instance state (Main:87-89) a context must be used from
+ * one thread at a time; distinct contexts are independent. */
+int  lagassign_create(lagassign_ctx **ctx, int device);
+
+/* Same, but all work is enqueued on the caller's CUDA stream (a cudaStream_t
+ * passed as void*), so a caller that times with its own events on that stream
+ * sees the kernels. */
+int  lagassign_create_on_stream(lagassign_ctx **ctx, int device, void *cuda_stream);
+
+void lagassign_destroy(lagassign_ctx *ctx);
+
+/* Last error text of this context (or of the calling thread when ctx is NULL). */
+const char *lagassign_last_error(const lagassign_ctx *ctx);
+
+int  lagassign_set_option(lagassign_ctx *ctx, int option, int64_t value);
+
+/* The whole hot path with host buffers in and out: what replaces the call at
+ * Main:149. Equivalent to upload + execute + download. Blocking. */
+int  lagassign_assign_batch(lagassign_ctx *ctx, const lagassign_batch *in,
+                            const lagassign_result *out);
+
+/* Split form. upload: validate, plan (bin topics by size), copy inputs to HBM.
+ * execute: enqueue the kernels (asynchronous). download: wait and copy results
+ * to host. execute may be repeated on the same uploaded batch. */
+int  lagassign_upload(lagassign_ctx *ctx, const lagassign_batch *in);
+int  lagassign_upload_offsets(lagassign_ctx *ctx, const lagassign_batch *in,
+                              const lagassign_offsets *offs);
+int  lagassign_execute(lagassign_ctx *ctx);
+int  lagassign_sync(lagassign_ctx *ctx);
+int  lagassign_download(lagassign_ctx *ctx, const lagassign_result *out);
+
+/* Multi-GPU: make execute() write out_partition / out_consumer_rank straight
+ * into caller-owned DEVICE memory (e.g. this rank's slice of an all-gather
+ * buffer). Pass NULLs to go back to the context's own buffers. */
+int  lagassign_bind_device_outputs(lagassign_ctx *ctx, int32_t *d_out_partition,
+                                   int32_t *d_out_consumer_rank);
+
+/* Device copy of the computed lags (valid after execute(); for tests of the
+ * fused lag computation). */
+int  lagassign_download_lags(lagassign_ctx *ctx, int64_t *lag_out);
+
+int  lagassign_get_stats(const lagassign_ctx *ctx, lagassign_stats *stats);
+
+/* Pinned host memory, so uploads/downloads run at full PCIe speed. A JNI
+ * caller wraps these with NewDirectByteBuffer. */
+int  lagassign_host_alloc(void **ptr, size_t bytes);
+int  lagassign_host_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAGASSIGN_H */
