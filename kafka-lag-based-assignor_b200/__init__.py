@@ -1,0 +1,297 @@
+"""B200-native lag-based partition assignment — Python binding of the C ABI.
+
+The product is ``liblagassign.so`` (hand-written sm_100a CUDA kernels behind the
+plain-C interface of ``include/lagassign.h``), the drop-in for the pure function
+``LagBasedPartitionAssignor.assign(Map, Map)`` of the reference
+(LagBasedPartitionAssignor.java:166-188). This module is only a ctypes binding
+for tests, benchmarks and Python callers; it contains no algorithm and there is
+no CPU fallback: without the built library or without a CUDA device every call
+raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+__all__ = ["LagAssignError", "FlatAssignor", "load_library", "library_path", "pinned_empty",
+           "LagBasedPartitionAssignor", "TopicPartitionLag", "TopicPartition", "compute_partition_lag"]
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_LIB_NAME = "liblagassign.so"
+_lib: Optional[ctypes.CDLL] = None
+
+ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_OOM", -4: "ERR_STATE",
+             -5: "ERR_NO_DEVICE", -6: "ERR_UNSUPPORTED"}
+OPT_TOTALS = 1
+
+
+class LagAssignError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"lagassign {ERR_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+class _Batch(ctypes.Structure):
+    _fields_ = [("n_topics", ctypes.c_int64), ("topic_off", ctypes.c_void_p), ("lag", ctypes.c_void_p),
+                ("partition", ctypes.c_void_p), ("topic_cset", ctypes.c_void_p), ("n_csets", ctypes.c_int64),
+                ("cset_off", ctypes.c_void_p), ("cset_rank", ctypes.c_void_p)]
+
+
+class _Result(ctypes.Structure):
+    _fields_ = [("out_partition", ctypes.c_void_p), ("out_consumer_rank", ctypes.c_void_p),
+                ("out_total", ctypes.c_void_p), ("out_count", ctypes.c_void_p)]
+
+
+class _Offsets(ctypes.Structure):
+    _fields_ = [("begin_offset", ctypes.c_void_p), ("end_offset", ctypes.c_void_p),
+                ("committed", ctypes.c_void_p), ("has_committed", ctypes.c_void_p),
+                ("reset_latest", ctypes.c_int32)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("n_partitions", ctypes.c_int64), ("n_assigned", ctypes.c_int64),
+                ("topics_warp", ctypes.c_int64), ("topics_cta", ctypes.c_int64),
+                ("topics_device", ctypes.c_int64), ("topics_unassigned", ctypes.c_int64),
+                ("device_sort_elems", ctypes.c_int64), ("radix_passes_run", ctypes.c_int32),
+                ("kernel_launches", ctypes.c_int32), ("h2d_bytes", ctypes.c_int64),
+                ("d2h_bytes", ctypes.c_int64)]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+def library_path() -> str:
+    return os.path.join(_PKG_DIR, _LIB_NAME)
+
+
+def load_library() -> ctypes.CDLL:
+    """Load liblagassign.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise LagAssignError(-5, f"{path} is missing: build it with __graft_entry__.build() "
+                                 "(nvcc, sm_100a). There is no CPU fallback.")
+    L = ctypes.CDLL(path)
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    L.lagassign_abi_version.restype = i32
+    L.lagassign_device_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
+    L.lagassign_create.argtypes = [ctypes.POINTER(vp), i32]
+    L.lagassign_create_on_stream.argtypes = [ctypes.POINTER(vp), i32, vp]
+    L.lagassign_destroy.argtypes = [vp]
+    L.lagassign_destroy.restype = None
+    L.lagassign_last_error.argtypes = [vp]
+    L.lagassign_last_error.restype = ctypes.c_char_p
+    L.lagassign_set_option.argtypes = [vp, i32, i64]
+    L.lagassign_assign_batch.argtypes = [vp, ctypes.POINTER(_Batch), ctypes.POINTER(_Result)]
+    L.lagassign_upload.argtypes = [vp, ctypes.POINTER(_Batch)]
+    L.lagassign_upload_offsets.argtypes = [vp, ctypes.POINTER(_Batch), ctypes.POINTER(_Offsets)]
+    L.lagassign_execute.argtypes = [vp]
+    L.lagassign_sync.argtypes = [vp]
+    L.lagassign_download.argtypes = [vp, ctypes.POINTER(_Result)]
+    L.lagassign_bind_device_outputs.argtypes = [vp, vp, vp]
+    L.lagassign_download_lags.argtypes = [vp, vp]
+    L.lagassign_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    L.lagassign_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
+    L.lagassign_host_free.argtypes = [vp]
+    for name in ("lagassign_device_count", "lagassign_create", "lagassign_create_on_stream",
+                 "lagassign_set_option", "lagassign_assign_batch", "lagassign_upload",
+                 "lagassign_upload_offsets", "lagassign_execute", "lagassign_sync", "lagassign_download",
+                 "lagassign_bind_device_outputs", "lagassign_download_lags", "lagassign_get_stats",
+                 "lagassign_host_alloc", "lagassign_host_free"):
+        getattr(L, name).restype = i32
+    _lib = L
+    return L
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+def _arr(a, dtype, name):
+    if a is None:
+        return None
+    out = np.ascontiguousarray(a, dtype=dtype)
+    if out.ndim != 1:
+        raise ValueError(f"{name} must be one-dimensional")
+    return out
+
+
+class _PinnedOwner:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            load_library().lagassign_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(n: int, dtype) -> np.ndarray:
+    """numpy array over pinned host memory from lagassign_host_alloc()."""
+    dtype = np.dtype(dtype)
+    L = load_library()
+    p = ctypes.c_void_p()
+    rc = L.lagassign_host_alloc(ctypes.byref(p), max(1, n) * dtype.itemsize)
+    if rc != 0:
+        raise LagAssignError(rc, L.lagassign_last_error(None).decode())
+    buf = (ctypes.c_char * (max(1, n) * dtype.itemsize)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n)
+    owner = _PinnedOwner(p.value)
+    _PINNED[arr.ctypes.data] = owner
+    return arr
+
+
+_PINNED = {}
+
+
+class FlatAssignor:
+    """One lagassign context (one GPU, one stream). Flat-array interface, see
+    include/lagassign.h for the layout."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None, want_totals: bool = False):
+        self._L = load_library()
+        self._ctx = ctypes.c_void_p()
+        if stream is None:
+            rc = self._L.lagassign_create(ctypes.byref(self._ctx), device)
+        else:
+            rc = self._L.lagassign_create_on_stream(ctypes.byref(self._ctx), device, ctypes.c_void_p(stream))
+        if rc != 0:
+            raise LagAssignError(rc, self._L.lagassign_last_error(None).decode())
+        self._keep = None
+        self._shape = None
+        if want_totals:
+            self.set_option(OPT_TOTALS, 1)
+        self.want_totals = want_totals
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._L.lagassign_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise LagAssignError(rc, self._L.lagassign_last_error(self._ctx).decode())
+
+    def set_option(self, option: int, value: int):
+        self._check(self._L.lagassign_set_option(self._ctx, option, value))
+
+    def _batch(self, topic_off, lag, partition, topic_cset, cset_off, cset_rank):
+        topic_off = _arr(topic_off, np.int64, "topic_off")
+        lag = _arr(lag, np.int64, "lag")
+        partition = _arr(partition, np.int32, "partition")
+        topic_cset = _arr(topic_cset, np.int32, "topic_cset")
+        cset_off = _arr(cset_off, np.int64, "cset_off")
+        cset_rank = _arr(cset_rank, np.int32, "cset_rank")
+        T = len(topic_off) - 1
+        S = len(cset_off) - 1
+        if T < 0 or S < 0:
+            raise ValueError("topic_off and cset_off need at least one entry")
+        N = int(topic_off[-1])
+        if lag is not None and len(lag) != N:
+            raise ValueError("len(lag) != topic_off[-1]")
+        if partition is not None and len(partition) != N:
+            raise ValueError("len(partition) != topic_off[-1]")
+        if len(topic_cset) != T:
+            raise ValueError("len(topic_cset) != number of topics")
+        b = _Batch(T, _ptr(topic_off), _ptr(lag), _ptr(partition), _ptr(topic_cset), S,
+                   _ptr(cset_off), _ptr(cset_rank))
+        keep = (topic_off, lag, partition, topic_cset, cset_off, cset_rank)
+        sizes = cset_off[1:] - cset_off[:-1]
+        total_tc = int(sizes[topic_cset].sum()) if T > 0 else 0
+        return b, keep, (T, N, total_tc)
+
+    def upload(self, topic_off, lag, partition, topic_cset, cset_off, cset_rank):
+        b, keep, shape = self._batch(topic_off, lag, partition, topic_cset, cset_off, cset_rank)
+        self._check(self._L.lagassign_upload(self._ctx, ctypes.byref(b)))
+        self._shape = shape
+
+    def upload_offsets(self, topic_off, begin_offset, end_offset, committed, has_committed,
+                       reset_latest, partition, topic_cset, cset_off, cset_rank):
+        b, keep, shape = self._batch(topic_off, None, partition, topic_cset, cset_off, cset_rank)
+        bo = _arr(begin_offset, np.int64, "begin_offset")
+        eo = _arr(end_offset, np.int64, "end_offset")
+        co = _arr(committed, np.int64, "committed")
+        hc = _arr(has_committed, np.uint8, "has_committed")
+        for a in (bo, eo, co, hc):
+            if len(a) != shape[1]:
+                raise ValueError("offset arrays must have topic_off[-1] entries")
+        o = _Offsets(_ptr(bo), _ptr(eo), _ptr(co), _ptr(hc), 1 if reset_latest else 0)
+        self._check(self._L.lagassign_upload_offsets(self._ctx, ctypes.byref(b), ctypes.byref(o)))
+        self._shape = shape
+
+    def execute(self):
+        self._check(self._L.lagassign_execute(self._ctx))
+
+    def sync(self):
+        self._check(self._L.lagassign_sync(self._ctx))
+
+    def bind_device_outputs(self, d_out_partition: Optional[int], d_out_consumer_rank: Optional[int]):
+        self._check(self._L.lagassign_bind_device_outputs(
+            self._ctx, ctypes.c_void_p(d_out_partition), ctypes.c_void_p(d_out_consumer_rank)))
+
+    def download(self, out_partition=None, out_consumer_rank=None):
+        T, N, total_tc = self._shape
+        op = np.empty(N, np.int32) if out_partition is None else out_partition
+        oc = np.empty(N, np.int32) if out_consumer_rank is None else out_consumer_rank
+        ot = on = None
+        if self.want_totals:
+            ot = np.empty(total_tc, np.int64)
+            on = np.empty(total_tc, np.int32)
+        r = _Result(_ptr(op), _ptr(oc), _ptr(ot), _ptr(on))
+        self._check(self._L.lagassign_download(self._ctx, ctypes.byref(r)))
+        return dict(out_partition=op, out_consumer_rank=oc, out_total=ot, out_count=on)
+
+    def download_lags(self):
+        T, N, _ = self._shape
+        out = np.empty(N, np.int64)
+        self._check(self._L.lagassign_download_lags(self._ctx, _ptr(out)))
+        return out
+
+    def assign_batch(self, topic_off, lag, partition, topic_cset, cset_off, cset_rank,
+                     out_partition=None, out_consumer_rank=None):
+        """The whole hot path through lagassign_assign_batch() (host buffers in and out)."""
+        b, keep, shape = self._batch(topic_off, lag, partition, topic_cset, cset_off, cset_rank)
+        T, N, total_tc = shape
+        op = np.empty(N, np.int32) if out_partition is None else out_partition
+        oc = np.empty(N, np.int32) if out_consumer_rank is None else out_consumer_rank
+        ot = on = None
+        if self.want_totals:
+            ot = np.empty(total_tc, np.int64)
+            on = np.empty(total_tc, np.int32)
+        r = _Result(_ptr(op), _ptr(oc), _ptr(ot), _ptr(on))
+        self._check(self._L.lagassign_assign_batch(self._ctx, ctypes.byref(b), ctypes.byref(r)))
+        self._shape = shape
+        return dict(out_partition=op, out_consumer_rank=oc, out_total=ot, out_count=on)
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self._L.lagassign_get_stats(self._ctx, ctypes.byref(s)))
+        return s.as_dict()
+
+
+def device_count() -> int:
+    n = ctypes.c_int(0)
+    load_library().lagassign_device_count(ctypes.byref(n))
+    return n.value
+
+
+from .assignor import (LagBasedPartitionAssignor, TopicPartition, TopicPartitionLag,  # noqa: E402
+                       compute_partition_lag)

@@ -1,0 +1,155 @@
+"""Python view of the host mirror of the reference plugin class.
+
+``LagBasedPartitionAssignor`` here has the reference's surface for the assign()
+path (LagBasedPartitionAssignor.java): ``configure`` (Main:97-130), ``name``
+(Main:132-135), ``assign(partitionLagPerTopic, subscriptions)`` (Main:166-188) and
+``compute_partition_lag`` (Main:376-404). Every call goes through the C++ host
+mirror (``liblagassign_host.so``, include/lagassign_host.h), which flattens the
+maps, calls the CUDA library and unflattens the result. Nothing is computed in
+Python and there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from collections import namedtuple
+from typing import Dict, List, Mapping, Optional, Sequence
+
+import numpy as np
+
+TopicPartition = namedtuple("TopicPartition", ["topic", "partition"])
+TopicPartitionLag = namedtuple("TopicPartitionLag", ["topic", "partition", "lag"])   # Main:431-455
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_host = None
+
+
+def _load_host():
+    global _host
+    if _host is not None:
+        return _host
+    from . import LagAssignError, load_library
+    load_library()   # the CUDA library first: the host library links against it
+    path = os.path.join(_PKG_DIR, "liblagassign_host.so")
+    if not os.path.exists(path):
+        raise LagAssignError(-5, f"{path} is missing: build it with __graft_entry__.build()")
+    H = ctypes.CDLL(path)
+    vp, i64, i32, cp = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_char_p
+    H.lagassign_group_create.argtypes = [ctypes.POINTER(vp), i32]
+    H.lagassign_group_destroy.argtypes = [vp]
+    H.lagassign_group_destroy.restype = None
+    H.lagassign_group_last_error.argtypes = [vp]
+    H.lagassign_group_last_error.restype = cp
+    H.lagassign_group_configure.argtypes = [vp, ctypes.POINTER(cp), ctypes.POINTER(cp), i32]
+    H.lagassign_group_metadata_client_id.argtypes = [vp]
+    H.lagassign_group_metadata_client_id.restype = cp
+    H.lagassign_group_name.argtypes = [vp]
+    H.lagassign_group_name.restype = cp
+    H.lagassign_group_clear.argtypes = [vp]
+    H.lagassign_group_add_subscription.argtypes = [vp, cp, ctypes.POINTER(cp), i32]
+    H.lagassign_group_add_topic_lags.argtypes = [vp, cp, vp, vp, i64]
+    H.lagassign_group_assign.argtypes = [vp]
+    H.lagassign_group_result_size.argtypes = [vp, cp]
+    H.lagassign_group_result_size.restype = i64
+    H.lagassign_group_result_get.argtypes = [vp, cp, i64, ctypes.POINTER(cp), ctypes.POINTER(ctypes.c_int32)]
+    H.lagassign_group_topic_count.argtypes = [vp]
+    H.lagassign_group_topic_count.restype = i64
+    H.lagassign_group_topic_at.argtypes = [vp, i64]
+    H.lagassign_group_topic_at.restype = cp
+    H.lagassign_compute_partition_lag.argtypes = [i32, i64, i64, i64, cp]
+    H.lagassign_compute_partition_lag.restype = i64
+    _host = H
+    return H
+
+
+def _enc(s: str) -> bytes:
+    return s.encode("utf-8", "surrogatepass")
+
+
+def compute_partition_lag(committed: Optional[int], begin_offset: int, end_offset: int,
+                          auto_offset_reset_mode: str) -> int:
+    """computePartitionLag (Main:376-404); ``committed`` None = no committed offset."""
+    H = _load_host()
+    return int(H.lagassign_compute_partition_lag(0 if committed is None else 1,
+                                                 0 if committed is None else committed,
+                                                 begin_offset, end_offset, _enc(auto_offset_reset_mode)))
+
+
+class LagBasedPartitionAssignor:
+    """Host mirror of com.github.grantneale.kafka.LagBasedPartitionAssignor."""
+
+    def __init__(self, device: int = 0):
+        from . import LagAssignError
+        self._H = _load_host()
+        self._g = ctypes.c_void_p()
+        rc = self._H.lagassign_group_create(ctypes.byref(self._g), device)
+        if rc != 0:
+            raise LagAssignError(rc, self._H.lagassign_group_last_error(None).decode())
+        self.topic_order: List[str] = []
+
+    def close(self):
+        if getattr(self, "_g", None) is not None and self._g.value:
+            self._H.lagassign_group_destroy(self._g)
+            self._g = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            from . import LagAssignError
+            raise LagAssignError(rc, self._H.lagassign_group_last_error(self._g).decode())
+
+    # Configurable.configure, Main:97-130
+    def configure(self, configs: Mapping[str, object]) -> None:
+        keys = [_enc(str(k)) for k in configs]
+        vals = [_enc(str(v)) for v in configs.values()]
+        ka = (ctypes.c_char_p * len(keys))(*keys)
+        va = (ctypes.c_char_p * len(vals))(*vals)
+        rc = self._H.lagassign_group_configure(self._g, ka, va, len(keys))
+        if rc == -1:
+            # the reference throws IllegalArgumentException (Main:108-113)
+            raise ValueError(self._H.lagassign_group_last_error(self._g).decode())
+        self._check(rc)
+
+    @property
+    def metadata_client_id(self) -> str:
+        return self._H.lagassign_group_metadata_client_id(self._g).decode()
+
+    # ConsumerPartitionAssignor.name, Main:132-135
+    def name(self) -> str:
+        return self._H.lagassign_group_name(self._g).decode()
+
+    # static assign(Map, Map), Main:166-188
+    def assign(self, partition_lag_per_topic: Mapping[str, Sequence[TopicPartitionLag]],
+               subscriptions: Mapping[str, Sequence[str]]) -> Dict[str, List[TopicPartition]]:
+        H = self._H
+        self._check(H.lagassign_group_clear(self._g))
+        members = list(subscriptions.keys())            # iteration order of the caller's map
+        for m in members:
+            topics = [_enc(t) for t in subscriptions[m]]
+            ta = (ctypes.c_char_p * max(1, len(topics)))(*topics)
+            self._check(H.lagassign_group_add_subscription(self._g, _enc(m), ta, len(topics)))
+        for topic, entries in partition_lag_per_topic.items():
+            parts = np.array([e[1] for e in entries], dtype=np.int32)
+            lags = np.array([e[2] for e in entries], dtype=np.int64)
+            self._check(H.lagassign_group_add_topic_lags(
+                self._g, _enc(topic), parts.ctypes.data if len(parts) else None,
+                lags.ctypes.data if len(lags) else None, len(lags)))
+        self._check(H.lagassign_group_assign(self._g))
+        out: Dict[str, List[TopicPartition]] = {}
+        t = ctypes.c_char_p()
+        p = ctypes.c_int32()
+        for m in members:
+            n = H.lagassign_group_result_size(self._g, _enc(m))
+            lst = []
+            for i in range(max(0, n)):
+                self._check(H.lagassign_group_result_get(self._g, _enc(m), i, ctypes.byref(t), ctypes.byref(p)))
+                lst.append(TopicPartition(t.value.decode("utf-8", "surrogatepass"), int(p.value)))
+            out[m] = lst
+        self.topic_order = [H.lagassign_group_topic_at(self._g, i).decode("utf-8", "surrogatepass")
+                            for i in range(H.lagassign_group_topic_count(self._g))]
+        return out

@@ -1,0 +1,139 @@
+// fill.cuh — the greedy bin-fill of LagBasedPartitionAssignor.java:237-277 in its
+// round form.
+//
+// The reference picks, for every partition in sorted order, the consumer that is
+// minimal under (count asc, total asc, member id asc) (Main:240-263) and then adds
+// the partition's lag to its total and 1 to its count (Main:265-266). Because
+// the count criterion dominates, a consumer that just received a partition cannot
+// be chosen again before every other consumer has caught up: partitions are
+// consumed in ROUNDS of C, and inside a round the untouched consumers' totals do
+// not change, so the round's picks are simply the consumers in ascending
+// (total at round start, member id) order. One round = one C-wide sort + one
+// C-wide wrapping add; ceil(P/C) rounds are sequentially dependent.
+//
+// Consumers are (key = total ^ 0x8000..., pay = index in the consumer set); the
+// set is listed in member-id order so "smaller id" == "smaller pay".
+#pragma once
+#include "common.cuh"
+#include "sort_cta.cuh"
+#include "sort_warp.cuh"
+
+namespace lagassign {
+
+// One warp, C <= 32*EPTC consumers in registers (position j = lane*EPTC + r).
+//   lag_at(k)        -> int64 lag of the k-th partition in sorted order
+//   put(k, rank)     -> record that sorted partition k goes to global member `rank`
+//   cset             -> global ranks of the set's members (already offset)
+//   out_total/out_count (may be null): per-consumer results, indexed by set position
+template <int EPTC, class LagAt, class PutCons>
+__device__ __forceinline__ void warp_round_fill(int64_t P, int C, const int32_t* __restrict__ cset,
+                                                LagAt lag_at, PutCons put,
+                                                int64_t* out_total, int32_t* out_count) {
+    const unsigned lane = lane_id();
+    uint64_t tkey[EPTC];
+    uint32_t cid[EPTC];
+    int64_t lag_cur[EPTC];
+#pragma unroll
+    for (int r = 0; r < EPTC; ++r) {
+        int j = (int)lane * EPTC + r;
+        bool live = j < C;
+        tkey[r] = live ? TOTAL_KEY_MASK : KEY_SENTINEL;   // total 0  (Main:218)
+        cid[r] = live ? (uint32_t)j : PAY_SENTINEL;
+        lag_cur[r] = (live && j < P) ? lag_at((int64_t)j) : 0;
+    }
+    for (int64_t base = 0; base < P; base += C) {
+        // issue next round's loads before the dependent sort
+        int64_t lag_nxt[EPTC];
+#pragma unroll
+        for (int r = 0; r < EPTC; ++r) {
+            int j = (int)lane * EPTC + r;
+            int64_t k = base + C + j;
+            lag_nxt[r] = (j < C && k < P) ? lag_at(k) : 0;
+        }
+        if (base > 0) warp_bitonic_sort<EPTC>(tkey, cid);  // round 0: all totals 0, already in id order
+#pragma unroll
+        for (int r = 0; r < EPTC; ++r) {
+            int j = (int)lane * EPTC + r;
+            if (j < C && base + j < P) {
+                put(base + j, cset[cid[r]]);                                       // Main:264
+                tkey[r] = ((tkey[r] ^ TOTAL_KEY_MASK) + (uint64_t)lag_cur[r]) ^ TOTAL_KEY_MASK;  // Main:265, wraps
+            }
+            lag_cur[r] = lag_nxt[r];
+        }
+    }
+    if (out_total != nullptr) {
+        const int64_t full = P / C;
+        const int rem = (int)(P % C);
+#pragma unroll
+        for (int r = 0; r < EPTC; ++r) {
+            int j = (int)lane * EPTC + r;
+            if (j < C) {
+                out_total[cid[r]] = (int64_t)(tkey[r] ^ TOTAL_KEY_MASK);
+                out_count[cid[r]] = (int32_t)(full + (j < rem ? 1 : 0));           // Main:266
+            }
+        }
+    }
+}
+
+template <class LagAt, class PutCons>
+__device__ __forceinline__ void warp_round_fill_dispatch(int64_t P, int C, const int32_t* __restrict__ cset,
+                                                         LagAt lag_at, PutCons put,
+                                                         int64_t* out_total, int32_t* out_count) {
+    if (C <= 32) warp_round_fill<1>(P, C, cset, lag_at, put, out_total, out_count);
+    else if (C <= 64) warp_round_fill<2>(P, C, cset, lag_at, put, out_total, out_count);
+    else if (C <= 128) warp_round_fill<4>(P, C, cset, lag_at, put, out_total, out_count);
+    else warp_round_fill<8>(P, C, cset, lag_at, put, out_total, out_count);
+}
+
+// One CTA, 256 < C <= FILL_CTA_MAX_C consumers in shared memory (ckey/cidx hold
+// nc = pow2 >= C slots). MAXJ*blockDim.x must cover C. All threads call.
+template <int MAXJ, class LagAt, class PutCons>
+__device__ __forceinline__ void cta_round_fill(int64_t P, int C, int nc, const int32_t* __restrict__ cset,
+                                               uint64_t* ckey, uint32_t* cidx,
+                                               LagAt lag_at, PutCons put,
+                                               int64_t* out_total, int32_t* out_count) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int j = tid; j < nc; j += nt) {
+        bool live = j < C;
+        ckey[j] = live ? TOTAL_KEY_MASK : KEY_SENTINEL;
+        cidx[j] = live ? (uint32_t)j : PAY_SENTINEL;
+    }
+    int64_t lag_cur[MAXJ];
+#pragma unroll
+    for (int m = 0; m < MAXJ; ++m) {
+        int j = tid + m * nt;
+        lag_cur[m] = (j < C && j < P) ? lag_at((int64_t)j) : 0;
+    }
+    __syncthreads();
+    for (int64_t base = 0; base < P; base += C) {
+        int64_t lag_nxt[MAXJ];
+#pragma unroll
+        for (int m = 0; m < MAXJ; ++m) {
+            int j = tid + m * nt;
+            int64_t k = base + C + j;
+            lag_nxt[m] = (j < C && k < P) ? lag_at(k) : 0;
+        }
+        if (base > 0) cta_bitonic_sort(ckey, cidx, nc);
+#pragma unroll
+        for (int m = 0; m < MAXJ; ++m) {
+            int j = tid + m * nt;
+            if (j < C && base + j < P) {
+                put(base + j, cset[cidx[j]]);
+                ckey[j] = ((ckey[j] ^ TOTAL_KEY_MASK) + (uint64_t)lag_cur[m]) ^ TOTAL_KEY_MASK;
+            }
+            lag_cur[m] = lag_nxt[m];
+        }
+        // the next sort starts with a __syncthreads()
+    }
+    __syncthreads();
+    if (out_total != nullptr) {
+        const int64_t full = P / C;
+        const int rem = (int)(P % C);
+        for (int j = tid; j < C; j += nt) {
+            out_total[cidx[j]] = (int64_t)(ckey[j] ^ TOTAL_KEY_MASK);
+            out_count[cidx[j]] = (int32_t)(full + (j < rem ? 1 : 0));
+        }
+    }
+}
+
+}  // namespace lagassign

@@ -1,0 +1,71 @@
+// lag_based_partition_assignor.hpp — C++ host mirror of the reference plugin
+// class com.github.grantneale.kafka.LagBasedPartitionAssignor for the assign()
+// path: same names, same argument meaning, same error behaviour; the per-topic
+// arithmetic (LagBasedPartitionAssignor.java:204-277) runs on the GPU through the
+// C ABI of include/lagassign.h. There is no CPU implementation of it here.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+struct lagassign_ctx;
+
+namespace lagassign_host {
+
+struct TopicPartition {            // org.apache.kafka.common.TopicPartition
+    std::string topic;
+    int32_t partition;
+};
+
+struct TopicPartitionLag {         // Main:431-455
+    std::string topic;
+    int32_t partition;
+    int64_t lag;
+};
+
+// Map<String, List<String>> member -> topics, as its entries in ITERATION ORDER
+// (Main:168; the order matters through consumersPerTopic, Main:413).
+using Subscriptions = std::vector<std::pair<std::string, std::vector<std::string>>>;
+// Map<String, List<TopicPartitionLag>> (Main:167); only looked up by key (Main:182).
+using PartitionLagPerTopic = std::unordered_map<std::string, std::vector<TopicPartitionLag>>;
+// Map<String, List<TopicPartition>> member -> assignment (Main:171), in the
+// order of `subscriptions`.
+using Assignment = std::vector<std::pair<std::string, std::vector<TopicPartition>>>;
+
+class LagBasedPartitionAssignor {
+ public:
+    explicit LagBasedPartitionAssignor(int device = 0);
+    ~LagBasedPartitionAssignor();
+    LagBasedPartitionAssignor(const LagBasedPartitionAssignor&) = delete;
+    LagBasedPartitionAssignor& operator=(const LagBasedPartitionAssignor&) = delete;
+
+    // Configurable.configure (Main:97-130). Throws std::invalid_argument when
+    // group.id is missing (IllegalArgumentException at Main:108-113).
+    void configure(const std::map<std::string, std::string>& configs);
+    const std::map<std::string, std::string>& metadataConsumerProps() const { return metadata_props_; }
+
+    // ConsumerPartitionAssignor.name (Main:132-135).
+    std::string name() const { return "lag"; }
+
+    // static assign(Map, Map) (Main:166-188). Throws std::runtime_error when the
+    // GPU path fails (no fallback). `topicOrderOut`, if given, receives the
+    // topics in the order they were assigned.
+    Assignment assign(const PartitionLagPerTopic& partitionLagPerTopic, const Subscriptions& subscriptions,
+                      std::vector<std::string>* topicOrderOut = nullptr);
+
+    // static computePartitionLag (Main:376-404); committed == nullptr means no
+    // committed offset (partitionMetadata == null).
+    static int64_t computePartitionLag(const int64_t* committed, int64_t beginOffset, int64_t endOffset,
+                                       const std::string& autoOffsetResetMode);
+
+ private:
+    lagassign_ctx* ctx_ = nullptr;
+    int device_;
+    std::map<std::string, std::string> consumer_group_props_;
+    std::map<std::string, std::string> metadata_props_;
+};
+
+}  // namespace lagassign_host

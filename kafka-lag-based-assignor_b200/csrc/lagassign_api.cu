@@ -1,0 +1,587 @@
+// lagassign_api.cu — the C ABI of include/lagassign.h: context, planning (binning
+// topics by size on the host from the offsets array), transfers and kernel
+// launches. Replaces the call at LagBasedPartitionAssignor.java:149 (the static
+// assign(Map, Map) of :166-188). There is no CPU path in this file: every result
+// is produced by the kernels in kernels_small.cuh / radix.cuh.
+#include "../../include/lagassign.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_small.cuh"
+#include "radix.cuh"
+
+using namespace lagassign;
+
+namespace {
+
+thread_local std::string g_thread_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// elementwise computePartitionLag (LagBasedPartitionAssignor.java:376-404)
+__global__ void __launch_bounds__(256)
+k_compute_lag(int64_t n, const int64_t* __restrict__ begin_off, const int64_t* __restrict__ end_off,
+              const int64_t* __restrict__ committed, const uint8_t* __restrict__ has_committed,
+              int reset_latest, int64_t* __restrict__ lag) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t end = end_off[i];
+        int64_t next;
+        if (has_committed[i]) next = committed[i];            // Main:384-386
+        else next = reset_latest ? end : begin_off[i];        // Main:391-396
+        const int64_t d = (int64_t)((uint64_t)end - (uint64_t)next);   // Java long '-' wraps
+        lag[i] = d > 0 ? d : 0;                               // Main:402
+    }
+}
+
+}  // namespace
+
+struct lagassign_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    std::string err;
+    bool want_totals = false;
+
+    // plan of the uploaded batch
+    bool uploaded = false, executed = false, has_part = false, has_offsets = false;
+    int reset_latest = 0;
+    int64_t T = 0, N = 0, S = 0, R = 0, total_tc = 0, n_assigned = 0;
+    int n_warp = 0, n_cta = 0, n_none = 0, n_big = 0, n_tiles = 0, n_fill = 0;
+    int64_t big_elems = 0;
+
+    // inputs in HBM
+    DevBuf d_topic_off, d_lag, d_part, d_topic_cset, d_cset_off, d_cset_rank, d_tc_off;
+    DevBuf d_begin, d_end, d_committed, d_hascommitted;
+    // plan lists
+    DevBuf d_list_warp, d_list_cta, d_list_none, d_list_fill;
+    DevBuf d_bt_topic, d_bt_off, d_bt_P, d_bt_boff, d_bt_tile0, d_tile_bt;
+    // radix workspaces
+    DevBuf d_keyA, d_keyB, d_payA, d_payB, d_ghist, d_gbase, d_sel, d_need_tie, d_status, d_ticket;
+    // outputs
+    DevBuf d_out_part, d_out_cons, d_out_total, d_out_count;
+    int32_t* bound_part = nullptr;
+    int32_t* bound_cons = nullptr;
+
+    lagassign_stats stats{};
+};
+
+namespace {
+
+int fail(lagassign_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    g_thread_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return fail(ctx, _e == cudaErrorMemoryAllocation ? LAGASSIGN_ERR_OOM : LAGASSIGN_ERR_CUDA, \
+                        "%s failed: %s", #expr, cudaGetErrorString(_e));                      \
+    } while (0)
+
+template <class T>
+int upload_vec(lagassign_ctx* ctx, DevBuf& buf, const T* host, size_t n) {
+    CUDA_TRY(ctx, buf.ensure(std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(buf.p, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->stats.h2d_bytes += (int64_t)(n * sizeof(T));
+    }
+    return LAGASSIGN_OK;
+}
+
+#define TRY(expr) do { int _rc = (expr); if (_rc != LAGASSIGN_OK) return _rc; } while (0)
+
+int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
+                      std::vector<int32_t>& l_warp, std::vector<int32_t>& l_cta, std::vector<int32_t>& l_none,
+                      std::vector<int32_t>& bt_topic, std::vector<int64_t>& bt_off, std::vector<int64_t>& bt_P,
+                      std::vector<int64_t>& bt_boff, std::vector<int32_t>& bt_tile0, std::vector<int32_t>& tile_bt,
+                      std::vector<int32_t>& l_fill, std::vector<int64_t>& tc_off) {
+    if (!in) return fail(ctx, LAGASSIGN_ERR_ARG, "batch is NULL");
+    const int64_t T = in->n_topics, S = in->n_csets;
+    if (T < 0 || S < 0) return fail(ctx, LAGASSIGN_ERR_ARG, "negative n_topics / n_csets");
+    if (T > 0x7FFFFFFF) return fail(ctx, LAGASSIGN_ERR_UNSUPPORTED, "more than 2^31-1 topics");
+    if (!in->topic_off || !in->cset_off) return fail(ctx, LAGASSIGN_ERR_ARG, "topic_off / cset_off is NULL");
+    if (in->topic_off[0] != 0 || in->cset_off[0] != 0) return fail(ctx, LAGASSIGN_ERR_ARG, "offsets must start at 0");
+    for (int64_t s = 0; s < S; ++s) {
+        if (in->cset_off[s + 1] < in->cset_off[s]) return fail(ctx, LAGASSIGN_ERR_ARG, "cset_off not monotone at %lld", (long long)s);
+    }
+    const int64_t R = in->cset_off[S];
+    if (R > 0 && !in->cset_rank) return fail(ctx, LAGASSIGN_ERR_ARG, "cset_rank is NULL");
+    for (int64_t s = 0; s < S; ++s) {
+        for (int64_t j = in->cset_off[s]; j < in->cset_off[s + 1]; ++j) {
+            if (in->cset_rank[j] < 0) return fail(ctx, LAGASSIGN_ERR_ARG, "negative member rank in set %lld", (long long)s);
+            if (j > in->cset_off[s] && in->cset_rank[j] <= in->cset_rank[j - 1])
+                return fail(ctx, LAGASSIGN_ERR_ARG, "member ranks of set %lld are not strictly ascending", (long long)s);
+        }
+    }
+    for (int64_t t = 0; t < T; ++t) {
+        if (in->topic_off[t + 1] < in->topic_off[t]) return fail(ctx, LAGASSIGN_ERR_ARG, "topic_off not monotone at %lld", (long long)t);
+    }
+    const int64_t N = in->topic_off[T];
+    if (N > 0 && !in->lag) return fail(ctx, LAGASSIGN_ERR_ARG, "lag is NULL");
+    if (T > 0 && !in->topic_cset) return fail(ctx, LAGASSIGN_ERR_ARG, "topic_cset is NULL");
+
+    tc_off.assign((size_t)T + 1, 0);
+    int64_t boff = 0, tiles = 0, assigned = 0;
+    for (int64_t t = 0; t < T; ++t) {
+        const int32_t s = in->topic_cset[t];
+        if (s < 0 || s >= S) return fail(ctx, LAGASSIGN_ERR_ARG, "topic_cset[%lld] out of range", (long long)t);
+        const int64_t P = in->topic_off[t + 1] - in->topic_off[t];
+        const int64_t C = in->cset_off[s + 1] - in->cset_off[s];
+        tc_off[(size_t)t + 1] = tc_off[(size_t)t] + C;
+        if (P == 0) continue;
+        if (C == 0) { l_none.push_back((int32_t)t); continue; }
+        assigned += P;
+        if (P > C && C > FILL_CTA_MAX_C)
+            return fail(ctx, LAGASSIGN_ERR_UNSUPPORTED,
+                        "topic %lld: %lld partitions over %lld consumers needs multi-round fill with more than %d consumers",
+                        (long long)t, (long long)P, (long long)C, FILL_CTA_MAX_C);
+        if (P <= WARP_MAX_P) l_warp.push_back((int32_t)t);
+        else if (P <= CTA_MAX_P) l_cta.push_back((int32_t)t);
+        else {
+            if (P >= (int64_t)ST_VAL) return fail(ctx, LAGASSIGN_ERR_UNSUPPORTED, "topic %lld has 2^30 or more partitions", (long long)t);
+            const int64_t nt = (P + RT_TILE - 1) / RT_TILE;
+            if (tiles + nt > 0x7FFFFFFF) return fail(ctx, LAGASSIGN_ERR_UNSUPPORTED, "too many radix tiles");
+            const int32_t b = (int32_t)bt_topic.size();
+            bt_topic.push_back((int32_t)t);
+            bt_off.push_back(in->topic_off[t]);
+            bt_P.push_back(P);
+            bt_boff.push_back(boff);
+            bt_tile0.push_back((int32_t)tiles);
+            for (int64_t k = 0; k < nt; ++k) tile_bt.push_back(b);
+            if (P > C) l_fill.push_back(b);
+            boff += P;
+            tiles += nt;
+        }
+    }
+    ctx->T = T; ctx->N = N; ctx->S = S; ctx->R = R;
+    ctx->total_tc = tc_off[(size_t)T];
+    ctx->n_assigned = assigned;
+    ctx->big_elems = boff;
+    return LAGASSIGN_OK;
+}
+
+DevBatch make_dev_batch(lagassign_ctx* ctx) {
+    DevBatch b{};
+    b.topic_off = ctx->d_topic_off.as<int64_t>();
+    b.lag = ctx->d_lag.as<int64_t>();
+    b.part = ctx->has_part ? ctx->d_part.as<int32_t>() : nullptr;
+    b.topic_cset = ctx->d_topic_cset.as<int32_t>();
+    b.cset_off = ctx->d_cset_off.as<int64_t>();
+    b.cset_rank = ctx->d_cset_rank.as<int32_t>();
+    b.tc_off = ctx->d_tc_off.as<int64_t>();
+    b.out_part = ctx->bound_part ? ctx->bound_part : ctx->d_out_part.as<int32_t>();
+    b.out_cons = ctx->bound_cons ? ctx->bound_cons : ctx->d_out_cons.as<int32_t>();
+    b.out_total = ctx->want_totals ? ctx->d_out_total.as<int64_t>() : nullptr;
+    b.out_count = ctx->want_totals ? ctx->d_out_count.as<int32_t>() : nullptr;
+    return b;
+}
+
+BigTopics make_big(lagassign_ctx* ctx) {
+    BigTopics bt{};
+    bt.n_big = ctx->n_big;
+    bt.n_tiles = ctx->n_tiles;
+    bt.topic = ctx->d_bt_topic.as<int32_t>();
+    bt.off = ctx->d_bt_off.as<int64_t>();
+    bt.P = ctx->d_bt_P.as<int64_t>();
+    bt.boff = ctx->d_bt_boff.as<int64_t>();
+    bt.tile0 = ctx->d_bt_tile0.as<int32_t>();
+    bt.tile_bt = ctx->d_tile_bt.as<int32_t>();
+    bt.keyA = ctx->d_keyA.as<uint64_t>(); bt.keyB = ctx->d_keyB.as<uint64_t>();
+    bt.payA = ctx->d_payA.as<uint32_t>(); bt.payB = ctx->d_payB.as<uint32_t>();
+    bt.ghist = ctx->d_ghist.as<uint32_t>();
+    bt.gbase = ctx->d_gbase.as<uint32_t>();
+    int8_t* sel = ctx->d_sel.as<int8_t>();
+    bt.sel_src = sel;
+    bt.sel_dst = sel + (size_t)ctx->n_big * N_PASS;
+    bt.sel_final = sel + (size_t)ctx->n_big * N_PASS * 2;
+    bt.need_tie = ctx->d_need_tie.as<int32_t>();
+    bt.status = ctx->d_status.as<uint32_t>();
+    bt.ticket = ctx->d_ticket.as<uint32_t>();
+    bt.passes_run = reinterpret_cast<int32_t*>(ctx->d_ticket.as<uint32_t>() + N_PASS);
+    return bt;
+}
+
+int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_offsets* offs) {
+    if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
+    ctx->uploaded = ctx->executed = false;
+    ctx->stats = lagassign_stats{};
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<int32_t> l_warp, l_cta, l_none, bt_topic, bt_tile0, tile_bt, l_fill;
+    std::vector<int64_t> bt_off, bt_P, bt_boff, tc_off;
+    lagassign_batch tmp;
+    if (offs) {
+        // lags are produced on the device; planning only needs the shapes
+        if (!offs->begin_offset || !offs->end_offset || !offs->committed || !offs->has_committed)
+            return fail(ctx, LAGASSIGN_ERR_ARG, "offset arrays must not be NULL");
+        tmp = *in;
+        static const int64_t dummy = 0;
+        tmp.lag = &dummy;   // not dereferenced by the planner
+        in = &tmp;
+    }
+    TRY(validate_and_plan(ctx, in, l_warp, l_cta, l_none, bt_topic, bt_off, bt_P, bt_boff, bt_tile0, tile_bt, l_fill, tc_off));
+    const int64_t T = ctx->T, N = ctx->N;
+    ctx->has_part = in->partition != nullptr;
+    ctx->has_offsets = offs != nullptr;
+    ctx->n_warp = (int)l_warp.size(); ctx->n_cta = (int)l_cta.size(); ctx->n_none = (int)l_none.size();
+    ctx->n_big = (int)bt_topic.size(); ctx->n_tiles = (int)tile_bt.size(); ctx->n_fill = (int)l_fill.size();
+
+    TRY(upload_vec(ctx, ctx->d_topic_off, in->topic_off, (size_t)T + 1));
+    if (offs) {
+        ctx->reset_latest = offs->reset_latest ? 1 : 0;
+        TRY(upload_vec(ctx, ctx->d_begin, offs->begin_offset, (size_t)N));
+        TRY(upload_vec(ctx, ctx->d_end, offs->end_offset, (size_t)N));
+        TRY(upload_vec(ctx, ctx->d_committed, offs->committed, (size_t)N));
+        TRY(upload_vec(ctx, ctx->d_hascommitted, offs->has_committed, (size_t)N));
+        CUDA_TRY(ctx, ctx->d_lag.ensure(std::max<size_t>((size_t)N, 1) * sizeof(int64_t)));
+    } else {
+        TRY(upload_vec(ctx, ctx->d_lag, in->lag, (size_t)N));
+    }
+    if (ctx->has_part) TRY(upload_vec(ctx, ctx->d_part, in->partition, (size_t)N));
+    TRY(upload_vec(ctx, ctx->d_topic_cset, in->topic_cset, (size_t)T));
+    TRY(upload_vec(ctx, ctx->d_cset_off, in->cset_off, (size_t)ctx->S + 1));
+    TRY(upload_vec(ctx, ctx->d_cset_rank, in->cset_rank, (size_t)ctx->R));
+    TRY(upload_vec(ctx, ctx->d_tc_off, tc_off.data(), tc_off.size()));
+    TRY(upload_vec(ctx, ctx->d_list_warp, l_warp.data(), l_warp.size()));
+    TRY(upload_vec(ctx, ctx->d_list_cta, l_cta.data(), l_cta.size()));
+    TRY(upload_vec(ctx, ctx->d_list_none, l_none.data(), l_none.size()));
+    TRY(upload_vec(ctx, ctx->d_list_fill, l_fill.data(), l_fill.size()));
+    TRY(upload_vec(ctx, ctx->d_bt_topic, bt_topic.data(), bt_topic.size()));
+    TRY(upload_vec(ctx, ctx->d_bt_off, bt_off.data(), bt_off.size()));
+    TRY(upload_vec(ctx, ctx->d_bt_P, bt_P.data(), bt_P.size()));
+    TRY(upload_vec(ctx, ctx->d_bt_boff, bt_boff.data(), bt_boff.size()));
+    TRY(upload_vec(ctx, ctx->d_bt_tile0, bt_tile0.data(), bt_tile0.size()));
+    TRY(upload_vec(ctx, ctx->d_tile_bt, tile_bt.data(), tile_bt.size()));
+
+    // outputs and workspaces
+    CUDA_TRY(ctx, ctx->d_out_part.ensure(std::max<size_t>((size_t)N, 1) * sizeof(int32_t)));
+    CUDA_TRY(ctx, ctx->d_out_cons.ensure(std::max<size_t>((size_t)N, 1) * sizeof(int32_t)));
+    if (ctx->want_totals) {
+        CUDA_TRY(ctx, ctx->d_out_total.ensure(std::max<size_t>((size_t)ctx->total_tc, 1) * sizeof(int64_t)));
+        CUDA_TRY(ctx, ctx->d_out_count.ensure(std::max<size_t>((size_t)ctx->total_tc, 1) * sizeof(int32_t)));
+    }
+    if (ctx->n_big > 0) {
+        const size_t nb = (size_t)ctx->big_elems;
+        CUDA_TRY(ctx, ctx->d_keyA.ensure(nb * sizeof(uint64_t)));
+        CUDA_TRY(ctx, ctx->d_keyB.ensure(nb * sizeof(uint64_t)));
+        CUDA_TRY(ctx, ctx->d_payA.ensure(nb * sizeof(uint32_t)));
+        CUDA_TRY(ctx, ctx->d_payB.ensure(nb * sizeof(uint32_t)));
+        const size_t hb = (size_t)ctx->n_big * N_PASS * 256 * sizeof(uint32_t);
+        CUDA_TRY(ctx, ctx->d_ghist.ensure(hb));
+        CUDA_TRY(ctx, ctx->d_gbase.ensure(hb));
+        CUDA_TRY(ctx, ctx->d_sel.ensure((size_t)ctx->n_big * (2 * N_PASS + 1)));
+        CUDA_TRY(ctx, ctx->d_need_tie.ensure((size_t)ctx->n_big * sizeof(int32_t)));
+        CUDA_TRY(ctx, ctx->d_status.ensure((size_t)N_PASS * ctx->n_tiles * 256 * sizeof(uint32_t)));
+        CUDA_TRY(ctx, ctx->d_ticket.ensure((N_PASS + 1) * sizeof(uint32_t)));
+    }
+    // the host vectors above must outlive the copies; also honours "the library
+    // copies what it needs before returning"
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.n_partitions = N;
+    ctx->stats.n_assigned = ctx->n_assigned;
+    ctx->stats.topics_warp = ctx->n_warp;
+    ctx->stats.topics_cta = ctx->n_cta;
+    ctx->stats.topics_device = ctx->n_big;
+    ctx->stats.topics_unassigned = ctx->n_none;
+    ctx->stats.device_sort_elems = ctx->big_elems;
+    ctx->uploaded = true;
+    return LAGASSIGN_OK;
+}
+
+int configure_kernels(lagassign_ctx* ctx) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_cta_topics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CtaSmemLayout::total));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_big_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_big_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_big_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILL_CTA_MAX_C * 12)));
+    return LAGASSIGN_OK;
+}
+
+int create_common(lagassign_ctx** out, int device, void* stream, bool own) {
+    if (!out) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx out-pointer is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, LAGASSIGN_ERR_NO_DEVICE,
+                    "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return fail(nullptr, LAGASSIGN_ERR_ARG, "device %d out of range [0,%d)", device, n);
+    lagassign_ctx* ctx = new (std::nothrow) lagassign_ctx();
+    if (!ctx) return fail(nullptr, LAGASSIGN_ERR_OOM, "out of host memory");
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return fail(nullptr, LAGASSIGN_ERR_CUDA, "cudaSetDevice(%d) failed", device); }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return fail(nullptr, LAGASSIGN_ERR_CUDA, "cudaGetDeviceProperties failed"); }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (own) {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return fail(nullptr, LAGASSIGN_ERR_CUDA, "cudaStreamCreate failed"); }
+        ctx->own_stream = true;
+    } else {
+        ctx->stream = reinterpret_cast<cudaStream_t>(stream);
+    }
+    int rc = configure_kernels(ctx);
+    if (rc != LAGASSIGN_OK) { std::string m = ctx->err; lagassign_destroy(ctx); return fail(nullptr, rc, "%s", m.c_str()); }
+    *out = ctx;
+    return LAGASSIGN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lagassign_abi_version(void) { return LAGASSIGN_ABI_VERSION; }
+
+int lagassign_device_count(int* n_devices) {
+    if (!n_devices) return fail(nullptr, LAGASSIGN_ERR_ARG, "n_devices is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *n_devices = n;
+    return LAGASSIGN_OK;
+}
+
+int lagassign_create(lagassign_ctx** ctx, int device) { return create_common(ctx, device, nullptr, true); }
+
+int lagassign_create_on_stream(lagassign_ctx** ctx, int device, void* cuda_stream) {
+    return create_common(ctx, device, cuda_stream, false);
+}
+
+void lagassign_destroy(lagassign_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->d_topic_off, &ctx->d_lag, &ctx->d_part, &ctx->d_topic_cset, &ctx->d_cset_off,
+                      &ctx->d_cset_rank, &ctx->d_tc_off, &ctx->d_begin, &ctx->d_end, &ctx->d_committed,
+                      &ctx->d_hascommitted, &ctx->d_list_warp, &ctx->d_list_cta, &ctx->d_list_none,
+                      &ctx->d_list_fill, &ctx->d_bt_topic, &ctx->d_bt_off, &ctx->d_bt_P, &ctx->d_bt_boff,
+                      &ctx->d_bt_tile0, &ctx->d_tile_bt, &ctx->d_keyA, &ctx->d_keyB, &ctx->d_payA,
+                      &ctx->d_payB, &ctx->d_ghist, &ctx->d_gbase, &ctx->d_sel, &ctx->d_need_tie,
+                      &ctx->d_status, &ctx->d_ticket, &ctx->d_out_part, &ctx->d_out_cons,
+                      &ctx->d_out_total, &ctx->d_out_count};
+    for (DevBuf* b : bufs) b->release();
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* lagassign_last_error(const lagassign_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_thread_error.c_str();
+}
+
+int lagassign_set_option(lagassign_ctx* ctx, int option, int64_t value) {
+    if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
+    switch (option) {
+        case LAGASSIGN_OPT_TOTALS:
+            ctx->want_totals = value != 0;
+            ctx->uploaded = false;   // output buffers are sized at upload
+            return LAGASSIGN_OK;
+        default:
+            return fail(ctx, LAGASSIGN_ERR_ARG, "unknown option %d", option);
+    }
+}
+
+int lagassign_upload(lagassign_ctx* ctx, const lagassign_batch* in) { return do_upload(ctx, in, nullptr); }
+
+int lagassign_upload_offsets(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_offsets* offs) {
+    if (!offs) return fail(ctx, LAGASSIGN_ERR_ARG, "offsets is NULL");
+    return do_upload(ctx, in, offs);
+}
+
+int lagassign_execute(lagassign_ctx* ctx) {
+    if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
+    if (!ctx->uploaded) return fail(ctx, LAGASSIGN_ERR_STATE, "execute() before a successful upload()");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int launches = 0;
+    DevBatch b = make_dev_batch(ctx);
+    const int sms = ctx->sm_count;
+
+    if (ctx->has_offsets && ctx->N > 0) {
+        int grid = (int)std::min<int64_t>((ctx->N + 255) / 256, (int64_t)sms * 16);
+        k_compute_lag<<<grid, 256, 0, st>>>(ctx->N, ctx->d_begin.as<int64_t>(), ctx->d_end.as<int64_t>(),
+                                            ctx->d_committed.as<int64_t>(), ctx->d_hascommitted.as<uint8_t>(),
+                                            ctx->reset_latest, ctx->d_lag.as<int64_t>());
+        ++launches;
+    }
+    if (ctx->want_totals && ctx->total_tc > 0) {
+        CUDA_TRY(ctx, cudaMemsetAsync(b.out_total, 0, (size_t)ctx->total_tc * sizeof(int64_t), st));
+        CUDA_TRY(ctx, cudaMemsetAsync(b.out_count, 0, (size_t)ctx->total_tc * sizeof(int32_t), st));
+    }
+    if (ctx->n_none > 0) {
+        dim3 grid(8, (unsigned)std::min(ctx->n_none, 65535));
+        k_unassigned_topics<<<grid, 256, 0, st>>>(b, ctx->d_list_none.as<int32_t>(), ctx->n_none);
+        ++launches;
+    }
+    if (ctx->n_warp > 0) {
+        int grid = (ctx->n_warp + SMALL_WARPS - 1) / SMALL_WARPS;
+        k_warp_topics<<<grid, SMALL_WARPS * 32, 0, st>>>(b, ctx->d_list_warp.as<int32_t>(), ctx->n_warp);
+        ++launches;
+    }
+    if (ctx->n_cta > 0) {
+        int grid = std::min(ctx->n_cta, sms * 2);
+        k_cta_topics<<<grid, CTA_THREADS, CtaSmemLayout::total, st>>>(b, ctx->d_list_cta.as<int32_t>(), ctx->n_cta);
+        ++launches;
+    }
+    if (ctx->n_big > 0) {
+        BigTopics bt = make_big(ctx);
+        const size_t hb = (size_t)ctx->n_big * N_PASS * 256 * sizeof(uint32_t);
+        CUDA_TRY(ctx, cudaMemsetAsync(bt.ghist, 0, hb, st));
+        CUDA_TRY(ctx, cudaMemsetAsync(bt.need_tie, 0, (size_t)ctx->n_big * sizeof(int32_t), st));
+        CUDA_TRY(ctx, cudaMemsetAsync(bt.status, 0, (size_t)N_PASS * ctx->n_tiles * 256 * sizeof(uint32_t), st));
+        CUDA_TRY(ctx, cudaMemsetAsync(bt.ticket, 0, (N_PASS + 1) * sizeof(uint32_t), st));
+        const int G = ctx->n_tiles;
+        const int first_pass = ctx->has_part ? 0 : N_TIE_PASS;
+        if (ctx->has_part) {
+            k_big_order_check<<<std::min(G, sms * 8), 256, 0, st>>>(bt, b.part);
+            ++launches;
+            k_big_hist<true><<<std::min(G, sms * 2), RT_THREADS, 0, st>>>(bt, b.lag, b.part);
+        } else {
+            k_big_hist<false><<<std::min(G, sms * 2), RT_THREADS, 0, st>>>(bt, b.lag, nullptr);
+        }
+        ++launches;
+        k_big_scan<<<ctx->n_big, 256, 0, st>>>(bt, first_pass);
+        ++launches;
+        const int pass_grid = std::min(G, sms * 2);
+        for (int p = first_pass; p < N_PASS; ++p) {
+            if (ctx->has_part) k_big_pass<true><<<pass_grid, RT_THREADS, sizeof(PassSmem), st>>>(bt, p, b.lag, b.part);
+            else k_big_pass<false><<<pass_grid, RT_THREADS, sizeof(PassSmem), st>>>(bt, p, b.lag, nullptr);
+            ++launches;
+        }
+        k_big_finalize<<<std::min(G, sms * 8), 256, 0, st>>>(bt, b.lag, b.part, b.topic_cset, b.cset_off, b.cset_rank,
+                                                            b.tc_off, b.out_part, b.out_cons, b.out_total, b.out_count);
+        ++launches;
+        if (ctx->n_fill > 0) {
+            k_big_fill<<<std::min(ctx->n_fill, sms), BIGFILL_THREADS, FILL_CTA_MAX_C * 12, st>>>(
+                bt, ctx->d_list_fill.as<int32_t>(), ctx->n_fill, b.lag, b.topic_cset, b.cset_off, b.cset_rank,
+                b.tc_off, b.out_cons, b.out_total, b.out_count);
+            ++launches;
+        }
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches = launches;
+    ctx->executed = true;
+    return LAGASSIGN_OK;
+}
+
+int lagassign_sync(lagassign_ctx* ctx) {
+    if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return LAGASSIGN_OK;
+}
+
+int lagassign_download(lagassign_ctx* ctx, const lagassign_result* out) {
+    if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
+    if (!out) return fail(ctx, LAGASSIGN_ERR_ARG, "result is NULL");
+    if (!ctx->executed) return fail(ctx, LAGASSIGN_ERR_STATE, "download() before execute()");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t N = (size_t)ctx->N;
+    ctx->stats.d2h_bytes = 0;
+    const int32_t* src_part = ctx->bound_part ? ctx->bound_part : ctx->d_out_part.as<int32_t>();
+    const int32_t* src_cons = ctx->bound_cons ? ctx->bound_cons : ctx->d_out_cons.as<int32_t>();
+    if (N && out->out_partition) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(out->out_partition, src_part, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += (int64_t)N * 4;
+    }
+    if (N && out->out_consumer_rank) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(out->out_consumer_rank, src_cons, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += (int64_t)N * 4;
+    }
+    if ((out->out_total || out->out_count) && !ctx->want_totals)
+        return fail(ctx, LAGASSIGN_ERR_STATE, "out_total/out_count requested but LAGASSIGN_OPT_TOTALS was not enabled before upload()");
+    const size_t TC = (size_t)ctx->total_tc;
+    if (TC && out->out_total) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(out->out_total, ctx->d_out_total.p, TC * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += (int64_t)TC * 8;
+    }
+    if (TC && out->out_count) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(out->out_count, ctx->d_out_count.p, TC * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += (int64_t)TC * 4;
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->n_big > 0) {
+        int32_t pr = 0;
+        CUDA_TRY(ctx, cudaMemcpy(&pr, ctx->d_ticket.as<uint32_t>() + N_PASS, sizeof pr, cudaMemcpyDeviceToHost));
+        ctx->stats.radix_passes_run = pr;
+    }
+    return LAGASSIGN_OK;
+}
+
+int lagassign_assign_batch(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_result* out) {
+    TRY(lagassign_upload(ctx, in));
+    TRY(lagassign_execute(ctx));
+    return lagassign_download(ctx, out);
+}
+
+int lagassign_bind_device_outputs(lagassign_ctx* ctx, int32_t* d_out_partition, int32_t* d_out_consumer_rank) {
+    if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
+    if ((d_out_partition == nullptr) != (d_out_consumer_rank == nullptr))
+        return fail(ctx, LAGASSIGN_ERR_ARG, "bind both device outputs or neither");
+    ctx->bound_part = d_out_partition;
+    ctx->bound_cons = d_out_consumer_rank;
+    return LAGASSIGN_OK;
+}
+
+int lagassign_download_lags(lagassign_ctx* ctx, int64_t* lag_out) {
+    if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
+    if (!lag_out) return fail(ctx, LAGASSIGN_ERR_ARG, "lag_out is NULL");
+    if (!ctx->executed) return fail(ctx, LAGASSIGN_ERR_STATE, "download_lags() before execute()");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (ctx->N) CUDA_TRY(ctx, cudaMemcpyAsync(lag_out, ctx->d_lag.p, (size_t)ctx->N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return LAGASSIGN_OK;
+}
+
+int lagassign_get_stats(const lagassign_ctx* ctx, lagassign_stats* stats) {
+    if (!ctx || !stats) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx or stats is NULL");
+    *stats = ctx->stats;
+    return LAGASSIGN_OK;
+}
+
+int lagassign_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(nullptr, LAGASSIGN_ERR_ARG, "ptr is NULL");
+    *ptr = nullptr;
+    cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, LAGASSIGN_ERR_OOM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
+    return LAGASSIGN_OK;
+}
+
+int lagassign_host_free(void* ptr) {
+    if (!ptr) return LAGASSIGN_OK;
+    cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, LAGASSIGN_ERR_CUDA, "cudaFreeHost failed: %s", cudaGetErrorString(e)); }
+    return LAGASSIGN_OK;
+}
+
+}  // extern "C"

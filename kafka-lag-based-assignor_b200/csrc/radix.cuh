@@ -1,0 +1,402 @@
+// radix.cuh — device-wide path for topics too large for one CTA (P > 4096):
+// a segmented, stable, least-significant-digit radix sort (8-bit digits, 64-bit
+// key + 32-bit payload) in the "onesweep" style — one histogram kernel for all
+// digit positions, then one pass per digit whose tiles obtain their global
+// offsets by decoupled look-back over the previous tiles OF THE SAME TOPIC —
+// followed by the finalize / round-fill kernels.
+//
+// Segmentation: a tile never straddles topics, histograms and look-back chains
+// are per topic, and scatter destinations stay inside the topic's own range, so
+// any number of large topics share one sequence of launches with no topic digit.
+//
+// Pass skipping is decided on the device per (topic, pass): if one digit value
+// holds all P elements of a topic the pass cannot reorder anything and its tiles
+// return at once; the per-topic source/destination buffer choice follows. With
+// all-zero lags (BASELINE config 5) every pass is skipped and the sorted order is
+// the input order, as the reference's stable sort gives (Main:228-235).
+//
+// Pass order (LSD): 4 passes over the partition id (only when the ids are given
+// and not already ascending inside the topic: they are the tie-break, Main:231),
+// then 8 passes over key = lag ^ 0x7FFF...F (descending signed lag, Main:234).
+#pragma once
+#include "common.cuh"
+#include "fill.cuh"
+
+namespace lagassign {
+
+constexpr int RT_THREADS = 512;
+constexpr int RT_IPT = 8;
+constexpr int RT_TILE = RT_THREADS * RT_IPT;   // 4096 elements per tile
+constexpr int RT_WARPS = RT_THREADS / 32;
+constexpr int N_TIE_PASS = 4;
+constexpr int N_LAG_PASS = 8;
+constexpr int N_PASS = N_TIE_PASS + N_LAG_PASS;
+
+constexpr uint32_t ST_AGG = 1u << 30;   // tile's own count is published
+constexpr uint32_t ST_INC = 2u << 30;   // inclusive prefix over the topic's tiles so far
+constexpr uint32_t ST_VAL = (1u << 30) - 1;
+
+enum : int { SEL_RAW = 0, SEL_A = 1, SEL_B = 2, SEL_SKIP = -1 };
+
+struct BigTopics {
+    int n_big;                 // B
+    int n_tiles;               // G
+    const int32_t* topic;      // [B] topic id
+    const int64_t* off;        // [B] offset in the caller's arrays (= topic_off[t])
+    const int64_t* P;          // [B]
+    const int64_t* boff;       // [B] offset in the compact sort buffers
+    const int32_t* tile0;      // [B] first tile of the topic
+    const int32_t* tile_bt;    // [G] tile -> b
+    uint64_t* keyA; uint64_t* keyB;   // [sum P]
+    uint32_t* payA; uint32_t* payB;
+    uint32_t* ghist;           // [B][N_PASS][256] digit counts
+    uint32_t* gbase;           // [B][N_PASS][256] exclusive prefix of ghist
+    int8_t* sel_src;           // [B][N_PASS]  SEL_* (SEL_SKIP = pass skipped for this topic)
+    int8_t* sel_dst;           // [B][N_PASS]
+    int8_t* sel_final;         // [B] where the sorted data of the topic ended up
+    int32_t* need_tie;         // [B] partition ids not ascending
+    uint32_t* status;          // [N_PASS][G][256] look-back words (zeroed per execute)
+    uint32_t* ticket;          // [N_PASS] dynamic tile ids (zeroed per execute)
+    int32_t* passes_run;       // [1] max over topics of executed passes (stat)
+};
+
+__device__ __forceinline__ uint32_t digit_of(uint64_t key, int lag_pass) {
+    return (uint32_t)(key >> (8 * lag_pass)) & 0xFFu;
+}
+
+// ---- 1. are the partition ids ascending inside each large topic? -----------------------
+__global__ void __launch_bounds__(256)
+k_big_order_check(BigTopics bt, const int32_t* __restrict__ part) {
+    for (int g = blockIdx.x; g < bt.n_tiles; g += gridDim.x) {
+        const int b = bt.tile_bt[g];
+        const int64_t P = bt.P[b];
+        const int64_t t0 = (int64_t)(g - bt.tile0[b]) * RT_TILE;
+        const int32_t* p = part + bt.off[b];
+        int bad = 0;
+        for (int i = threadIdx.x; i < RT_TILE; i += blockDim.x) {
+            int64_t e = t0 + i;
+            if (e + 1 < P) bad |= p[e] > p[e + 1];
+        }
+        if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(&bt.need_tie[b], 1);
+    }
+}
+
+// ---- 2. digit histograms of every pass, per topic -------------------------------------
+template <bool HAS_PART>
+__global__ void __launch_bounds__(RT_THREADS)
+k_big_hist(BigTopics bt, const int64_t* __restrict__ lag, const int32_t* __restrict__ part) {
+    __shared__ uint32_t h[N_PASS][256];
+    for (int i = threadIdx.x; i < N_PASS * 256; i += blockDim.x) (&h[0][0])[i] = 0;
+    __syncthreads();
+    // contiguous range of tiles per CTA so the shared histogram is flushed rarely
+    const int per = (bt.n_tiles + gridDim.x - 1) / gridDim.x;
+    const int g0 = blockIdx.x * per, g1 = min(bt.n_tiles, g0 + per);
+    int cur_b = -1;
+    auto flush = [&](int b) {
+        __syncthreads();
+        if (b >= 0) {
+            uint32_t* gh = bt.ghist + (size_t)b * N_PASS * 256;
+            for (int i = threadIdx.x; i < N_PASS * 256; i += blockDim.x) {
+                uint32_t v = (&h[0][0])[i];
+                if (v) { atomicAdd(gh + i, v); (&h[0][0])[i] = 0; }
+            }
+        }
+        __syncthreads();
+    };
+    for (int g = g0; g < g1; ++g) {
+        const int b = bt.tile_bt[g];
+        if (b != cur_b) { flush(cur_b); cur_b = b; }
+        const int64_t P = bt.P[b];
+        const int64_t t0 = (int64_t)(g - bt.tile0[b]) * RT_TILE;
+        const int64_t* lg = lag + bt.off[b];
+        const bool tie = HAS_PART && bt.need_tie[b] != 0;
+#pragma unroll 4
+        for (int k = 0; k < RT_IPT; ++k) {
+            int64_t e = t0 + k * RT_THREADS + threadIdx.x;
+            if (e < P) {
+                uint64_t key = (uint64_t)ld_stream(lg + e) ^ LAG_KEY_MASK;
+#pragma unroll
+                for (int d = 0; d < N_LAG_PASS; ++d) atomicAdd(&h[N_TIE_PASS + d][digit_of(key, d)], 1u);
+                if (tie) {
+                    uint32_t pk = (uint32_t)part[bt.off[b] + e] ^ 0x80000000u;
+#pragma unroll
+                    for (int d = 0; d < N_TIE_PASS; ++d) atomicAdd(&h[d][(pk >> (8 * d)) & 0xFFu], 1u);
+                }
+            }
+        }
+    }
+    flush(cur_b);
+}
+
+// ---- 3. per topic: prefix sums, skip decisions, buffer ping-pong ------------------------
+__global__ void __launch_bounds__(256)
+k_big_scan(BigTopics bt, int first_pass) {
+    __shared__ uint32_t wsum[8];
+    __shared__ int s_cur, s_run;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t P = bt.P[b];
+    if (tid == 0) { s_cur = SEL_RAW; s_run = 0; }
+    __syncthreads();
+    for (int p = 0; p < N_PASS; ++p) {
+        const size_t base = ((size_t)b * N_PASS + p) * 256;
+        uint32_t c = bt.ghist[base + tid];
+        bool off = p < first_pass || (p < N_TIE_PASS && bt.need_tie[b] == 0);
+        int constant = __syncthreads_or((int64_t)c == P);
+        // exclusive scan over the 256 digit values
+        uint32_t x = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        uint32_t add = 0;
+        for (int w = 0; w < warp; ++w) add += wsum[w];
+        bt.gbase[base + tid] = x - c + add;
+        if (tid == 0) {
+            if (off || constant) {
+                bt.sel_src[b * N_PASS + p] = SEL_SKIP;
+                bt.sel_dst[b * N_PASS + p] = SEL_SKIP;
+            } else {
+                int dst = (s_cur == SEL_A) ? SEL_B : SEL_A;
+                bt.sel_src[b * N_PASS + p] = (int8_t)s_cur;
+                bt.sel_dst[b * N_PASS + p] = (int8_t)dst;
+                s_cur = dst;
+                s_run += 1;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        bt.sel_final[b] = (int8_t)s_cur;
+        atomicMax(bt.passes_run, s_run);
+    }
+}
+
+// ---- 4. one digit pass ------------------------------------------------------------------
+struct PassSmem {
+    uint64_t key[RT_TILE];
+    uint32_t pay[RT_TILE];
+    uint32_t whist[RT_WARPS][256];   // per-warp digit counts, then exclusive offsets over warps
+    uint32_t tile_excl[256];         // exclusive scan of the tile's digit counts
+    int64_t dst_base[256];           // global index of the tile's first element of each digit, minus tile_excl
+    uint32_t wsum[8];
+    int tile;
+};
+
+template <bool HAS_PART>
+__global__ void __launch_bounds__(RT_THREADS)
+k_big_pass(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int32_t* __restrict__ part) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PassSmem& sm = *reinterpret_cast<PassSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t* status = bt.status + (size_t)pass * bt.n_tiles * 256;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sm.tile = (int)atomicAdd(&bt.ticket[pass], 1u);
+        __syncthreads();
+        const int g = sm.tile;
+        if (g >= bt.n_tiles) return;
+        const int b = bt.tile_bt[g];
+        const int src = bt.sel_src[b * N_PASS + pass];
+        if (src == SEL_SKIP) continue;           // nothing to reorder for this topic in this pass
+        const int dst = bt.sel_dst[b * N_PASS + pass];
+        const int64_t P = bt.P[b];
+        const int tile_in_topic = g - bt.tile0[b];
+        const int64_t t0 = (int64_t)tile_in_topic * RT_TILE;
+        const int n_valid = (int)min((int64_t)RT_TILE, P - t0);
+        const int64_t boff = bt.boff[b];
+        const uint64_t* skey = (src == SEL_A) ? bt.keyA + boff : bt.keyB + boff;
+        const uint32_t* spay = (src == SEL_A) ? bt.payA + boff : bt.payB + boff;
+        uint64_t* dkey = (dst == SEL_A) ? bt.keyA + boff : bt.keyB + boff;
+        uint32_t* dpay = (dst == SEL_A) ? bt.payA + boff : bt.payB + boff;
+        const int64_t* lg = lag + bt.off[b];
+        const int32_t* pt = HAS_PART ? part + bt.off[b] : nullptr;
+
+        for (int i = tid; i < RT_WARPS * 256; i += RT_THREADS) (&sm.whist[0][0])[i] = 0;
+
+        // load: each warp owns 32*IPT consecutive elements, item k of lane l is
+        // element warp*256 + k*32 + l (coalesced, and in memory order k-major)
+        uint64_t key[RT_IPT];
+        uint32_t pay[RT_IPT];
+        uint32_t dig[RT_IPT];
+#pragma unroll
+        for (int k = 0; k < RT_IPT; ++k) {
+            const int i = warp * (32 * RT_IPT) + k * 32 + lane;
+            const int64_t e = t0 + i;
+            if (i < n_valid) {
+                if (src == SEL_RAW) { key[k] = (uint64_t)ld_stream(lg + e) ^ LAG_KEY_MASK; pay[k] = (uint32_t)e; }
+                else { key[k] = skey[e]; pay[k] = spay[e]; }
+                if (HAS_PART && pass < N_TIE_PASS)
+                    dig[k] = (((uint32_t)pt[pay[k]] ^ 0x80000000u) >> (8 * pass)) & 0xFFu;
+                else
+                    dig[k] = digit_of(key[k], pass - N_TIE_PASS);
+            } else {
+                key[k] = KEY_SENTINEL; pay[k] = PAY_SENTINEL; dig[k] = 255u;  // sorts behind every valid element
+            }
+        }
+        __syncthreads();
+
+        // rank inside the warp: elements with equal digit keep memory order
+        uint32_t rank[RT_IPT];
+#pragma unroll
+        for (int k = 0; k < RT_IPT; ++k) {
+            const unsigned peers = __match_any_sync(0xffffffffu, dig[k]);
+            const uint32_t pre = sm.whist[warp][dig[k]];
+            __syncwarp();
+            if ((peers & ((1u << lane) - 1u)) == 0) sm.whist[warp][dig[k]] = pre + __popc(peers);
+            __syncwarp();
+            rank[k] = pre + __popc(peers & ((1u << lane) - 1u));
+        }
+        __syncthreads();
+
+        // per digit: exclusive offsets over warps, tile count, look-back
+        uint32_t cnt = 0;
+        if (tid < 256) {
+#pragma unroll
+            for (int w = 0; w < RT_WARPS; ++w) {
+                uint32_t v = sm.whist[w][tid];
+                sm.whist[w][tid] = cnt;
+                cnt += v;
+            }
+            uint32_t valid_cnt = cnt;
+            if (tid == 255) valid_cnt -= (uint32_t)(RT_TILE - n_valid);   // padding is not data
+            // publish this tile's count right away so later tiles can proceed
+            uint32_t* st = status + (size_t)g * 256 + tid;
+            if (tile_in_topic == 0) {
+                __stcg(st, ST_INC | valid_cnt);
+            } else {
+                __stcg(st, ST_AGG | valid_cnt);
+            }
+            // exclusive scan of cnt over digits (tile-local positions; padding included, it is last)
+            uint32_t x = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x += y;
+            }
+            if (lane == 31) sm.wsum[warp] = x;
+            // (barrier below, inside the tid<256 region all 8 warps are complete warps)
+            asm volatile("bar.sync 1, 256;");
+            uint32_t add = 0;
+            for (int w = 0; w < warp; ++w) add += sm.wsum[w];
+            const uint32_t excl = x - cnt + add;
+            sm.tile_excl[tid] = excl;
+
+            // decoupled look-back over the earlier tiles of this topic
+            uint32_t prefix = 0;
+            if (tile_in_topic > 0) {
+                int look = g - 1;
+                for (;;) {
+                    uint32_t v;
+                    do { v = __ldcg(status + (size_t)look * 256 + tid); } while ((v >> 30) == 0);
+                    prefix += v & ST_VAL;
+                    if ((v >> 30) == 2u) break;
+                    --look;
+                }
+                __stcg(st, ST_INC | (prefix + valid_cnt));
+            }
+            const uint32_t gb = bt.gbase[((size_t)b * N_PASS + pass) * 256 + tid];
+            sm.dst_base[tid] = (int64_t)gb + (int64_t)prefix - (int64_t)excl;
+        }
+        __syncthreads();
+
+        // scatter inside the tile (shared memory), then out in digit runs (coalesced)
+#pragma unroll
+        for (int k = 0; k < RT_IPT; ++k) {
+            const uint32_t pos = sm.tile_excl[dig[k]] + sm.whist[warp][dig[k]] + rank[k];
+            sm.key[pos] = key[k];
+            sm.pay[pos] = pay[k];
+        }
+        __syncthreads();
+        for (int i = tid; i < n_valid; i += RT_THREADS) {
+            const uint64_t kk = sm.key[i];
+            const uint32_t pp = sm.pay[i];
+            uint32_t d;
+            if (HAS_PART && pass < N_TIE_PASS) d = (((uint32_t)pt[pp] ^ 0x80000000u) >> (8 * pass)) & 0xFFu;
+            else d = digit_of(kk, pass - N_TIE_PASS);
+            const int64_t o = sm.dst_base[d] + i;
+            dkey[o] = kk;
+            dpay[o] = pp;
+        }
+    }
+}
+
+// ---- 5. finalize: out_partition (and out_consumer for single-round topics) ---------------
+__global__ void __launch_bounds__(256)
+k_big_finalize(BigTopics bt, const int64_t* __restrict__ lag, const int32_t* __restrict__ part,
+               const int32_t* __restrict__ topic_cset, const int64_t* __restrict__ cset_off,
+               const int32_t* __restrict__ cset_rank, const int64_t* __restrict__ tc_off,
+               int32_t* __restrict__ out_part, int32_t* __restrict__ out_cons,
+               int64_t* __restrict__ out_total, int32_t* __restrict__ out_count) {
+    for (int g = blockIdx.x; g < bt.n_tiles; g += gridDim.x) {
+        const int b = bt.tile_bt[g];
+        const int t = bt.topic[b];
+        const int64_t P = bt.P[b], off = bt.off[b], boff = bt.boff[b];
+        const int sel = bt.sel_final[b];
+        const uint64_t* fkey = (sel == SEL_A) ? bt.keyA + boff : bt.keyB + boff;
+        const uint32_t* fpay = (sel == SEL_A) ? bt.payA + boff : bt.payB + boff;
+        const int s = topic_cset[t];
+        const int64_t coff = cset_off[s], C = cset_off[s + 1] - coff;
+        const bool single_round = P <= C;
+        const int64_t t0 = (int64_t)(g - bt.tile0[b]) * RT_TILE;
+        for (int i = threadIdx.x; i < RT_TILE; i += blockDim.x) {
+            const int64_t e = t0 + i;
+            if (e >= P) break;
+            const uint32_t pay = (sel == SEL_RAW) ? (uint32_t)e : fpay[e];
+            out_part[off + e] = part ? part[off + pay] : (int32_t)pay;
+            if (single_round) {
+                out_cons[off + e] = cset_rank[coff + e];
+                if (out_total) {
+                    int64_t lg = (sel == SEL_RAW) ? lag[off + e] : (int64_t)(fkey[e] ^ LAG_KEY_MASK);
+                    out_total[tc_off[t] + e] = lg;
+                    out_count[tc_off[t] + e] = 1;
+                }
+            }
+        }
+    }
+}
+
+// ---- 6. round fill of a large topic: one CTA per topic -----------------------------------
+constexpr int BIGFILL_THREADS = 1024;
+constexpr int BIGFILL_MAXJ = FILL_CTA_MAX_C / BIGFILL_THREADS;
+
+__global__ void __launch_bounds__(BIGFILL_THREADS)
+k_big_fill(BigTopics bt, const int32_t* __restrict__ fill_list, int n_fill,
+           const int64_t* __restrict__ lag,
+           const int32_t* __restrict__ topic_cset, const int64_t* __restrict__ cset_off,
+           const int32_t* __restrict__ cset_rank, const int64_t* __restrict__ tc_off,
+           int32_t* __restrict__ out_cons, int64_t* __restrict__ out_total, int32_t* __restrict__ out_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* ckey = reinterpret_cast<uint64_t*>(smem_raw);
+    uint32_t* cidx = reinterpret_cast<uint32_t*>(smem_raw + sizeof(uint64_t) * FILL_CTA_MAX_C);
+    for (int li = blockIdx.x; li < n_fill; li += gridDim.x) {
+        const int b = fill_list[li];
+        const int t = bt.topic[b];
+        const int64_t P = bt.P[b], off = bt.off[b], boff = bt.boff[b];
+        const int sel = bt.sel_final[b];
+        const uint64_t* fkey = (sel == SEL_A) ? bt.keyA + boff : bt.keyB + boff;
+        const int64_t* lg = lag + off;
+        const int s = topic_cset[t];
+        const int64_t coff = cset_off[s];
+        const int C = (int)(cset_off[s + 1] - coff);
+        const int32_t* __restrict__ cset = cset_rank + coff;
+        int64_t* tot = out_total ? out_total + tc_off[t] : nullptr;
+        int32_t* cnt = out_count ? out_count + tc_off[t] : nullptr;
+        auto lag_at = [&](int64_t k) -> int64_t {
+            return (sel == SEL_RAW) ? __ldg(lg + k) : (int64_t)(__ldg(fkey + k) ^ LAG_KEY_MASK);
+        };
+        auto put = [&](int64_t k, int32_t rank) { out_cons[off + k] = rank; };
+        if (C <= FILL_WARP_MAX_C) {
+            if (threadIdx.x < 32) warp_round_fill_dispatch(P, C, cset, lag_at, put, tot, cnt);
+        } else {
+            cta_round_fill<BIGFILL_MAXJ>(P, C, max(64, 1 << (32 - __clz(C - 1))), cset, ckey, cidx,
+                                         lag_at, put, tot, cnt);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace lagassign

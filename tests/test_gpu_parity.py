@@ -1,0 +1,321 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle: bit-exact.
+
+Layout of this file follows the reference's own test class
+(LagBasedPartitionAssignorTest.java): first its vectors through the plugin-shaped
+host mirror, then generated cases per kernel bin, then BASELINE-shaped configs.
+"""
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import args_of, baseline_config, random_flat, uniform_batch
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("out_partition", "out_consumer_rank", "out_total", "out_count")
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__
+    __graft_entry__.build()
+    import kafka_lag_based_assignor_b200 as p
+    return p
+
+
+@pytest.fixture(scope="module")
+def flat(pkg):
+    with pkg.FlatAssignor(0, want_totals=True) as f:
+        yield f
+
+
+def check(flat, batch, mode=oracle.ROUNDS, threads=8):
+    got = flat.assign_batch(*args_of(batch))
+    exp = oracle.assign_batch(*args_of(batch), mode=mode, want_totals=True, threads=threads)
+    for k in KEYS:
+        if not np.array_equal(got[k], exp[k]):
+            bad = np.nonzero(got[k] != exp[k])[0]
+            raise AssertionError(f"{k}: {len(bad)} mismatches, first at {bad[:5]}: "
+                                 f"got {got[k][bad[:5]]} expected {exp[k][bad[:5]]}; stats={flat.stats()}")
+    return got
+
+
+# ---- the reference's own vectors, written like its tests -----------------------------------
+
+def _tpl(pkg, topic, lags, parts=None):
+    parts = range(len(lags)) if parts is None else parts
+    return [pkg.TopicPartitionLag(topic, p, l) for p, l in zip(parts, lags)]
+
+
+def test_assign_reference_vector(pkg):
+    """LagBasedPartitionAssignorTest.testAssign (Test:82-132), list order included."""
+    partition_lag_per_topic = {
+        "topic1": _tpl(pkg, "topic1", [100000, 100000, 500, 1]),
+        "topic2": _tpl(pkg, "topic2", [900000, 100000]),
+    }
+    subscriptions = {"consumer-1": ["topic1", "topic2"], "consumer-2": ["topic1"]}
+    expected = {
+        "consumer-1": [("topic1", 0), ("topic1", 2), ("topic2", 0), ("topic2", 1)],
+        "consumer-2": [("topic1", 1), ("topic1", 3)],
+    }
+    actual = pkg.LagBasedPartitionAssignor().assign(partition_lag_per_topic, subscriptions)
+    assert actual == expected
+
+
+def test_assign_readme_example(pkg):
+    """README.md:42-57 / Main:57-69."""
+    a = pkg.LagBasedPartitionAssignor()
+    actual = a.assign({"t0": _tpl(pkg, "t0", [100000, 50000, 60000])}, {"C0": ["t0"], "C1": ["t0"]})
+    assert {m: sorted(v) for m, v in actual.items()} == {"C0": [("t0", 0)], "C1": [("t0", 1), ("t0", 2)]}
+    assert actual["C1"] == [("t0", 2), ("t0", 1)]     # assignment order is lag-descending
+
+
+def test_assign_with_zero_lags(pkg):
+    """testAssignWithZeroLags (Test:134-175): max <= min + 1."""
+    actual = pkg.LagBasedPartitionAssignor().assign(
+        {"topic1": _tpl(pkg, "topic1", [0] * 7)},
+        {"consumer-1": ["topic1"], "consumer-2": ["topic1"]})
+    sizes = [len(v) for v in actual.values()]
+    assert max(sizes) <= min(sizes) + 1 and sum(sizes) == 7
+
+
+def test_assign_with_heavily_skewed_lags(pkg):
+    """testAssignWithHeavilySkewedLags (Test:177-228)."""
+    actual = pkg.LagBasedPartitionAssignor().assign(
+        {"topic1": _tpl(pkg, "topic1", [360, 359, 230, 118, 444, 122, 65, 111, 455000, 424000])},
+        {"consumer-1": ["topic1"], "consumer-2": ["topic1"], "consumer-3": ["topic1"]})
+    sizes = [len(v) for v in actual.values()]
+    assert max(sizes) <= min(sizes) + 1 and sum(sizes) == 10
+
+
+def test_golden_files_through_host_mirror(pkg, golden_dir):
+    a = pkg.LagBasedPartitionAssignor()
+    kats = json.load(open(os.path.join(golden_dir, "reference_kats.json")))["assign"]
+    reg = json.load(open(os.path.join(golden_dir, "oracle_regression.json")))["cases"]
+    for case in kats + reg:
+        lags = {t: [pkg.TopicPartitionLag(*e) for e in v] for t, v in case["partition_lag_per_topic"].items()}
+        subs = {m: ts for m, ts in case["subscriptions"]}
+        got = a.assign(lags, subs)
+        exp = {m: [tuple(tp) for tp in v] for m, v in case["expected"].items()}
+        if case.get("order_sensitive", True):
+            assert got == exp, case["name"]
+        else:
+            assert {m: sorted(v) for m, v in got.items()} == {m: sorted(v) for m, v in exp.items()}, case["name"]
+
+
+# ---- generated cases per kernel bin ----------------------------------------------------------
+
+LAG_KINDS = ["u40", "full", "dups", "zero", "neg", "bigpos"]
+
+
+@pytest.mark.parametrize("lag_kind", LAG_KINDS)
+@pytest.mark.parametrize("ids", [None, "sorted", "shuffled", "dups"])
+def test_warp_bin(flat, lag_kind, ids):
+    """P <= 256: one warp per topic; consumer sets from empty to larger than P."""
+    rng = np.random.default_rng(zlib.crc32(repr((lag_kind, ids)).encode()))
+    for C in (1, 2, 5, 31, 32, 33, 100, 255, 256, 300):
+        b = random_flat(rng, T=60, pmin=0, pmax=256, C=C, lag_kind=lag_kind, explicit_ids=ids, n_sets=4)
+        check(flat, b, mode=oracle.LITERAL)
+
+
+def test_warp_bin_every_size(flat):
+    rng = np.random.default_rng(11)
+    sizes = np.arange(0, 258)
+    sizes = sizes[sizes <= 256]
+    topic_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    for C in (3, 64, 256):
+        b = dict(topic_off=topic_off, lag=rng.integers(0, 50, size=int(topic_off[-1]), dtype=np.int64),
+                 partition=None, topic_cset=np.zeros(len(sizes), np.int32),
+                 cset_off=np.array([0, C], np.int64), cset_rank=np.arange(C, dtype=np.int32) * 2 + 1)
+        check(flat, b, mode=oracle.LITERAL)
+
+
+@pytest.mark.parametrize("lag_kind", ["u40", "full", "dups", "zero"])
+@pytest.mark.parametrize("ids", [None, "shuffled", "dups"])
+def test_cta_bin(flat, lag_kind, ids):
+    """256 < P <= 4096: one CTA per topic; warp-level and CTA-level round fill."""
+    rng = np.random.default_rng(zlib.crc32(repr(("cta", lag_kind, ids)).encode()))
+    for C in (1, 7, 200, 256, 257, 1000, 4000, 5000):
+        b = random_flat(rng, T=12, pmin=257, pmax=4096, C=C, lag_kind=lag_kind, explicit_ids=ids,
+                        n_sets=3, full_sets=(C >= 257))
+        check(flat, b)
+
+
+@pytest.mark.parametrize("lag_kind", ["u40", "full", "dups", "zero", "small"])
+@pytest.mark.parametrize("ids", [None, "sorted", "shuffled", "dups"])
+def test_device_bin(flat, lag_kind, ids):
+    """P > 4096: segmented radix sort + finalize / round fill."""
+    rng = np.random.default_rng(zlib.crc32(repr(("dev", lag_kind, ids)).encode()))
+    for C, pmax in ((3, 9000), (300, 30000), (1024, 70000), (8192, 20000), (50000, 40000)):
+        b = random_flat(rng, T=5, pmin=4097, pmax=pmax, C=C, lag_kind=lag_kind, explicit_ids=ids,
+                        n_sets=2, full_sets=True)
+        got = check(flat, b)
+        st = flat.stats()
+        assert st["topics_device"] == 5
+        if lag_kind == "zero" and ids in (None, "sorted"):
+            assert st["radix_passes_run"] == 0      # every digit constant: nothing moves
+        if lag_kind == "small" and ids is None:
+            assert st["radix_passes_run"] <= 3      # lags < 2^20: upper five digits constant
+        assert got is not None
+
+
+def test_mixed_bins_and_edge_topics(flat):
+    """All bins in one batch, empty topics, empty consumer sets, repeated execute()."""
+    rng = np.random.default_rng(5)
+    sizes = np.array([0, 1, 2, 31, 32, 33, 255, 256, 257, 511, 4095, 4096, 4097, 8192, 8193, 12289, 0, 100, 5000])
+    topic_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    N = int(topic_off[-1])
+    sets = [np.zeros(0, np.int32), np.array([4], np.int32), np.arange(0, 40, 2, dtype=np.int32),
+            np.arange(600, dtype=np.int32), np.arange(6000, dtype=np.int32)]
+    cset_off = np.concatenate([[0], np.cumsum([len(s) for s in sets])]).astype(np.int64)
+    b = dict(topic_off=topic_off, lag=rng.integers(-5, 1 << 33, size=N, dtype=np.int64),
+             partition=rng.permutation(N).astype(np.int32),
+             topic_cset=(np.arange(len(sizes)) % len(sets)).astype(np.int32),
+             cset_off=cset_off, cset_rank=np.concatenate(sets).astype(np.int32))
+    first = check(flat, b)
+    # execute() twice on the same upload gives the same answer
+    flat.upload(*args_of(b))
+    flat.execute()
+    flat.execute()
+    again = flat.download()
+    for k in KEYS:
+        assert np.array_equal(first[k], again[k]), k
+    st = flat.stats()
+    assert st["topics_unassigned"] > 0 and st["topics_warp"] > 0 and st["topics_cta"] > 0 and st["topics_device"] > 0
+    assert st["kernel_launches"] > 0
+
+
+def test_single_consumer_and_single_partition(flat):
+    rng = np.random.default_rng(9)
+    for P, C in ((1, 1), (1, 5000), (257, 1), (5000, 1), (70000, 1), (70000, 2)):
+        lag = rng.integers(0, 1000, size=P, dtype=np.int64)
+        check(flat, uniform_batch(1, P, C, lag))
+
+
+def test_wraparound_totals(flat):
+    """Totals wrap like Java long (Main:265) and the wrapped value drives later picks."""
+    big = (1 << 63) - 1
+    for P, C in ((64, 3), (1000, 7), (6000, 300), (20000, 1024)):
+        rng = np.random.default_rng(P)
+        lag = rng.integers(big // 2, big, size=P, dtype=np.int64)
+        check(flat, uniform_batch(1, P, C, lag))
+
+
+def test_argument_errors(pkg):
+    with pkg.FlatAssignor(0) as f:
+        with pytest.raises(pkg.LagAssignError) as e:   # ranks of a set must ascend
+            f.assign_batch([0, 2], [1, 2], None, [0], [0, 2], [3, 3])
+        assert e.value.code == -1
+        with pytest.raises(pkg.LagAssignError) as e:   # topic_cset out of range
+            f.assign_batch([0, 2], [1, 2], None, [4], [0, 2], [0, 1])
+        assert e.value.code == -1
+        with pytest.raises(pkg.LagAssignError) as e:   # offsets not monotone
+            f.assign_batch([0, 2, 1], [1, 2], None, [0, 0], [0, 2], [0, 1])
+        assert e.value.code == -1
+        with pytest.raises(pkg.LagAssignError) as e:   # execute before upload
+            f.execute()
+        assert e.value.code == -4
+        # more consumers than the multi-round fill covers -> explicit error, no fallback
+        P, C = 10000, 9000
+        with pytest.raises(pkg.LagAssignError) as e:
+            f.assign_batch([0, P], np.zeros(P, np.int64), None, [0], [0, C], np.arange(C, dtype=np.int32))
+        assert e.value.code == -6
+
+
+def test_fused_lag_computation(pkg):
+    """upload_offsets(): computePartitionLag (Main:376-404) on the device, then assign."""
+    rng = np.random.default_rng(21)
+    b = random_flat(rng, T=40, pmin=0, pmax=6000, C=50, lag_kind="u40", n_sets=2)
+    N = len(b["lag"])
+    end = rng.integers(0, 1 << 40, size=N, dtype=np.int64)
+    begin = (end * rng.random(N)).astype(np.int64)
+    committed = rng.integers(0, 1 << 40, size=N, dtype=np.int64)   # sometimes beyond end -> clamp
+    has = (rng.random(N) < 0.7).astype(np.uint8)
+    for latest in (0, 1):
+        exp_lag = np.array([oracle.compute_partition_lag(int(committed[i]) if has[i] else None, int(begin[i]),
+                                                         int(end[i]), "latest" if latest else "earliest")
+                            for i in range(N)], dtype=np.int64)
+        with pkg.FlatAssignor(0) as f:
+            f.upload_offsets(b["topic_off"], begin, end, committed, has, latest, None,
+                             b["topic_cset"], b["cset_off"], b["cset_rank"])
+            f.execute()
+            got = f.download()
+            assert np.array_equal(f.download_lags(), exp_lag)
+        exp = oracle.assign_batch(b["topic_off"], exp_lag, None, b["topic_cset"], b["cset_off"], b["cset_rank"])
+        assert np.array_equal(got["out_partition"], exp["out_partition"])
+        assert np.array_equal(got["out_consumer_rank"], exp["out_consumer_rank"])
+
+
+# ---- BASELINE.json configs --------------------------------------------------------------------
+
+def test_config1_readme(flat):
+    b, _ = baseline_config(1)
+    got = check(flat, b, mode=oracle.LITERAL)
+    assert got["out_partition"].tolist() == [0, 2, 1] and got["out_consumer_rank"].tolist() == [0, 1, 1]
+    assert got["out_total"].tolist() == [100000, 110000]      # README.md:54-57
+
+
+def test_config2_full(flat):
+    """1 topic x 2^20 partitions, 1024 consumers: 1024 dependent rounds; totals wrap."""
+    b, _ = baseline_config(2)
+    got = check(flat, b)
+    assert flat.stats()["radix_passes_run"] == 8
+    assert (got["out_count"] == 1024).all()
+
+
+def test_config3_full(flat):
+    b, _ = baseline_config(3)
+    check(flat, b)
+
+
+def test_config4_scaled(flat):
+    b, _ = baseline_config(4, scale=0.05)
+    check(flat, b)
+
+
+def test_config5_scaled_vs_oracle(flat):
+    b, _ = baseline_config(5, scale=0.02)
+    check(flat, b)
+
+
+def test_config4_full_properties(pkg):
+    """Full size: 100 000 topics x 256. Size-independent properties (P < C: one
+    partial round): every topic's out_partition is a permutation of 0..255 whose
+    lags are non-increasing with ties by partition id; sorted partition k goes to
+    member rank k; plus a sampled comparison with the oracle."""
+    b, _ = baseline_config(4)
+    with pkg.FlatAssignor(0) as f:
+        got = f.assign_batch(*args_of(b))
+    T, P = 100000, 256
+    part = got["out_partition"].reshape(T, P)
+    cons = got["out_consumer_rank"].reshape(T, P)
+    assert (np.sort(part, axis=1) == np.arange(P, dtype=np.int32)).all()
+    assert (cons == np.arange(P, dtype=np.int32)).all()
+    lag = b["lag"].reshape(T, P)
+    sl = np.take_along_axis(lag, part.astype(np.int64), axis=1)
+    d = np.diff(sl, axis=1)
+    assert (d <= 0).all()
+    assert (np.diff(part, axis=1)[d == 0] > 0).all()
+    lo, hi = 5000, 5600
+    exp = oracle.assign_batch(*args_of(b), topic_lo=lo, topic_hi=hi)
+    assert np.array_equal(exp["out_partition"][lo * P:hi * P], got["out_partition"][lo * P:hi * P])
+    assert np.array_equal(exp["out_consumer_rank"][lo * P:hi * P], got["out_consumer_rank"][lo * P:hi * P])
+
+
+def test_config5_full_closed_form(pkg):
+    """All-zero lag: the sort is the identity and partition i goes to member i mod C
+     — a self-checking config at full size."""
+    b, _ = baseline_config(5)
+    with pkg.FlatAssignor(0) as f:
+        got = f.assign_batch(*args_of(b))
+        st = f.stats()
+    off = b["topic_off"]
+    N = int(off[-1])
+    local = np.arange(N, dtype=np.int64) - np.repeat(off[:-1], np.diff(off))
+    assert np.array_equal(got["out_partition"], local.astype(np.int32))
+    assert np.array_equal(got["out_consumer_rank"], (local % 1024).astype(np.int32))
+    assert st["radix_passes_run"] == 0 and st["topics_device"] > 0
