@@ -215,7 +215,9 @@ class FlatAssignor:
                    _ptr(cset_off), _ptr(cset_rank))
         keep = (topic_off, lag, partition, topic_cset, cset_off, cset_rank)
         sizes = cset_off[1:] - cset_off[:-1]
-        total_tc = int(sizes[topic_cset].sum()) if T > 0 else 0
+        # invalid set ids are reported by the library's own validation, not here
+        ok = T > 0 and S > 0 and topic_cset.min() >= 0 and topic_cset.max() < S
+        total_tc = int(sizes[topic_cset].sum()) if ok else 0
         return b, keep, (T, N, total_tc)
 
     def upload(self, topic_off, lag, partition, topic_cset, cset_off, cset_rank):

@@ -60,6 +60,19 @@ struct BigTopics {
     int32_t* passes_run;       // [1] max over topics of executed passes (stat)
 };
 
+// Look-back status words are polled by other CTAs while they are being written:
+// the accesses must be real memory operations every time (never hoisted, merged
+// or speculated by the compiler), at gpu scope. Flag and value share one 32-bit
+// word, so relaxed ordering is sufficient.
+__device__ __forceinline__ uint32_t ld_status(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ uint32_t digit_of(uint64_t key, int lag_pass) {
     return (uint32_t)(key >> (8 * lag_pass)) & 0xFFu;
 }
@@ -265,11 +278,7 @@ k_big_pass(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int32_
             if (tid == 255) valid_cnt -= (uint32_t)(RT_TILE - n_valid);   // padding is not data
             // publish this tile's count right away so later tiles can proceed
             uint32_t* st = status + (size_t)g * 256 + tid;
-            if (tile_in_topic == 0) {
-                __stcg(st, ST_INC | valid_cnt);
-            } else {
-                __stcg(st, ST_AGG | valid_cnt);
-            }
+            st_status(st, (tile_in_topic == 0 ? ST_INC : ST_AGG) | valid_cnt);
             // exclusive scan of cnt over digits (tile-local positions; padding included, it is last)
             uint32_t x = cnt;
 #pragma unroll
@@ -289,14 +298,16 @@ k_big_pass(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int32_
             uint32_t prefix = 0;
             if (tile_in_topic > 0) {
                 int look = g - 1;
+                const int first = g - tile_in_topic;
                 for (;;) {
-                    uint32_t v;
-                    do { v = __ldcg(status + (size_t)look * 256 + tid); } while ((v >> 30) == 0);
+                    const uint32_t v = ld_status(status + (size_t)look * 256 + tid);
+                    const uint32_t state = v >> 30;
+                    if (state == 0) continue;            // predecessor has not published yet
                     prefix += v & ST_VAL;
-                    if ((v >> 30) == 2u) break;
+                    if (state == 2u || look == first) break;
                     --look;
                 }
-                __stcg(st, ST_INC | (prefix + valid_cnt));
+                st_status(st, ST_INC | (prefix + valid_cnt));
             }
             const uint32_t gb = bt.gbase[((size_t)b * N_PASS + pass) * 256 + tid];
             sm.dst_base[tid] = (int64_t)gb + (int64_t)prefix - (int64_t)excl;

@@ -214,7 +214,7 @@ def test_argument_errors(pkg):
             f.assign_batch([0, 2], [1, 2], None, [4], [0, 2], [0, 1])
         assert e.value.code == -1
         with pytest.raises(pkg.LagAssignError) as e:   # offsets not monotone
-            f.assign_batch([0, 2, 1], [1, 2], None, [0, 0], [0, 2], [0, 1])
+            f.assign_batch([0, 2, 1], [1], None, [0, 0], [0, 2], [0, 1])
         assert e.value.code == -1
         with pytest.raises(pkg.LagAssignError) as e:   # execute before upload
             f.execute()
