@@ -125,7 +125,8 @@ typedef struct lagassign_stats {
     int64_t d2h_bytes;           /* bytes copied device->host by the last download() */
 } lagassign_stats;
 
-#define LAGASSIGN_OPT_TOTALS 1   /* produce out_total / out_count (default 0) */
+#define LAGASSIGN_OPT_TOTALS  1  /* produce out_total / out_count (default 0) */
+#define LAGASSIGN_OPT_PROFILE 2  /* bracket every kernel launch with CUDA events (default 0) */
 
 int  lagassign_abi_version(void);
 
@@ -176,6 +177,14 @@ int  lagassign_bind_device_outputs(lagassign_ctx *ctx, int32_t *d_out_partition,
 int  lagassign_download_lags(lagassign_ctx *ctx, int64_t *lag_out);
 
 int  lagassign_get_stats(const lagassign_ctx *ctx, lagassign_stats *stats);
+
+/* Per-kernel device times of the last execute() when LAGASSIGN_OPT_PROFILE is on
+ * (CUDA events on the context's stream around each launch). Entries are kernel
+ * kinds; a kind launched several times (radix passes) accumulates. Waits for the
+ * stream. Returns the number of kinds in *n_out; names are static strings. */
+int  lagassign_profile_count(lagassign_ctx *ctx, int *n_out);
+int  lagassign_profile_entry(lagassign_ctx *ctx, int i, const char **name_out,
+                             float *ms_out, int *launches_out);
 
 /* Pinned host memory, so uploads/downloads run at full PCIe speed. A JNI
  * caller wraps these with NewDirectByteBuffer. */

@@ -26,6 +26,7 @@ _lib: Optional[ctypes.CDLL] = None
 ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_OOM", -4: "ERR_STATE",
              -5: "ERR_NO_DEVICE", -6: "ERR_UNSUPPORTED"}
 OPT_TOTALS = 1
+OPT_PROFILE = 2
 
 
 class LagAssignError(RuntimeError):
@@ -64,7 +65,8 @@ class Stats(ctypes.Structure):
 
 
 def library_path() -> str:
-    return os.path.join(_PKG_DIR, _LIB_NAME)
+    # LAGASSIGN_LIBRARY selects another build of the same library (tuning experiments)
+    return os.environ.get("LAGASSIGN_LIBRARY") or os.path.join(_PKG_DIR, _LIB_NAME)
 
 
 def load_library() -> ctypes.CDLL:
@@ -96,12 +98,16 @@ def load_library() -> ctypes.CDLL:
     L.lagassign_bind_device_outputs.argtypes = [vp, vp, vp]
     L.lagassign_download_lags.argtypes = [vp, vp]
     L.lagassign_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    L.lagassign_profile_count.argtypes = [vp, ctypes.POINTER(ctypes.c_int)]
+    L.lagassign_profile_entry.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_char_p),
+                                          ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]
     L.lagassign_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
     L.lagassign_host_free.argtypes = [vp]
     for name in ("lagassign_device_count", "lagassign_create", "lagassign_create_on_stream",
                  "lagassign_set_option", "lagassign_assign_batch", "lagassign_upload",
                  "lagassign_upload_offsets", "lagassign_execute", "lagassign_sync", "lagassign_download",
                  "lagassign_bind_device_outputs", "lagassign_download_lags", "lagassign_get_stats",
+                 "lagassign_profile_count", "lagassign_profile_entry",
                  "lagassign_host_alloc", "lagassign_host_free"):
         getattr(L, name).restype = i32
     _lib = L
@@ -282,6 +288,21 @@ class FlatAssignor:
         self._check(self._L.lagassign_assign_batch(self._ctx, ctypes.byref(b), ctypes.byref(r)))
         self._shape = shape
         return dict(out_partition=op, out_consumer_rank=oc, out_total=ot, out_count=on)
+
+    def profile(self) -> dict:
+        """{kernel name: (milliseconds, launches)} of the last execute() (OPT_PROFILE on)."""
+        n = ctypes.c_int(0)
+        self._check(self._L.lagassign_profile_count(self._ctx, ctypes.byref(n)))
+        out = {}
+        for i in range(n.value):
+            name = ctypes.c_char_p()
+            ms = ctypes.c_float(0)
+            k = ctypes.c_int(0)
+            self._check(self._L.lagassign_profile_entry(self._ctx, i, ctypes.byref(name), ctypes.byref(ms),
+                                                        ctypes.byref(k)))
+            if k.value:
+                out[name.value.decode()] = (float(ms.value), int(k.value))
+        return out
 
     def stats(self) -> dict:
         s = Stats()

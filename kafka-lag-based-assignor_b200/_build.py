@@ -19,8 +19,6 @@ ROOT = os.path.dirname(PKG_DIR)
 LIB = os.path.join(PKG_DIR, "liblagassign.so")
 HOST_LIB = os.path.join(PKG_DIR, "liblagassign_host.so")
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 
 
 def _nvcc() -> str:
@@ -40,16 +38,38 @@ def _sources(sub, exts):
 
 
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
-    deps = _sources("", (".cu", ".cuh")) + [os.path.join(ROOT, "include", "lagassign.h")]
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest(deps):
-        return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB, os.path.join(CSRC, "lagassign_api.cu")]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    """One nvcc -c per .cu (in parallel: the sort templates are slow to compile), then link."""
+    from concurrent.futures import ThreadPoolExecutor
+    cus = _sources("", (".cu",))
+    hdrs = _sources("", (".cuh",)) + [os.path.join(ROOT, "include", "lagassign.h")]
+    objdir = os.path.join(PKG_DIR, "build")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_time = _newest(hdrs)
+    nvcc = _nvcc()
+    compile_flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+                     "-Xcompiler", "-fPIC"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(cu):
+        obj = os.path.join(objdir, os.path.basename(cu)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(cu), hdr_time):
+            return obj, ""
+        r = subprocess.run([nvcc] + compile_flags + ["-c", "-o", obj, cu], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {cu}:\n" + r.stdout + r.stderr)
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=len(cus)) as ex:
+        results = list(ex.map(compile_one, cus))
+    objs = [o for o, _ in results]
     if verbose:
-        print(r.stderr)
+        for _, log in results:
+            if log:
+                print(log)
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < _newest(objs):
+        r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static",
+                            "-Xcompiler", "-fPIC", "-o", LIB] + objs, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
     return LIB
 
 

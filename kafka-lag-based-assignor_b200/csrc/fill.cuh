@@ -136,4 +136,60 @@ __device__ __forceinline__ void cta_round_fill(int64_t P, int C, int nc, const i
     }
 }
 
+// One CTA of NT threads, consumers in REGISTERS (position j = tid*EPT + r, n =
+// NT*EPT >= C): per round one cta_bitonic_sort_regs() and a wrapping add, nothing
+// else touches shared memory. Used for 256 < C <= 4096.
+template <int EPT, int NT, class LagAt, class PutCons>
+__device__ __forceinline__ void cta_round_fill_regs(int64_t P, int C, const int32_t* __restrict__ cset,
+                                                    uint32_t* xbuf, LagAt lag_at, PutCons put,
+                                                    int64_t* out_total, int32_t* out_count) {
+    const int tid = threadIdx.x;
+    uint32_t w[3][EPT];          // w[2]:w[1] = total ^ 0x8000..., w[0] = consumer index
+    int64_t lag_cur[EPT];
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+        const int j = tid * EPT + r;
+        const bool live = j < C;
+        w[2][r] = live ? 0x80000000u : 0xFFFFFFFFu;    // total 0 (Main:218) / padding
+        w[1][r] = live ? 0u : 0xFFFFFFFFu;
+        w[0][r] = live ? (uint32_t)j : PAY_SENTINEL;
+        lag_cur[r] = (live && j < P) ? lag_at((int64_t)j) : 0;
+    }
+    for (int64_t base = 0; base < P; base += C) {
+        int64_t lag_nxt[EPT];
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            const int j = tid * EPT + r;
+            const int64_t k = base + C + j;
+            lag_nxt[r] = (j < C && k < P) ? lag_at(k) : 0;
+        }
+        if (base > 0) cta_bitonic_sort_regs<EPT, NT>(w, xbuf);
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            const int j = tid * EPT + r;
+            if (j < C && base + j < P) {
+                put(base + j, cset[w[0][r]]);                                        // Main:264
+                const uint64_t tk = (((uint64_t)w[2][r] << 32) | w[1][r]);
+                const uint64_t nk = ((tk ^ TOTAL_KEY_MASK) + (uint64_t)lag_cur[r]) ^ TOTAL_KEY_MASK;  // Main:265
+                w[1][r] = (uint32_t)nk;
+                w[2][r] = (uint32_t)(nk >> 32);
+            }
+            lag_cur[r] = lag_nxt[r];
+        }
+    }
+    if (out_total != nullptr) {
+        const int64_t full = P / C;
+        const int rem = (int)(P % C);
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            const int j = tid * EPT + r;
+            if (j < C) {
+                const uint64_t tk = (((uint64_t)w[2][r] << 32) | w[1][r]);
+                out_total[w[0][r]] = (int64_t)(tk ^ TOTAL_KEY_MASK);
+                out_count[w[0][r]] = (int32_t)(full + (j < rem ? 1 : 0));
+            }
+        }
+    }
+}
+
 }  // namespace lagassign

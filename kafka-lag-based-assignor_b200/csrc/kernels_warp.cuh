@@ -1,0 +1,259 @@
+// kernels_warp.cuh — topics whose partitions fit on chip: the whole of
+// assignTopic (LagBasedPartitionAssignor.java:204-277) for one topic in one warp
+// (P <= 256, registers) or one CTA (P <= 4096, shared memory). Lags are read from
+// HBM once and the two result arrays written once: 16 B per partition (20 B with
+// explicit partition ids).
+#pragma once
+#include "common.cuh"
+#include "types.cuh"
+#include "fill.cuh"
+#include "sort_cta.cuh"
+#include "sort_warp.cuh"
+
+namespace lagassign {
+
+#ifndef LAGASSIGN_WARP_MINBLOCKS
+#define LAGASSIGN_WARP_MINBLOCKS 4   // CTAs per SM the register allocation aims for
+#endif
+constexpr int SMALL_WARPS = 8;   // warps (= topics in flight) per CTA of k_warp_topics
+
+struct __align__(16) WarpScratch {
+    uint64_t lag_key[WARP_MAX_P];   // sorted keys, for the round fill / totals
+    uint32_t out_a[WARP_MAX_P];     // out_partition staging (blocked -> coalesced)
+    uint32_t out_b[WARP_MAX_P];     // out_consumer staging
+    uint32_t part_tab[WARP_MAX_P];  // partition ids in ascending order (unordered-input path)
+};
+
+// Staging of a warp's 32*EPT result words: written in sort order ("blocked": lane
+// owns EPT consecutive words) and read back striped so the global store is
+// coalesced. 16-byte chunks are XOR-swizzled so neither side has bank conflicts.
+template <int EPT>
+__device__ __forceinline__ int stage_addr(int i) {
+    if (EPT < 4) return i;
+    const int chunk = i >> 2;
+    return ((chunk ^ ((chunk >> 3) & 1)) << 2) | (i & 3);
+}
+template <int EPT>
+__device__ __forceinline__ void stage_store(uint32_t* buf, unsigned lane, const uint32_t (&v)[EPT]) {
+    if constexpr (EPT >= 4) {
+#pragma unroll
+        for (int c = 0; c < EPT / 4; ++c) {
+            const int i = (int)lane * EPT + c * 4;
+            *reinterpret_cast<uint4*>(buf + stage_addr<EPT>(i)) = make_uint4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
+        }
+    } else if constexpr (EPT == 2) {
+        *reinterpret_cast<uint2*>(buf + lane * 2) = make_uint2(v[0], v[1]);
+    } else {
+        buf[lane] = v[0];
+    }
+}
+
+template <int EPT> struct Log2Slots;
+template <> struct Log2Slots<1> { static constexpr int value = 5; };
+template <> struct Log2Slots<2> { static constexpr int value = 6; };
+template <> struct Log2Slots<4> { static constexpr int value = 7; };
+template <> struct Log2Slots<8> { static constexpr int value = 8; };
+
+// Sort (key, pay) ascending, pay < 32*EPT distinct for live elements, padding =
+// (KEY_SENTINEL, PAY_SENTINEL). Keys of one topic usually share most of their
+// high bits (real lags are small numbers), so the sort runs on the narrowest
+// element that still orders them: the s significant key bits above the B payload
+// bits, in one 32-bit word (s + B <= 32), one 64-bit word (s + B <= 64) or the
+// general three words. The choice is uniform across the warp.
+// The general three-word sort and the multi-round fill are kept out of line so
+// that their register needs do not set the occupancy of the common path.
+template <int EPT>
+__device__ __noinline__ void warp_sort_general(uint64_t (&key)[EPT], uint32_t (&pay)[EPT]) {
+    warp_bitonic_sort<EPT>(key, pay);
+}
+
+template <int EPT>
+__device__ __forceinline__ void warp_sort_adaptive(uint64_t (&key)[EPT], uint32_t (&pay)[EPT], int P) {
+    constexpr int B = Log2Slots<EPT>::value;
+    const unsigned lane = lane_id();
+    const uint64_t ref = __shfl_sync(0xffffffffu, key[0], 0);   // element 0 is live (P >= 1)
+    uint64_t x = 0;
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) x |= (pay[r] != PAY_SENTINEL) ? (key[r] ^ ref) : 0ull;
+    const uint32_t xlo = __reduce_or_sync(0xffffffffu, (uint32_t)x);
+    const uint32_t xhi = __reduce_or_sync(0xffffffffu, (uint32_t)(x >> 32));
+    const int s = xhi ? 64 - __clz(xhi) : (xlo ? 32 - __clz(xlo) : 0);   // bits in which keys differ
+    (void)lane; (void)P;
+    if (s + B <= 32) {
+        const uint32_t mask = s ? (0xFFFFFFFFu >> (32 - s)) : 0u;   // s <= 27
+        uint32_t w[1][EPT];
+#pragma unroll
+        for (int r = 0; r < EPT; ++r)
+            w[0][r] = (pay[r] != PAY_SENTINEL) ? ((((uint32_t)key[r] & mask) << B) | pay[r]) : 0xFFFFFFFFu;
+        warp_bitonic_sort_words<1, EPT>(w);
+        const uint64_t hi = ref & ~(uint64_t)mask;
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            pay[r] = w[0][r] & ((1u << B) - 1u);
+            key[r] = hi | (uint64_t)(w[0][r] >> B);
+        }
+    } else if (s + B <= 64) {
+        const uint64_t mask = ~0ull >> (64 - s);   // 1 <= s <= 59
+        uint32_t w[2][EPT];
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            const uint64_t v = (pay[r] != PAY_SENTINEL) ? (((key[r] & mask) << B) | pay[r]) : ~0ull;
+            w[0][r] = (uint32_t)v;
+            w[1][r] = (uint32_t)(v >> 32);
+        }
+        warp_bitonic_sort_words<2, EPT>(w);
+        const uint64_t hi = ref & ~mask;
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            const uint64_t v = ((uint64_t)w[1][r] << 32) | w[0][r];
+            pay[r] = (uint32_t)v & ((1u << B) - 1u);
+            key[r] = hi | (v >> B);
+        }
+    } else {
+        warp_sort_general<EPT>(key, pay);
+    }
+}
+
+__device__ __noinline__ void warp_rounds_path(int P, int C, const int32_t* __restrict__ cset, WarpScratch& ws,
+                                              int64_t* tot, int32_t* cnt);
+
+template <int EPT>
+__device__ __forceinline__ void warp_topic(const DevBatch& b, int t, WarpScratch& ws) {
+    const unsigned lane = lane_id();
+    const int64_t off = b.topic_off[t];
+    const int P = (int)(b.topic_off[t + 1] - off);
+    const int s = b.topic_cset[t];
+    const int64_t coff = b.cset_off[s];
+    const int64_t C64 = b.cset_off[s + 1] - coff;
+    const int32_t* __restrict__ cset = b.cset_rank + coff;
+
+    uint64_t key[EPT];
+    uint32_t pay[EPT];
+    // Coalesced load; which register slot an element lands in does not matter,
+    // the payload carries its list position (Main:228 sorts the whole list).
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+        int m = r * 32 + (int)lane;
+        bool live = m < P;
+        key[r] = live ? ((uint64_t)ld_stream(b.lag + off + m) ^ LAG_KEY_MASK) : KEY_SENTINEL;
+        pay[r] = live ? (uint32_t)m : PAY_SENTINEL;
+    }
+
+    bool use_tab = false;
+    if (b.part != nullptr) {
+        // Ties on lag break on partition id ascending (Main:230-231). A list that
+        // is already ascending in partition id lets the position stand in for it;
+        // otherwise order it by partition id first (stable by position).
+        bool bad = false;
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            int m = r * 32 + (int)lane;
+            if (m + 1 < P) bad |= b.part[off + m] > b.part[off + m + 1];
+        }
+        if (__any_sync(0xffffffffu, bad)) {
+            uint64_t k2[EPT];
+            uint32_t p2[EPT];
+#pragma unroll
+            for (int r = 0; r < EPT; ++r) {
+                int m = r * 32 + (int)lane;
+                bool live = m < P;
+                k2[r] = live ? (uint64_t)((uint32_t)b.part[off + m] ^ 0x80000000u) : KEY_SENTINEL;
+                p2[r] = live ? (uint32_t)m : PAY_SENTINEL;
+            }
+            warp_sort_adaptive<EPT>(k2, p2, P);
+#pragma unroll
+            for (int r = 0; r < EPT; ++r) {
+                int i = (int)lane * EPT + r;
+                bool live = i < P;
+                if (live) ws.part_tab[i] = (uint32_t)k2[r] ^ 0x80000000u;
+                key[r] = live ? ((uint64_t)b.lag[off + p2[r]] ^ LAG_KEY_MASK) : KEY_SENTINEL;
+                pay[r] = live ? (uint32_t)i : PAY_SENTINEL;
+            }
+            use_tab = true;
+            __syncwarp();
+        }
+    }
+
+    warp_sort_adaptive<EPT>(key, pay, P);     // Main:228-235
+
+    // out_partition, staged through shared memory so the global store is coalesced
+    {
+        uint32_t v[EPT];
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            int i = (int)lane * EPT + r;
+            v[r] = 0;
+            if (i < P) {
+                if (b.part == nullptr) v[r] = pay[r];
+                else if (use_tab) v[r] = ws.part_tab[pay[r]];
+                else v[r] = (uint32_t)b.part[off + pay[r]];
+            }
+        }
+        stage_store<EPT>(ws.out_a, lane, v);
+    }
+    const bool rounds = (int64_t)P > C64;
+    const bool need_keys = rounds || b.out_total != nullptr;
+    if (need_keys) {
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            int i = (int)lane * EPT + r;
+            if (i < P) ws.lag_key[i] = key[r];
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+        int m = r * 32 + (int)lane;
+        if (m < P) __stcs(b.out_part + off + m, (int32_t)ws.out_a[stage_addr<EPT>(m)]);
+    }
+
+    int64_t* tot = b.out_total ? b.out_total + b.tc_off[t] : nullptr;
+    int32_t* cnt = b.out_count ? b.out_count + b.tc_off[t] : nullptr;
+    if (!rounds) {
+        // P <= C: one partial round on all-zero totals, so the k-th partition in
+        // sorted order goes to the k-th member in id order.
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            int m = r * 32 + (int)lane;
+            if (m < P) {
+                __stcs(b.out_cons + off + m, cset[m]);
+                if (tot) { tot[m] = (int64_t)(ws.lag_key[m] ^ LAG_KEY_MASK); cnt[m] = 1; }
+            }
+        }
+        // members beyond P keep total 0 / count 0 (buffers are zero-filled)
+    } else {
+        warp_rounds_path(P, (int)C64, cset, ws, tot, cnt);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            int m = r * 32 + (int)lane;
+            if (m < P) __stcs(b.out_cons + off + m, (int32_t)ws.out_b[m]);
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __noinline__ void warp_rounds_path(int P, int C, const int32_t* __restrict__ cset, WarpScratch& ws,
+                                              int64_t* tot, int32_t* cnt) {
+    auto lag_at = [&](int64_t k) { return (int64_t)(ws.lag_key[k] ^ LAG_KEY_MASK); };
+    auto put = [&](int64_t k, int32_t rank) { ws.out_b[k] = (uint32_t)rank; };
+    warp_round_fill_dispatch(P, C, cset, lag_at, put, tot, cnt);
+}
+
+// One warp per topic of `list` (topics with 1 <= P <= 256 and a non-empty consumer set).
+__global__ void __launch_bounds__(SMALL_WARPS * 32, LAGASSIGN_WARP_MINBLOCKS)
+k_warp_topics(DevBatch b, const int32_t* __restrict__ list, int n_list) {
+    __shared__ WarpScratch scratch[SMALL_WARPS];
+    const int warp = threadIdx.x >> 5;
+    const int idx = blockIdx.x * SMALL_WARPS + warp;
+    if (idx >= n_list) return;
+    const int t = list[idx];
+    const int P = (int)(b.topic_off[t + 1] - b.topic_off[t]);
+    WarpScratch& ws = scratch[warp];
+    if (P <= 32) warp_topic<1>(b, t, ws);
+    else if (P <= 64) warp_topic<2>(b, t, ws);
+    else if (P <= 128) warp_topic<4>(b, t, ws);
+    else warp_topic<8>(b, t, ws);
+}
+
+}  // namespace lagassign

@@ -14,8 +14,7 @@
 #include <vector>
 
 #include "common.cuh"
-#include "kernels_small.cuh"
-#include "radix.cuh"
+#include "types.cuh"
 
 using namespace lagassign;
 
@@ -57,7 +56,21 @@ k_compute_lag(int64_t n, const int64_t* __restrict__ begin_off, const int64_t* _
 
 }  // namespace
 
+enum KernelKind { K_COMPUTE_LAG = 0, K_UNASSIGNED, K_WARP, K_CTA, K_ORDER, K_HIST, K_SCAN, K_PASS, K_FINALIZE,
+                  K_FILL, K_KINDS };
+static const char* const kKernelNames[K_KINDS] = {"k_compute_lag", "k_unassigned_topics", "k_warp_topics",
+                                                  "k_cta_topics", "k_big_order_check", "k_big_hist",
+                                                  "k_big_scan", "k_big_pass", "k_big_finalize", "k_big_fill"};
+struct ProfRec { int kind; cudaEvent_t a, b; };
+
 struct lagassign_ctx {
+    bool profile = false;
+    std::vector<ProfRec> prof;        // event pairs of the last execute()
+    std::vector<cudaEvent_t> ev_pool; // reusable events
+    size_t ev_used = 0;
+    float prof_ms[K_KINDS] = {0};
+    int prof_n[K_KINDS] = {0};
+    bool prof_resolved = true;
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -120,6 +133,30 @@ int upload_vec(lagassign_ctx* ctx, DevBuf& buf, const T* host, size_t n) {
 }
 
 #define TRY(expr) do { int _rc = (expr); if (_rc != LAGASSIGN_OK) return _rc; } while (0)
+
+cudaEvent_t prof_event(lagassign_ctx* ctx) {
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        ctx->ev_pool.push_back(e);
+    }
+    return ctx->ev_pool[ctx->ev_used++];
+}
+
+struct ProfScope {   // records an event pair around one launch when profiling is on
+    lagassign_ctx* ctx;
+    ProfRec rec;
+    ProfScope(lagassign_ctx* c, int kind) : ctx(c) {
+        if (!ctx->profile) return;
+        rec.kind = kind; rec.a = prof_event(ctx); rec.b = prof_event(ctx);
+        cudaEventRecord(rec.a, ctx->stream);
+    }
+    ~ProfScope() {
+        if (!ctx->profile) return;
+        cudaEventRecord(rec.b, ctx->stream);
+        ctx->prof.push_back(rec);
+    }
+};
 
 int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
                       std::vector<int32_t>& l_warp, std::vector<int32_t>& l_cta, std::vector<int32_t>& l_none,
@@ -229,6 +266,7 @@ BigTopics make_big(lagassign_ctx* ctx) {
     bt.status = ctx->d_status.as<uint32_t>();
     bt.ticket = ctx->d_ticket.as<uint32_t>();
     bt.passes_run = reinterpret_cast<int32_t*>(ctx->d_ticket.as<uint32_t>() + N_PASS);
+    bt.pass_any = ctx->d_ticket.as<uint32_t>() + N_PASS + 1;
     return bt;
 }
 
@@ -302,7 +340,7 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
         CUDA_TRY(ctx, ctx->d_sel.ensure((size_t)ctx->n_big * (2 * N_PASS + 1)));
         CUDA_TRY(ctx, ctx->d_need_tie.ensure((size_t)ctx->n_big * sizeof(int32_t)));
         CUDA_TRY(ctx, ctx->d_status.ensure((size_t)N_PASS * ctx->n_tiles * 256 * sizeof(uint32_t)));
-        CUDA_TRY(ctx, ctx->d_ticket.ensure((N_PASS + 1) * sizeof(uint32_t)));
+        CUDA_TRY(ctx, ctx->d_ticket.ensure((2 * N_PASS + 1) * sizeof(uint32_t)));
     }
     // the host vectors above must outlive the copies; also honours "the library
     // copies what it needs before returning"
@@ -319,10 +357,8 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
 }
 
 int configure_kernels(lagassign_ctx* ctx) {
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_cta_topics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CtaSmemLayout::total));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_big_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_big_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_big_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILL_CTA_MAX_C * 12)));
+    CUDA_TRY(ctx, configure_cta_kernels());
+    CUDA_TRY(ctx, configure_big_kernels());
     return LAGASSIGN_OK;
 }
 
@@ -391,6 +427,7 @@ void lagassign_destroy(lagassign_ctx* ctx) {
                       &ctx->d_status, &ctx->d_ticket, &ctx->d_out_part, &ctx->d_out_cons,
                       &ctx->d_out_total, &ctx->d_out_count};
     for (DevBuf* b : bufs) b->release();
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -402,6 +439,9 @@ const char* lagassign_last_error(const lagassign_ctx* ctx) {
 int lagassign_set_option(lagassign_ctx* ctx, int option, int64_t value) {
     if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
     switch (option) {
+        case LAGASSIGN_OPT_PROFILE:
+            ctx->profile = value != 0;
+            return LAGASSIGN_OK;
         case LAGASSIGN_OPT_TOTALS:
             ctx->want_totals = value != 0;
             ctx->uploaded = false;   // output buffers are sized at upload
@@ -424,11 +464,15 @@ int lagassign_execute(lagassign_ctx* ctx) {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     int launches = 0;
+    ctx->prof.clear();
+    ctx->ev_used = 0;
+    ctx->prof_resolved = false;
     DevBatch b = make_dev_batch(ctx);
     const int sms = ctx->sm_count;
 
     if (ctx->has_offsets && ctx->N > 0) {
         int grid = (int)std::min<int64_t>((ctx->N + 255) / 256, (int64_t)sms * 16);
+        ProfScope ps(ctx, K_COMPUTE_LAG);
         k_compute_lag<<<grid, 256, 0, st>>>(ctx->N, ctx->d_begin.as<int64_t>(), ctx->d_end.as<int64_t>(),
                                             ctx->d_committed.as<int64_t>(), ctx->d_hascommitted.as<uint8_t>(),
                                             ctx->reset_latest, ctx->d_lag.as<int64_t>());
@@ -439,18 +483,18 @@ int lagassign_execute(lagassign_ctx* ctx) {
         CUDA_TRY(ctx, cudaMemsetAsync(b.out_count, 0, (size_t)ctx->total_tc * sizeof(int32_t), st));
     }
     if (ctx->n_none > 0) {
-        dim3 grid(8, (unsigned)std::min(ctx->n_none, 65535));
-        k_unassigned_topics<<<grid, 256, 0, st>>>(b, ctx->d_list_none.as<int32_t>(), ctx->n_none);
+        ProfScope ps(ctx, K_UNASSIGNED);
+        launch_unassigned_topics(b, ctx->d_list_none.as<int32_t>(), ctx->n_none, st);
         ++launches;
     }
     if (ctx->n_warp > 0) {
-        int grid = (ctx->n_warp + SMALL_WARPS - 1) / SMALL_WARPS;
-        k_warp_topics<<<grid, SMALL_WARPS * 32, 0, st>>>(b, ctx->d_list_warp.as<int32_t>(), ctx->n_warp);
+        ProfScope ps(ctx, K_WARP);
+        launch_warp_topics(b, ctx->d_list_warp.as<int32_t>(), ctx->n_warp, st);
         ++launches;
     }
     if (ctx->n_cta > 0) {
-        int grid = std::min(ctx->n_cta, sms * 2);
-        k_cta_topics<<<grid, CTA_THREADS, CtaSmemLayout::total, st>>>(b, ctx->d_list_cta.as<int32_t>(), ctx->n_cta);
+        ProfScope ps(ctx, K_CTA);
+        launch_cta_topics(b, ctx->d_list_cta.as<int32_t>(), ctx->n_cta, sms, st);
         ++launches;
     }
     if (ctx->n_big > 0) {
@@ -459,32 +503,36 @@ int lagassign_execute(lagassign_ctx* ctx) {
         CUDA_TRY(ctx, cudaMemsetAsync(bt.ghist, 0, hb, st));
         CUDA_TRY(ctx, cudaMemsetAsync(bt.need_tie, 0, (size_t)ctx->n_big * sizeof(int32_t), st));
         CUDA_TRY(ctx, cudaMemsetAsync(bt.status, 0, (size_t)N_PASS * ctx->n_tiles * 256 * sizeof(uint32_t), st));
-        CUDA_TRY(ctx, cudaMemsetAsync(bt.ticket, 0, (N_PASS + 1) * sizeof(uint32_t), st));
-        const int G = ctx->n_tiles;
+        CUDA_TRY(ctx, cudaMemsetAsync(bt.ticket, 0, (2 * N_PASS + 1) * sizeof(uint32_t), st));
         const int first_pass = ctx->has_part ? 0 : N_TIE_PASS;
         if (ctx->has_part) {
-            k_big_order_check<<<std::min(G, sms * 8), 256, 0, st>>>(bt, b.part);
+            ProfScope ps(ctx, K_ORDER);
+            launch_big_order_check(bt, b.part, sms, st);
             ++launches;
-            k_big_hist<true><<<std::min(G, sms * 2), RT_THREADS, 0, st>>>(bt, b.lag, b.part);
-        } else {
-            k_big_hist<false><<<std::min(G, sms * 2), RT_THREADS, 0, st>>>(bt, b.lag, nullptr);
         }
-        ++launches;
-        k_big_scan<<<ctx->n_big, 256, 0, st>>>(bt, first_pass);
-        ++launches;
-        const int pass_grid = std::min(G, sms * 2);
+        {
+            ProfScope ps(ctx, K_HIST);
+            launch_big_hist(bt, b.lag, b.part, sms, st);
+            ++launches;
+        }
+        {
+            ProfScope ps(ctx, K_SCAN);
+            launch_big_scan(bt, first_pass, st);
+            ++launches;
+        }
         for (int p = first_pass; p < N_PASS; ++p) {
-            if (ctx->has_part) k_big_pass<true><<<pass_grid, RT_THREADS, sizeof(PassSmem), st>>>(bt, p, b.lag, b.part);
-            else k_big_pass<false><<<pass_grid, RT_THREADS, sizeof(PassSmem), st>>>(bt, p, b.lag, nullptr);
+            ProfScope ps(ctx, K_PASS);
+            launch_big_pass(bt, p, b.lag, b.part, sms, st);
             ++launches;
         }
-        k_big_finalize<<<std::min(G, sms * 8), 256, 0, st>>>(bt, b.lag, b.part, b.topic_cset, b.cset_off, b.cset_rank,
-                                                            b.tc_off, b.out_part, b.out_cons, b.out_total, b.out_count);
-        ++launches;
+        {
+            ProfScope ps(ctx, K_FINALIZE);
+            launch_big_finalize(bt, b, sms, st);
+            ++launches;
+        }
         if (ctx->n_fill > 0) {
-            k_big_fill<<<std::min(ctx->n_fill, sms), BIGFILL_THREADS, FILL_CTA_MAX_C * 12, st>>>(
-                bt, ctx->d_list_fill.as<int32_t>(), ctx->n_fill, b.lag, b.topic_cset, b.cset_off, b.cset_rank,
-                b.tc_off, b.out_cons, b.out_total, b.out_count);
+            ProfScope ps(ctx, K_FILL);
+            launch_big_fill(bt, ctx->d_list_fill.as<int32_t>(), ctx->n_fill, b, sms, st);
             ++launches;
         }
     }
@@ -566,6 +614,37 @@ int lagassign_download_lags(lagassign_ctx* ctx, int64_t* lag_out) {
 int lagassign_get_stats(const lagassign_ctx* ctx, lagassign_stats* stats) {
     if (!ctx || !stats) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx or stats is NULL");
     *stats = ctx->stats;
+    return LAGASSIGN_OK;
+}
+
+static int resolve_profile(lagassign_ctx* ctx) {
+    if (ctx->prof_resolved) return LAGASSIGN_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < K_KINDS; ++k) { ctx->prof_ms[k] = 0.f; ctx->prof_n[k] = 0; }
+    for (const ProfRec& r : ctx->prof) {
+        float ms = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, r.a, r.b));
+        ctx->prof_ms[r.kind] += ms;
+        ctx->prof_n[r.kind] += 1;
+    }
+    ctx->prof_resolved = true;
+    return LAGASSIGN_OK;
+}
+
+int lagassign_profile_count(lagassign_ctx* ctx, int* n_out) {
+    if (!ctx || !n_out) return fail(ctx, LAGASSIGN_ERR_ARG, "ctx or n_out is NULL");
+    TRY(resolve_profile(ctx));
+    *n_out = K_KINDS;
+    return LAGASSIGN_OK;
+}
+
+int lagassign_profile_entry(lagassign_ctx* ctx, int i, const char** name_out, float* ms_out, int* launches_out) {
+    if (!ctx || i < 0 || i >= K_KINDS) return fail(ctx, LAGASSIGN_ERR_ARG, "bad profile index");
+    TRY(resolve_profile(ctx));
+    if (name_out) *name_out = kKernelNames[i];
+    if (ms_out) *ms_out = ctx->prof_ms[i];
+    if (launches_out) *launches_out = ctx->prof_n[i];
     return LAGASSIGN_OK;
 }
 

@@ -1,0 +1,53 @@
+// launch_big.cu — translation unit of the device-wide path (radix.cuh).
+#include <algorithm>
+
+#include "radix.cuh"
+
+namespace lagassign {
+
+static int g_pass_ctas_per_sm[2] = {1, 1};   // resident CTAs per SM of k_big_pass<false/true>
+
+cudaError_t configure_big_kernels() {
+    cudaError_t e = cudaFuncSetAttribute(k_big_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_big_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
+    if (e != cudaSuccess) return e;
+    // the pass kernel is persistent (tiles are handed out by a ticket counter): one wave of resident CTAs
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_pass_ctas_per_sm[0], k_big_pass<false>, RT_THREADS, sizeof(PassSmem));
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_pass_ctas_per_sm[1], k_big_pass<true>, RT_THREADS, sizeof(PassSmem));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_big_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIGFILL_SMEM);
+}
+
+void launch_big_order_check(const BigTopics& bt, const int32_t* part, int sms, cudaStream_t st) {
+    k_big_order_check<<<std::min(bt.n_tiles, sms * 8), 256, 0, st>>>(bt, part);
+}
+
+void launch_big_hist(const BigTopics& bt, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st) {
+    const int grid = std::min(bt.n_tiles, sms * 2);
+    if (part) k_big_hist<true><<<grid, RT_THREADS, 0, st>>>(bt, lag, part);
+    else k_big_hist<false><<<grid, RT_THREADS, 0, st>>>(bt, lag, nullptr);
+}
+
+void launch_big_scan(const BigTopics& bt, int first_pass, cudaStream_t st) {
+    k_big_scan<<<bt.n_big, 256, 0, st>>>(bt, first_pass);
+}
+
+void launch_big_pass(const BigTopics& bt, int pass, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st) {
+    const int grid = std::min(bt.n_tiles, sms * std::max(1, g_pass_ctas_per_sm[part ? 1 : 0]));
+    if (part) k_big_pass<true><<<grid, RT_THREADS, sizeof(PassSmem), st>>>(bt, pass, lag, part);
+    else k_big_pass<false><<<grid, RT_THREADS, sizeof(PassSmem), st>>>(bt, pass, lag, nullptr);
+}
+
+void launch_big_finalize(const BigTopics& bt, const DevBatch& b, int sms, cudaStream_t st) {
+    k_big_finalize<<<std::min(bt.n_tiles, sms * 8), 256, 0, st>>>(bt, b.lag, b.part, b.topic_cset, b.cset_off, b.cset_rank,
+                                                                 b.tc_off, b.out_part, b.out_cons, b.out_total, b.out_count);
+}
+
+void launch_big_fill(const BigTopics& bt, const int32_t* fill_list, int n_fill, const DevBatch& b, int sms, cudaStream_t st) {
+    k_big_fill<<<std::min(n_fill, sms), BIGFILL_THREADS, BIGFILL_SMEM, st>>>(
+        bt, fill_list, n_fill, b.lag, b.topic_cset, b.cset_off, b.cset_rank, b.tc_off, b.out_cons, b.out_total, b.out_count);
+}
+
+}  // namespace lagassign

@@ -1,0 +1,11 @@
+// launch_warp.cu — translation unit of k_warp_topics (one warp per topic, P <= 256).
+#include "kernels_warp.cuh"
+
+namespace lagassign {
+
+void launch_warp_topics(const DevBatch& b, const int32_t* list, int n, cudaStream_t st) {
+    const int grid = (n + SMALL_WARPS - 1) / SMALL_WARPS;
+    k_warp_topics<<<grid, SMALL_WARPS * 32, 0, st>>>(b, list, n);
+}
+
+}  // namespace lagassign

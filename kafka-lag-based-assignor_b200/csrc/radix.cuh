@@ -20,45 +20,10 @@
 // then 8 passes over key = lag ^ 0x7FFF...F (descending signed lag, Main:234).
 #pragma once
 #include "common.cuh"
+#include "types.cuh"
 #include "fill.cuh"
 
 namespace lagassign {
-
-constexpr int RT_THREADS = 512;
-constexpr int RT_IPT = 8;
-constexpr int RT_TILE = RT_THREADS * RT_IPT;   // 4096 elements per tile
-constexpr int RT_WARPS = RT_THREADS / 32;
-constexpr int N_TIE_PASS = 4;
-constexpr int N_LAG_PASS = 8;
-constexpr int N_PASS = N_TIE_PASS + N_LAG_PASS;
-
-constexpr uint32_t ST_AGG = 1u << 30;   // tile's own count is published
-constexpr uint32_t ST_INC = 2u << 30;   // inclusive prefix over the topic's tiles so far
-constexpr uint32_t ST_VAL = (1u << 30) - 1;
-
-enum : int { SEL_RAW = 0, SEL_A = 1, SEL_B = 2, SEL_SKIP = -1 };
-
-struct BigTopics {
-    int n_big;                 // B
-    int n_tiles;               // G
-    const int32_t* topic;      // [B] topic id
-    const int64_t* off;        // [B] offset in the caller's arrays (= topic_off[t])
-    const int64_t* P;          // [B]
-    const int64_t* boff;       // [B] offset in the compact sort buffers
-    const int32_t* tile0;      // [B] first tile of the topic
-    const int32_t* tile_bt;    // [G] tile -> b
-    uint64_t* keyA; uint64_t* keyB;   // [sum P]
-    uint32_t* payA; uint32_t* payB;
-    uint32_t* ghist;           // [B][N_PASS][256] digit counts
-    uint32_t* gbase;           // [B][N_PASS][256] exclusive prefix of ghist
-    int8_t* sel_src;           // [B][N_PASS]  SEL_* (SEL_SKIP = pass skipped for this topic)
-    int8_t* sel_dst;           // [B][N_PASS]
-    int8_t* sel_final;         // [B] where the sorted data of the topic ended up
-    int32_t* need_tie;         // [B] partition ids not ascending
-    uint32_t* status;          // [N_PASS][G][256] look-back words (zeroed per execute)
-    uint32_t* ticket;          // [N_PASS] dynamic tile ids (zeroed per execute)
-    int32_t* passes_run;       // [1] max over topics of executed passes (stat)
-};
 
 // Look-back status words are polled by other CTAs while they are being written:
 // the accesses must be real memory operations every time (never hoisted, merged
@@ -177,6 +142,7 @@ k_big_scan(BigTopics bt, int first_pass) {
                 bt.sel_dst[b * N_PASS + p] = (int8_t)dst;
                 s_cur = dst;
                 s_run += 1;
+                atomicOr(&bt.pass_any[p], 1u);
             }
         }
         __syncthreads();
@@ -199,12 +165,13 @@ struct PassSmem {
 };
 
 template <bool HAS_PART>
-__global__ void __launch_bounds__(RT_THREADS)
+__global__ void __launch_bounds__(RT_THREADS, LAGASSIGN_RT_MINBLOCKS)
 k_big_pass(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int32_t* __restrict__ part) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PassSmem& sm = *reinterpret_cast<PassSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t* status = bt.status + (size_t)pass * bt.n_tiles * 256;
+    if (bt.pass_any[pass] == 0) return;   // every topic's digit is constant: nothing to move
 
     for (;;) {
         __syncthreads();
@@ -293,6 +260,9 @@ k_big_pass(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int32_
             for (int w = 0; w < warp; ++w) add += sm.wsum[w];
             const uint32_t excl = x - cnt + add;
             sm.tile_excl[tid] = excl;
+            // fold the tile-local digit offset into the per-warp offsets: one lookup per item later
+#pragma unroll
+            for (int w = 0; w < RT_WARPS; ++w) sm.whist[w][tid] += excl;
 
             // decoupled look-back over the earlier tiles of this topic
             uint32_t prefix = 0;
@@ -317,7 +287,7 @@ k_big_pass(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int32_
         // scatter inside the tile (shared memory), then out in digit runs (coalesced)
 #pragma unroll
         for (int k = 0; k < RT_IPT; ++k) {
-            const uint32_t pos = sm.tile_excl[dig[k]] + sm.whist[warp][dig[k]] + rank[k];
+            const uint32_t pos = sm.whist[warp][dig[k]] + rank[k];
             sm.key[pos] = key[k];
             sm.pay[pos] = pay[k];
         }
@@ -371,8 +341,6 @@ k_big_finalize(BigTopics bt, const int64_t* __restrict__ lag, const int32_t* __r
 }
 
 // ---- 6. round fill of a large topic: one CTA per topic -----------------------------------
-constexpr int BIGFILL_THREADS = 1024;
-constexpr int BIGFILL_MAXJ = FILL_CTA_MAX_C / BIGFILL_THREADS;
 
 __global__ void __launch_bounds__(BIGFILL_THREADS)
 k_big_fill(BigTopics bt, const int32_t* __restrict__ fill_list, int n_fill,
@@ -400,8 +368,17 @@ k_big_fill(BigTopics bt, const int32_t* __restrict__ fill_list, int n_fill,
             return (sel == SEL_RAW) ? __ldg(lg + k) : (int64_t)(__ldg(fkey + k) ^ LAG_KEY_MASK);
         };
         auto put = [&](int64_t k, int32_t rank) { out_cons[off + k] = rank; };
+        uint32_t* xbuf = reinterpret_cast<uint32_t*>(smem_raw);
         if (C <= FILL_WARP_MAX_C) {
             if (threadIdx.x < 32) warp_round_fill_dispatch(P, C, cset, lag_at, put, tot, cnt);
+        } else if (C <= 512) {
+            cta_round_fill_regs<2, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
+        } else if (C <= 1024) {
+            cta_round_fill_regs<4, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
+        } else if (C <= 2048) {
+            cta_round_fill_regs<8, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
+        } else if (C <= BIGFILL_REG_MAX_C) {
+            cta_round_fill_regs<16, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
         } else {
             cta_round_fill<BIGFILL_MAXJ>(P, C, max(64, 1 << (32 - __clz(C - 1))), cset, ckey, cidx,
                                          lag_at, put, tot, cnt);

@@ -4,6 +4,7 @@
 // __syncthreads() per stage.
 #pragma once
 #include "common.cuh"
+#include "sort_warp.cuh"
 
 namespace lagassign {
 
@@ -43,6 +44,86 @@ __device__ __forceinline__ void cta_bitonic_sort(uint64_t* key, uint32_t* pay, i
         if (k >= 64) __syncthreads();
     }
     __syncthreads();
+}
+
+// ---- register-resident variant -----------------------------------------------------------
+// n = NT*EPT three-word elements (see sort_warp.cuh) held in registers by a CTA of
+// NT threads, logical index i = tid*EPT + r. Strides below EPT are in-register,
+// below 32*EPT warp shuffles, and only the log2(NT/32) highest index bits cross
+// warps: those stages exchange through shared memory (one __syncthreads() each,
+// two alternating buffers). A 1024-element sort is 49 barrier-free stages + 6
+// exchanges instead of 20 barriers in cta_bitonic_sort().
+//
+// xbuf: 2 * 3 * n words of shared memory. All NT threads must call.
+template <int EPT, int NT>
+__device__ __forceinline__ void cta_bitonic_sort_regs(uint32_t (&w)[3][EPT], uint32_t* xbuf) {
+    constexpr int N = NT * EPT;
+    constexpr int WARP_SPAN = 32 * EPT;
+    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    int flip = 0;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            // direction of the size-k block holding this thread's elements (k > j)
+            bool asc_hi;   // valid when k >= EPT
+            if (k == N) asc_hi = true;
+            else asc_hi = ((tid & (unsigned)(k / EPT)) == 0);
+            if (j >= WARP_SPAN) {
+                // partner element lives in another warp: same lane, same slot
+                const unsigned tj = (unsigned)(j / EPT);
+                uint32_t* buf = xbuf + flip * (3 * N);
+                flip ^= 1;
+#pragma unroll
+                for (int r = 0; r < EPT; ++r) {
+#pragma unroll
+                    for (int x = 0; x < 3; ++x) buf[(x * EPT + r) * NT + tid] = w[x][r];
+                }
+                __syncthreads();
+                const bool keep_max = (((tid & tj) == 0) != asc_hi);
+                const unsigned pt = tid ^ tj;
+#pragma unroll
+                for (int r = 0; r < EPT; ++r) {
+                    uint32_t o[3];
+#pragma unroll
+                    for (int x = 0; x < 3; ++x) o[x] = buf[(x * EPT + r) * NT + pt];
+                    const bool lt = lt3(o[2], o[1], o[0], w[2][r], w[1][r], w[0][r]);
+                    const bool take = (lt != keep_max);
+#pragma unroll
+                    for (int x = 0; x < 3; ++x) w[x][r] = take ? o[x] : w[x][r];
+                }
+            } else if (j >= EPT) {
+                const unsigned lj = (unsigned)(j / EPT);
+                const bool keep_max = (((lane & lj) == 0) != asc_hi);
+#pragma unroll
+                for (int r = 0; r < EPT; ++r) {
+                    uint32_t o[3];
+#pragma unroll
+                    for (int x = 0; x < 3; ++x) o[x] = __shfl_xor_sync(0xffffffffu, w[x][r], lj);
+                    const bool lt = lt3(o[2], o[1], o[0], w[2][r], w[1][r], w[0][r]);
+                    const bool take = (lt != keep_max);
+#pragma unroll
+                    for (int x = 0; x < 3; ++x) w[x][r] = take ? o[x] : w[x][r];
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < EPT; ++r) {
+                    if ((r & j) == 0) {
+                        const bool asc = (k < EPT) ? ((r & k) == 0) : asc_hi;
+                        const int q = r | j;
+                        const bool lt = lt3(w[2][q], w[1][q], w[0][q], w[2][r], w[1][r], w[0][r]);
+                        const bool swap = (lt == asc);
+#pragma unroll
+                        for (int x = 0; x < 3; ++x) {
+                            const uint32_t a = w[x][r], b = w[x][q];
+                            w[x][r] = swap ? b : a;
+                            w[x][q] = swap ? a : b;
+                        }
+                    }
+                }
+            }
+        }
+    }
 }
 
 }  // namespace lagassign

@@ -1,26 +1,41 @@
-// sort_warp.cuh — bitonic sort of 32*EPT (key, pay) elements held in the registers
-// of one warp. Logical index i = lane*EPT + r ("blocked"): the low log2(EPT) index
-// bits are register bits (compare-exchange without communication), the five high
-// bits are lane bits (shuffle). The low bits are the ones a bitonic network visits
-// most often, so blocked costs 15 shuffle stages at EPT=8 where a striped layout
-// would cost 30. Input placement is arbitrary (the payload remembers where an
-// element came from), so loads can stay fully coalesced.
+// sort_warp.cuh — bitonic sort of 32*EPT elements held in the registers of one
+// warp. An element is W 32-bit words compared as one unsigned integer (word W-1
+// most significant): W=3 is the general (64-bit key, 32-bit payload) element,
+// W=2 / W=1 are the packed forms used when a topic's keys share a common prefix
+// (see kernels_small.cuh). Elements must be pairwise distinct, except padding
+// elements, which are identical to each other.
+//
+// Logical index i = lane*EPT + r ("blocked"): the low log2(EPT) index bits are
+// register bits (compare-exchange without communication), the five high bits are
+// lane bits (shuffle). The low bits are the ones a bitonic network visits most
+// often, so blocked costs 15 shuffle stages at EPT=8 where a striped layout would
+// cost 30. Input placement is arbitrary (the payload remembers where an element
+// came from), so loads stay coalesced.
+//
+// Everything is branch-free: compare-exchange is a borrow chain / 64-bit compare /
+// min-max plus selects, so all 32 lanes stay converged.
 #pragma once
 #include "common.cuh"
 
 namespace lagassign {
 
-// In-register compare-exchange: after the call (ka,pa) <= (kb,pb) if asc, else >=.
-__device__ __forceinline__ void cmpx(uint64_t& ka, uint32_t& pa, uint64_t& kb, uint32_t& pb, bool asc) {
-    bool swap = asc ? elem_less(kb, pb, ka, pa) : elem_less(ka, pa, kb, pb);
-    if (swap) {
-        uint64_t tk = ka; ka = kb; kb = tk;
-        uint32_t tp = pa; pa = pb; pb = tp;
-    }
+// a < b for W-word unsigned integers (scalars passed most significant first).
+__device__ __forceinline__ bool lt3(uint32_t a2, uint32_t a1, uint32_t a0, uint32_t b2, uint32_t b1, uint32_t b0) {
+    uint32_t borrow;
+    asm("{\n\t.reg .u32 t;\n\t"
+        "sub.cc.u32 t, %1, %4;\n\t"
+        "subc.cc.u32 t, %2, %5;\n\t"
+        "subc.cc.u32 t, %3, %6;\n\t"
+        "subc.u32 %0, 0, 0;\n\t}"
+        : "=r"(borrow) : "r"(a0), "r"(a1), "r"(a2), "r"(b0), "r"(b1), "r"(b2));
+    return borrow != 0;
+}
+__device__ __forceinline__ bool lt2(uint32_t a1, uint32_t a0, uint32_t b1, uint32_t b0) {
+    return (((uint64_t)a1 << 32) | a0) < (((uint64_t)b1 << 32) | b0);
 }
 
-template <int EPT>
-__device__ __forceinline__ void warp_bitonic_sort(uint64_t (&key)[EPT], uint32_t (&pay)[EPT]) {
+template <int W, int EPT>
+__device__ __forceinline__ void warp_bitonic_sort_words(uint32_t (&w)[W][EPT]) {
     constexpr int N = 32 * EPT;
     const unsigned lane = lane_id();
 #pragma unroll
@@ -30,16 +45,24 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t (&key)[EPT], uint32_t
             if (j >= EPT) {
                 // partner lives in another lane, same register slot
                 const unsigned lj = (unsigned)(j / EPT);
-                // direction of the size-k block this element is in (k > j >= EPT: a lane bit)
                 const bool asc = (k == N) ? true : ((lane & (unsigned)(k / EPT)) == 0);
-                const bool keep_min = (((lane & lj) == 0) == asc);
+                const bool keep_max = (((lane & lj) == 0) != asc);
 #pragma unroll
                 for (int r = 0; r < EPT; ++r) {
-                    uint64_t ok = __shfl_xor_sync(0xffffffffu, key[r], lj);
-                    uint32_t op = __shfl_xor_sync(0xffffffffu, pay[r], lj);
-                    bool take = keep_min ? elem_less(ok, op, key[r], pay[r])
-                                         : elem_less(key[r], pay[r], ok, op);
-                    if (take) { key[r] = ok; pay[r] = op; }
+                    uint32_t o[W];
+#pragma unroll
+                    for (int x = 0; x < W; ++x) o[x] = __shfl_xor_sync(0xffffffffu, w[x][r], lj);
+                    if (W == 1) {
+                        const uint32_t lo = min(w[0][r], o[0]), hi = max(w[0][r], o[0]);
+                        w[0][r] = keep_max ? hi : lo;
+                    } else {
+                        bool lt;   // other < mine
+                        if (W == 2) lt = lt2(o[1], o[0], w[1][r], w[0][r]);
+                        else lt = lt3(o[W - 1], o[W - 2], o[0], w[W - 1][r], w[W - 2][r], w[0][r]);
+                        const bool take = (lt != keep_max);   // equal elements are identical: either choice is the same
+#pragma unroll
+                        for (int x = 0; x < W; ++x) w[x][r] = take ? o[x] : w[x][r];
+                    }
                 }
             } else {
 #pragma unroll
@@ -49,11 +72,45 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t (&key)[EPT], uint32_t
                         if (k == N) asc = true;
                         else if (k < EPT) asc = ((r & k) == 0);
                         else asc = ((lane & (unsigned)(k / EPT)) == 0);
-                        cmpx(key[r], pay[r], key[r | j], pay[r | j], asc);
+                        const int q = r | j;
+                        if (W == 1) {
+                            const uint32_t lo = min(w[0][r], w[0][q]), hi = max(w[0][r], w[0][q]);
+                            w[0][r] = asc ? lo : hi;
+                            w[0][q] = asc ? hi : lo;
+                        } else {
+                            bool lt;   // w[q] < w[r]
+                            if (W == 2) lt = lt2(w[1][q], w[0][q], w[1][r], w[0][r]);
+                            else lt = lt3(w[W - 1][q], w[W - 2][q], w[0][q], w[W - 1][r], w[W - 2][r], w[0][r]);
+                            const bool swap = (lt == asc);
+#pragma unroll
+                            for (int x = 0; x < W; ++x) {
+                                const uint32_t a = w[x][r], b = w[x][q];
+                                w[x][r] = swap ? b : a;
+                                w[x][q] = swap ? a : b;
+                            }
+                        }
                     }
                 }
             }
         }
+    }
+}
+
+// (64-bit key, 32-bit payload) interface over the 3-word sort.
+template <int EPT>
+__device__ __forceinline__ void warp_bitonic_sort(uint64_t (&key)[EPT], uint32_t (&pay)[EPT]) {
+    uint32_t w[3][EPT];
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+        w[0][r] = pay[r];
+        w[1][r] = (uint32_t)key[r];
+        w[2][r] = (uint32_t)(key[r] >> 32);
+    }
+    warp_bitonic_sort_words<3, EPT>(w);
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+        pay[r] = w[0][r];
+        key[r] = ((uint64_t)w[2][r] << 32) | w[1][r];
     }
 }
 

@@ -1,0 +1,90 @@
+// types.cuh — plain structs and constants shared by the host API and the kernels.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace lagassign {
+
+struct DevBatch {
+    const int64_t* topic_off;   // [T+1]
+    const int64_t* lag;         // [N]
+    const int32_t* part;        // [N] or null
+    const int32_t* topic_cset;  // [T]
+    const int64_t* cset_off;    // [S+1]
+    const int32_t* cset_rank;   // [R]
+    const int64_t* tc_off;      // [T+1] offsets of the totals/counts blocks (or null)
+    int32_t* out_part;          // [N]
+    int32_t* out_cons;          // [N]
+    int64_t* out_total;         // null unless enabled
+    int32_t* out_count;
+};
+
+#ifndef LAGASSIGN_RT_THREADS
+#define LAGASSIGN_RT_THREADS 512
+#endif
+#ifndef LAGASSIGN_RT_IPT
+#define LAGASSIGN_RT_IPT 8
+#endif
+#ifndef LAGASSIGN_RT_MINBLOCKS
+#define LAGASSIGN_RT_MINBLOCKS 2
+#endif
+constexpr int RT_THREADS = LAGASSIGN_RT_THREADS;
+constexpr int RT_IPT = LAGASSIGN_RT_IPT;
+constexpr int RT_TILE = RT_THREADS * RT_IPT;   // 4096 elements per tile
+constexpr int RT_WARPS = RT_THREADS / 32;
+constexpr int N_TIE_PASS = 4;
+constexpr int N_LAG_PASS = 8;
+constexpr int N_PASS = N_TIE_PASS + N_LAG_PASS;
+
+constexpr uint32_t ST_AGG = 1u << 30;   // tile's own count is published
+constexpr uint32_t ST_INC = 2u << 30;   // inclusive prefix over the topic's tiles so far
+constexpr uint32_t ST_VAL = (1u << 30) - 1;
+
+enum : int { SEL_RAW = 0, SEL_A = 1, SEL_B = 2, SEL_SKIP = -1 };
+
+struct BigTopics {
+    int n_big;                 // B
+    int n_tiles;               // G
+    const int32_t* topic;      // [B] topic id
+    const int64_t* off;        // [B] offset in the caller's arrays (= topic_off[t])
+    const int64_t* P;          // [B]
+    const int64_t* boff;       // [B] offset in the compact sort buffers
+    const int32_t* tile0;      // [B] first tile of the topic
+    const int32_t* tile_bt;    // [G] tile -> b
+    uint64_t* keyA; uint64_t* keyB;   // [sum P]
+    uint32_t* payA; uint32_t* payB;
+    uint32_t* ghist;           // [B][N_PASS][256] digit counts
+    uint32_t* gbase;           // [B][N_PASS][256] exclusive prefix of ghist
+    int8_t* sel_src;           // [B][N_PASS]  SEL_* (SEL_SKIP = pass skipped for this topic)
+    int8_t* sel_dst;           // [B][N_PASS]
+    int8_t* sel_final;         // [B] where the sorted data of the topic ended up
+    int32_t* need_tie;         // [B] partition ids not ascending
+    uint32_t* status;          // [N_PASS][G][256] look-back words (zeroed per execute)
+    uint32_t* ticket;          // [N_PASS] dynamic tile ids (zeroed per execute)
+    int32_t* passes_run;       // [1] max over topics of executed passes (stat)
+    uint32_t* pass_any;        // [N_PASS] does any topic run this pass? (else the launch returns at once)
+};
+
+
+constexpr int BIGFILL_THREADS = 256;
+constexpr int BIGFILL_MAXJ = FILL_CTA_MAX_C / BIGFILL_THREADS;
+constexpr int BIGFILL_REG_MAX_C = 4096;                      // consumers kept in registers up to here
+constexpr size_t BIGFILL_SMEM = (size_t)FILL_CTA_MAX_C * 12; // >= 2*3*4096 words of exchange buffers
+
+// ---- launchers (one translation unit per kernel family, see launch_*.cu) ----------------
+cudaError_t configure_cta_kernels();
+cudaError_t configure_big_kernels();
+void launch_unassigned_topics(const DevBatch& b, const int32_t* list, int n, cudaStream_t st);
+void launch_warp_topics(const DevBatch& b, const int32_t* list, int n, cudaStream_t st);
+void launch_cta_topics(const DevBatch& b, const int32_t* list, int n, int sms, cudaStream_t st);
+void launch_big_order_check(const BigTopics& bt, const int32_t* part, int sms, cudaStream_t st);
+void launch_big_hist(const BigTopics& bt, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st);
+void launch_big_scan(const BigTopics& bt, int first_pass, cudaStream_t st);
+void launch_big_pass(const BigTopics& bt, int pass, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st);
+void launch_big_finalize(const BigTopics& bt, const DevBatch& b, int sms, cudaStream_t st);
+void launch_big_fill(const BigTopics& bt, const int32_t* fill_list, int n_fill, const DevBatch& b, int sms, cudaStream_t st);
+
+}  // namespace lagassign

@@ -102,6 +102,13 @@ def baseline_config(n, scale=1.0):
                     topic_cset=np.zeros(T, np.int32), cset_off=np.array([0, C], np.int64),
                     cset_rank=np.arange(C, dtype=np.int32)), \
             f"{T} topics, power-law partition counts (N={N}), {C} consumers, all-zero lag"
+    if n == 6:
+        # SURVEY.md 8(d) "scaled sort-only variant": the device-wide radix sort with a
+        # working set far beyond the 126 MB L2; P <= C so the fill is the trivial round.
+        T = max(1, int(64 * scale))
+        P = 1 << 20
+        lag = (splitmix64(np.uint64(0xB200) + np.arange(T * P, dtype=np.uint64)) >> np.uint64(1)).astype(np.int64)
+        return uniform_batch(T, P, P, lag), f"{T} topics x {P} partitions, {P} consumers, uniform int64 lag (sort-only variant)"
     raise ValueError(n)
 
 

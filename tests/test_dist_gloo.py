@@ -1,0 +1,87 @@
+"""Host-side multi-GPU logic on CPU: topic sharding and the result all-gather,
+world_size 2 and 3 over gloo. The per-rank compute is stood in for by the oracle
+(the kernels need a GPU); what is under test is kafka_lag_based_assignor_b200
+.distributed — shard bounds, sub-batch slicing, equal and ragged gathers."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, kind, ret):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle
+        from helpers import args_of, random_flat, uniform_batch
+        from kafka_lag_based_assignor_b200 import distributed as D
+        rng = np.random.default_rng(123)     # same batch on every rank
+        if kind == "equal":
+            batch = uniform_batch(12, 20, 7, rng.integers(0, 1000, size=240, dtype=np.int64))
+        else:
+            batch = random_flat(rng, T=23, pmin=0, pmax=90, C=9, lag_kind="dups", explicit_ids="shuffled", n_sets=3)
+        bounds = D.shard_bounds(batch["topic_off"], world)
+        counts = D.partition_counts(batch["topic_off"], bounds)
+        assert sum(counts) == int(batch["topic_off"][-1])
+        assert bounds[0][0] == 0 and bounds[-1][1] == len(batch["topic_off"]) - 1
+        assert all(bounds[i][1] == bounds[i + 1][0] for i in range(world - 1))
+        lo, hi = bounds[rank]
+        local = D.shard_batch(batch, lo, hi)
+        loc = oracle.assign_batch(*args_of(local))          # stand-in for the GPU kernels
+        fp, fc = D.all_gather_results(torch.from_numpy(loc["out_partition"]),
+                                      torch.from_numpy(loc["out_consumer_rank"]), counts)
+        full = oracle.assign_batch(*args_of(batch))
+        ok = np.array_equal(fp.numpy(), full["out_partition"]) and np.array_equal(fc.numpy(), full["out_consumer_rank"])
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("kind", ["equal", "ragged"])
+def test_shard_and_gather_gloo(world, kind):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, kind, ret), nprocs=world, join=True)
+    assert dict(ret) == {r: True for r in range(world)}
+
+
+def test_shard_bounds_properties():
+    from kafka_lag_based_assignor_b200 import distributed as D
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        T = int(rng.integers(0, 40))
+        P = rng.integers(0, 1000, size=T)
+        off = np.concatenate([[0], np.cumsum(P)]).astype(np.int64)
+        for world in (1, 2, 4, 8):
+            b = D.shard_bounds(off, world)
+            assert len(b) == world and b[0][0] == 0 and b[-1][1] == T
+            assert all(lo <= hi for lo, hi in b)
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+    # equal topics split equally (BASELINE config 4 shape)
+    off = np.arange(0, 100001, dtype=np.int64) * 256
+    for world in (2, 4, 8):
+        assert D.partition_counts(off, D.shard_bounds(off, world)) == [25600000 // world] * world
+    # one giant topic is never split
+    off = np.array([0, 10, 1 << 20, (1 << 20) + 5], dtype=np.int64)
+    b = D.shard_bounds(off, 4)
+    assert sum(hi - lo for lo, hi in b) == 3
