@@ -144,7 +144,8 @@ def run_reference(args, batch, desc):
     if rank != 0:
         return
     oracle.build()
-    threads = oracle.max_threads()
+    # all host threads (torchrun exports OMP_NUM_THREADS=1, so do not ask OpenMP)
+    threads = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     off = batch["topic_off"]
     T = len(off) - 1
     # one step = a bounded sample of topics, sized for ~2 s
