@@ -90,13 +90,19 @@ struct lagassign_ctx {
     DevBuf d_begin, d_end, d_committed, d_hascommitted;
     // plan lists
     DevBuf d_list_warp, d_list_cta, d_list_none, d_list_fill;
-    DevBuf d_bt_topic, d_bt_off, d_bt_P, d_bt_boff, d_bt_tile0, d_tile_bt;
+    DevBuf d_bt_topic, d_bt_off, d_bt_P, d_bt_boff, d_bt_tile0, d_bt_chunk0, d_tile_bt, d_cstatus;
+    int n_chunks = 0;
     // radix workspaces
     DevBuf d_keyA, d_keyB, d_payA, d_payB, d_ghist, d_gbase, d_sel, d_need_tie, d_status, d_ticket;
     // outputs
     DevBuf d_out_part, d_out_cons, d_out_total, d_out_count;
     int32_t* bound_part = nullptr;
     int32_t* bound_cons = nullptr;
+
+    // host copies of the bin lists (ascending topic ids) for the chunked assign_batch() pipeline
+    std::vector<int32_t> h_list_warp, h_list_cta, h_list_none;
+    cudaStream_t stream_in = nullptr, stream_out = nullptr;
+    std::vector<cudaEvent_t> pipe_events;
 
     lagassign_stats stats{};
 };
@@ -162,7 +168,7 @@ int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
                       std::vector<int32_t>& l_warp, std::vector<int32_t>& l_cta, std::vector<int32_t>& l_none,
                       std::vector<int32_t>& bt_topic, std::vector<int64_t>& bt_off, std::vector<int64_t>& bt_P,
                       std::vector<int64_t>& bt_boff, std::vector<int32_t>& bt_tile0, std::vector<int32_t>& tile_bt,
-                      std::vector<int32_t>& l_fill, std::vector<int64_t>& tc_off) {
+                      std::vector<int32_t>& l_fill, std::vector<int64_t>& tc_off, std::vector<int32_t>& bt_chunk0) {
     if (!in) return fail(ctx, LAGASSIGN_ERR_ARG, "batch is NULL");
     const int64_t T = in->n_topics, S = in->n_csets;
     if (T < 0 || S < 0) return fail(ctx, LAGASSIGN_ERR_ARG, "negative n_topics / n_csets");
@@ -189,6 +195,7 @@ int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
     if (T > 0 && !in->topic_cset) return fail(ctx, LAGASSIGN_ERR_ARG, "topic_cset is NULL");
 
     tc_off.assign((size_t)T + 1, 0);
+    ctx->n_chunks = 0;
     int64_t boff = 0, tiles = 0, assigned = 0;
     for (int64_t t = 0; t < T; ++t) {
         const int32_t s = in->topic_cset[t];
@@ -215,6 +222,8 @@ int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
             bt_P.push_back(P);
             bt_boff.push_back(boff);
             bt_tile0.push_back((int32_t)tiles);
+            bt_chunk0.push_back((int32_t)ctx->n_chunks);
+            ctx->n_chunks += (int)((nt + RT_CHUNK - 1) / RT_CHUNK);
             for (int64_t k = 0; k < nt; ++k) tile_bt.push_back(b);
             if (P > C) l_fill.push_back(b);
             boff += P;
@@ -264,18 +273,21 @@ BigTopics make_big(lagassign_ctx* ctx) {
     bt.sel_final = sel + (size_t)ctx->n_big * N_PASS * 2;
     bt.need_tie = ctx->d_need_tie.as<int32_t>();
     bt.status = ctx->d_status.as<uint32_t>();
+    bt.chunk0 = ctx->d_bt_chunk0.as<int32_t>();
+    bt.n_chunks = ctx->n_chunks;
+    bt.cstatus = ctx->d_cstatus.as<uint32_t>();
     bt.ticket = ctx->d_ticket.as<uint32_t>();
     bt.passes_run = reinterpret_cast<int32_t*>(ctx->d_ticket.as<uint32_t>() + N_PASS);
     bt.pass_any = ctx->d_ticket.as<uint32_t>() + N_PASS + 1;
     return bt;
 }
 
-int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_offsets* offs) {
+int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_offsets* offs, bool defer_data = false) {
     if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
     ctx->uploaded = ctx->executed = false;
     ctx->stats = lagassign_stats{};
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    std::vector<int32_t> l_warp, l_cta, l_none, bt_topic, bt_tile0, tile_bt, l_fill;
+    std::vector<int32_t> l_warp, l_cta, l_none, bt_topic, bt_tile0, tile_bt, l_fill, bt_chunk0;
     std::vector<int64_t> bt_off, bt_P, bt_boff, tc_off;
     lagassign_batch tmp;
     if (offs) {
@@ -287,7 +299,7 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
         tmp.lag = &dummy;   // not dereferenced by the planner
         in = &tmp;
     }
-    TRY(validate_and_plan(ctx, in, l_warp, l_cta, l_none, bt_topic, bt_off, bt_P, bt_boff, bt_tile0, tile_bt, l_fill, tc_off));
+    TRY(validate_and_plan(ctx, in, l_warp, l_cta, l_none, bt_topic, bt_off, bt_P, bt_boff, bt_tile0, tile_bt, l_fill, tc_off, bt_chunk0));
     const int64_t T = ctx->T, N = ctx->N;
     ctx->has_part = in->partition != nullptr;
     ctx->has_offsets = offs != nullptr;
@@ -302,10 +314,13 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
         TRY(upload_vec(ctx, ctx->d_committed, offs->committed, (size_t)N));
         TRY(upload_vec(ctx, ctx->d_hascommitted, offs->has_committed, (size_t)N));
         CUDA_TRY(ctx, ctx->d_lag.ensure(std::max<size_t>((size_t)N, 1) * sizeof(int64_t)));
+    } else if (defer_data) {
+        CUDA_TRY(ctx, ctx->d_lag.ensure(std::max<size_t>((size_t)N, 1) * sizeof(int64_t)));
+        if (ctx->has_part) CUDA_TRY(ctx, ctx->d_part.ensure(std::max<size_t>((size_t)N, 1) * sizeof(int32_t)));
     } else {
         TRY(upload_vec(ctx, ctx->d_lag, in->lag, (size_t)N));
     }
-    if (ctx->has_part) TRY(upload_vec(ctx, ctx->d_part, in->partition, (size_t)N));
+    if (ctx->has_part && !defer_data) TRY(upload_vec(ctx, ctx->d_part, in->partition, (size_t)N));
     TRY(upload_vec(ctx, ctx->d_topic_cset, in->topic_cset, (size_t)T));
     TRY(upload_vec(ctx, ctx->d_cset_off, in->cset_off, (size_t)ctx->S + 1));
     TRY(upload_vec(ctx, ctx->d_cset_rank, in->cset_rank, (size_t)ctx->R));
@@ -319,6 +334,7 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
     TRY(upload_vec(ctx, ctx->d_bt_P, bt_P.data(), bt_P.size()));
     TRY(upload_vec(ctx, ctx->d_bt_boff, bt_boff.data(), bt_boff.size()));
     TRY(upload_vec(ctx, ctx->d_bt_tile0, bt_tile0.data(), bt_tile0.size()));
+    TRY(upload_vec(ctx, ctx->d_bt_chunk0, bt_chunk0.data(), bt_chunk0.size()));
     TRY(upload_vec(ctx, ctx->d_tile_bt, tile_bt.data(), tile_bt.size()));
 
     // outputs and workspaces
@@ -340,6 +356,7 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
         CUDA_TRY(ctx, ctx->d_sel.ensure((size_t)ctx->n_big * (2 * N_PASS + 1)));
         CUDA_TRY(ctx, ctx->d_need_tie.ensure((size_t)ctx->n_big * sizeof(int32_t)));
         CUDA_TRY(ctx, ctx->d_status.ensure((size_t)N_PASS * ctx->n_tiles * 256 * sizeof(uint32_t)));
+        CUDA_TRY(ctx, ctx->d_cstatus.ensure((size_t)N_PASS * ctx->n_chunks * 256 * sizeof(uint32_t)));
         CUDA_TRY(ctx, ctx->d_ticket.ensure((2 * N_PASS + 1) * sizeof(uint32_t)));
     }
     // the host vectors above must outlive the copies; also honours "the library
@@ -352,7 +369,105 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
     ctx->stats.topics_device = ctx->n_big;
     ctx->stats.topics_unassigned = ctx->n_none;
     ctx->stats.device_sort_elems = ctx->big_elems;
+    ctx->h_list_warp.swap(l_warp);
+    ctx->h_list_cta.swap(l_cta);
+    ctx->h_list_none.swap(l_none);
+    ctx->uploaded = !defer_data;
+    return LAGASSIGN_OK;
+}
+
+// Upload of the two large arrays when do_upload() was asked to defer them.
+int upload_data_now(lagassign_ctx* ctx, const lagassign_batch* in) {
+    const size_t N = (size_t)ctx->N;
+    if (N) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_lag.p, in->lag, N * 8, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->stats.h2d_bytes += (int64_t)N * 8;
+        if (ctx->has_part) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_part.p, in->partition, N * 4, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->stats.h2d_bytes += (int64_t)N * 4;
+        }
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     ctx->uploaded = true;
+    return LAGASSIGN_OK;
+}
+
+constexpr int64_t PIPE_MIN_ELEMS = 1 << 21;      // below this one copy each way is as good
+constexpr int64_t PIPE_CHUNK_ELEMS = 3 << 20;    // ~24 MB of lags per chunk
+
+// lagassign_assign_batch for batches made of on-chip topics only: the batch is cut
+// into contiguous topic ranges and the three legs (H2D of the lags, kernels, D2H of
+// the results) of successive chunks overlap on three streams. PCIe is full duplex,
+// so the call approaches max(H2D, D2H) instead of their sum.
+int assign_batch_pipelined(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_result* out) {
+    if (!ctx->stream_in) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking));
+    }
+    const int64_t N = ctx->N, T = ctx->T;
+    const int K = (int)std::min<int64_t>(64, std::max<int64_t>(2, (N + PIPE_CHUNK_ELEMS - 1) / PIPE_CHUNK_ELEMS));
+    while ((int)ctx->pipe_events.size() < 2 * K) {
+        cudaEvent_t e = nullptr;
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->pipe_events.push_back(e);
+    }
+    DevBatch b = make_dev_batch(ctx);
+    const int32_t* src_part = b.out_part;
+    const int32_t* src_cons = b.out_cons;
+    int launches = 0;
+    int64_t t_lo = 0;
+    ctx->stats.d2h_bytes = 0;
+    for (int c = 0; c < K; ++c) {
+        int64_t t_hi = T;
+        if (c + 1 < K) {
+            const int64_t target = N / K * (c + 1);
+            t_hi = std::lower_bound(in->topic_off, in->topic_off + T + 1, target) - in->topic_off;
+            t_hi = std::min<int64_t>(std::max(t_hi, t_lo), T);
+        }
+        const int64_t e0 = in->topic_off[t_lo], e1 = in->topic_off[t_hi];
+        const size_t n = (size_t)(e1 - e0);
+        cudaEvent_t ev_in = ctx->pipe_events[2 * c], ev_out = ctx->pipe_events[2 * c + 1];
+        if (n) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_lag.as<int64_t>() + e0, in->lag + e0, n * 8, cudaMemcpyHostToDevice, ctx->stream_in));
+            ctx->stats.h2d_bytes += (int64_t)n * 8;
+            if (ctx->has_part) {
+                CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_part.as<int32_t>() + e0, in->partition + e0, n * 4, cudaMemcpyHostToDevice, ctx->stream_in));
+                ctx->stats.h2d_bytes += (int64_t)n * 4;
+            }
+        }
+        CUDA_TRY(ctx, cudaEventRecord(ev_in, ctx->stream_in));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ev_in, 0));
+        auto slice = [&](const std::vector<int32_t>& v, int& lo, int& hi) {
+            lo = (int)(std::lower_bound(v.begin(), v.end(), (int32_t)t_lo) - v.begin());
+            hi = (int)(std::lower_bound(v.begin(), v.end(), (int32_t)t_hi) - v.begin());
+        };
+        int lo, hi;
+        slice(ctx->h_list_none, lo, hi);
+        if (hi > lo) { launch_unassigned_topics(b, ctx->d_list_none.as<int32_t>() + lo, hi - lo, ctx->stream); ++launches; }
+        slice(ctx->h_list_warp, lo, hi);
+        if (hi > lo) { launch_warp_topics(b, ctx->d_list_warp.as<int32_t>() + lo, hi - lo, ctx->stream); ++launches; }
+        slice(ctx->h_list_cta, lo, hi);
+        if (hi > lo) { launch_cta_topics(b, ctx->d_list_cta.as<int32_t>() + lo, hi - lo, ctx->sm_count, ctx->stream); ++launches; }
+        CUDA_TRY(ctx, cudaEventRecord(ev_out, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_out, ev_out, 0));
+        if (n && out->out_partition) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(out->out_partition + e0, src_part + e0, n * 4, cudaMemcpyDeviceToHost, ctx->stream_out));
+            ctx->stats.d2h_bytes += (int64_t)n * 4;
+        }
+        if (n && out->out_consumer_rank) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(out->out_consumer_rank + e0, src_cons + e0, n * 4, cudaMemcpyDeviceToHost, ctx->stream_out));
+            ctx->stats.d2h_bytes += (int64_t)n * 4;
+        }
+        t_lo = t_hi;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream_out));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.kernel_launches = launches;
+    ctx->uploaded = true;
+    ctx->executed = true;
+    ctx->prof.clear();
+    ctx->prof_resolved = true;
     return LAGASSIGN_OK;
 }
 
@@ -424,10 +539,13 @@ void lagassign_destroy(lagassign_ctx* ctx) {
                       &ctx->d_list_fill, &ctx->d_bt_topic, &ctx->d_bt_off, &ctx->d_bt_P, &ctx->d_bt_boff,
                       &ctx->d_bt_tile0, &ctx->d_tile_bt, &ctx->d_keyA, &ctx->d_keyB, &ctx->d_payA,
                       &ctx->d_payB, &ctx->d_ghist, &ctx->d_gbase, &ctx->d_sel, &ctx->d_need_tie,
-                      &ctx->d_status, &ctx->d_ticket, &ctx->d_out_part, &ctx->d_out_cons,
+                      &ctx->d_status, &ctx->d_cstatus, &ctx->d_bt_chunk0, &ctx->d_ticket, &ctx->d_out_part, &ctx->d_out_cons,
                       &ctx->d_out_total, &ctx->d_out_count};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->pipe_events) cudaEventDestroy(e);
+    if (ctx->stream_in) cudaStreamDestroy(ctx->stream_in);
+    if (ctx->stream_out) cudaStreamDestroy(ctx->stream_out);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -502,7 +620,12 @@ int lagassign_execute(lagassign_ctx* ctx) {
         const size_t hb = (size_t)ctx->n_big * N_PASS * 256 * sizeof(uint32_t);
         CUDA_TRY(ctx, cudaMemsetAsync(bt.ghist, 0, hb, st));
         CUDA_TRY(ctx, cudaMemsetAsync(bt.need_tie, 0, (size_t)ctx->n_big * sizeof(int32_t), st));
-        CUDA_TRY(ctx, cudaMemsetAsync(bt.status, 0, (size_t)N_PASS * ctx->n_tiles * 256 * sizeof(uint32_t), st));
+        {   // look-back words of the passes that can run (tie passes only with explicit ids)
+            const int fp = ctx->has_part ? 0 : N_TIE_PASS;
+            const size_t per_pass = (size_t)ctx->n_tiles * 256, cper_pass = (size_t)ctx->n_chunks * 256;
+            CUDA_TRY(ctx, cudaMemsetAsync(bt.status + fp * per_pass, 0, (N_PASS - fp) * per_pass * sizeof(uint32_t), st));
+            CUDA_TRY(ctx, cudaMemsetAsync(bt.cstatus + fp * cper_pass, 0, (N_PASS - fp) * cper_pass * sizeof(uint32_t), st));
+        }
         CUDA_TRY(ctx, cudaMemsetAsync(bt.ticket, 0, (2 * N_PASS + 1) * sizeof(uint32_t), st));
         const int first_pass = ctx->has_part ? 0 : N_TIE_PASS;
         if (ctx->has_part) {
@@ -587,7 +710,12 @@ int lagassign_download(lagassign_ctx* ctx, const lagassign_result* out) {
 }
 
 int lagassign_assign_batch(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_result* out) {
-    TRY(lagassign_upload(ctx, in));
+    if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
+    if (!out) return fail(ctx, LAGASSIGN_ERR_ARG, "result is NULL");
+    TRY(do_upload(ctx, in, nullptr, /*defer_data=*/true));     // plan + metadata; the large arrays follow
+    if (ctx->n_big == 0 && !ctx->want_totals && ctx->N >= PIPE_MIN_ELEMS && !out->out_total && !out->out_count)
+        return assign_batch_pipelined(ctx, in, out);
+    TRY(upload_data_now(ctx, in));
     TRY(lagassign_execute(ctx));
     return lagassign_download(ctx, out);
 }

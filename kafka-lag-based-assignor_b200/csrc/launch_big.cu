@@ -35,9 +35,13 @@ void launch_big_scan(const BigTopics& bt, int first_pass, cudaStream_t st) {
 }
 
 void launch_big_pass(const BigTopics& bt, int pass, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st) {
+    // exactly one resident wave, launched cooperatively so that co-residency (which the
+    // static tile striding relies on) is checked by the runtime instead of assumed
     const int grid = std::min(bt.n_tiles, sms * std::max(1, g_pass_ctas_per_sm[part ? 1 : 0]));
-    if (part) k_big_pass<true><<<grid, RT_THREADS, sizeof(PassSmem), st>>>(bt, pass, lag, part);
-    else k_big_pass<false><<<grid, RT_THREADS, sizeof(PassSmem), st>>>(bt, pass, lag, nullptr);
+    BigTopics bt_arg = bt;
+    void* args[] = {&bt_arg, &pass, &lag, &part};
+    const void* fn = part ? (const void*)k_big_pass<true> : (const void*)k_big_pass<false>;
+    cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(RT_THREADS), args, sizeof(PassSmem), st);
 }
 
 void launch_big_finalize(const BigTopics& bt, const DevBatch& b, int sms, cudaStream_t st) {

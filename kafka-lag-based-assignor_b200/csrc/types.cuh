@@ -23,13 +23,13 @@ struct DevBatch {
 };
 
 #ifndef LAGASSIGN_RT_THREADS
-#define LAGASSIGN_RT_THREADS 512
+#define LAGASSIGN_RT_THREADS 256
 #endif
 #ifndef LAGASSIGN_RT_IPT
 #define LAGASSIGN_RT_IPT 8
 #endif
 #ifndef LAGASSIGN_RT_MINBLOCKS
-#define LAGASSIGN_RT_MINBLOCKS 2
+#define LAGASSIGN_RT_MINBLOCKS 3
 #endif
 constexpr int RT_THREADS = LAGASSIGN_RT_THREADS;
 constexpr int RT_IPT = LAGASSIGN_RT_IPT;
@@ -39,6 +39,7 @@ constexpr int N_TIE_PASS = 4;
 constexpr int N_LAG_PASS = 8;
 constexpr int N_PASS = N_TIE_PASS + N_LAG_PASS;
 
+constexpr int RT_CHUNK = 16;            // tiles per look-back chunk
 constexpr uint32_t ST_AGG = 1u << 30;   // tile's own count is published
 constexpr uint32_t ST_INC = 2u << 30;   // inclusive prefix over the topic's tiles so far
 constexpr uint32_t ST_VAL = (1u << 30) - 1;
@@ -62,7 +63,10 @@ struct BigTopics {
     int8_t* sel_dst;           // [B][N_PASS]
     int8_t* sel_final;         // [B] where the sorted data of the topic ended up
     int32_t* need_tie;         // [B] partition ids not ascending
-    uint32_t* status;          // [N_PASS][G][256] look-back words (zeroed per execute)
+    uint32_t* status;          // [N_PASS][G][256] per-tile digit counts for the look-back (zeroed per execute)
+    const int32_t* chunk0;     // [B] first look-back chunk of the topic (chunks of RT_CHUNK tiles)
+    int n_chunks;
+    uint32_t* cstatus;         // [N_PASS][n_chunks][256] per-chunk aggregate / inclusive prefix
     uint32_t* ticket;          // [N_PASS] dynamic tile ids (zeroed per execute)
     int32_t* passes_run;       // [1] max over topics of executed passes (stat)
     uint32_t* pass_any;        // [N_PASS] does any topic run this pass? (else the launch returns at once)

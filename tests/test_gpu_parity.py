@@ -189,6 +189,34 @@ def test_mixed_bins_and_edge_topics(flat):
     assert st["kernel_launches"] > 0
 
 
+def test_chunked_pipeline_path(pkg):
+    """Large batches of on-chip topics go through the chunked H2D / kernel / D2H pipeline
+    of lagassign_assign_batch(); same answer as the oracle, pinned or pageable buffers."""
+    rng = np.random.default_rng(77)
+    b = random_flat(rng, T=30000, pmin=0, pmax=600, C=40, lag_kind="small", explicit_ids="shuffled", n_sets=4)
+    assert len(b["lag"]) > (1 << 22)
+    exp = oracle.assign_batch(*args_of(b), threads=8)
+    with pkg.FlatAssignor(0) as f:
+        got = f.assign_batch(*args_of(b))
+        st = f.stats()
+        assert st["topics_device"] == 0 and st["kernel_launches"] >= 4     # several chunks
+        assert np.array_equal(got["out_partition"], exp["out_partition"])
+        assert np.array_equal(got["out_consumer_rank"], exp["out_consumer_rank"])
+        # pinned buffers, implicit ids
+        b2 = dict(b, partition=None)
+        exp2 = oracle.assign_batch(*args_of(b2), threads=8)
+        lag = pkg.pinned_empty(len(b2["lag"]), np.int64)
+        lag[:] = b2["lag"]
+        op = pkg.pinned_empty(len(lag), np.int32)
+        oc = pkg.pinned_empty(len(lag), np.int32)
+        f.assign_batch(b2["topic_off"], lag, None, b2["topic_cset"], b2["cset_off"], b2["cset_rank"], op, oc)
+        assert np.array_equal(op, exp2["out_partition"]) and np.array_equal(oc, exp2["out_consumer_rank"])
+        # execute() again on what the pipeline left resident gives the same result
+        f.execute()
+        again = f.download()
+        assert np.array_equal(again["out_partition"], exp2["out_partition"])
+
+
 def test_single_consumer_and_single_partition(flat):
     rng = np.random.default_rng(9)
     for P, C in ((1, 1), (1, 5000), (257, 1), (5000, 1), (70000, 1), (70000, 2)):
