@@ -324,10 +324,13 @@ def main():
         dom_name, (dom_ms, dom_n) = dom[0], dom[1]
         step_ms = t_compute_ms / args.steps
         share = dom_ms / max(sum(v[0] for v in prof_acc.values()), 1e-12)
-        if dom_name == "k_big_pass":
-            # 64-bit key + 32-bit payload read and written once per executed pass
+        if dom_name == "k_big_scatter":
+            # 64-bit key + 32-bit payload read and written once per executed digit pass
             alg = 24 * stats["device_sort_elems"]
-            alg_note = "24 B x elements per radix pass launch"
+            alg_note = "24 B x elements per scatter launch (one launch per executed digit pass)"
+        elif dom_name == "k_big_tile_hist":
+            alg = 8 * stats["device_sort_elems"]
+            alg_note = "8 B x elements per per-tile histogram launch"
         elif dom_name in ("k_warp_topics", "k_cta_topics"):
             alg = local_alg_bytes
             alg_note = "16 B/partition (+4 B explicit ids) + 12 B/topic, whole step in one launch"

@@ -41,6 +41,7 @@ __device__ __forceinline__ void warp_round_fill(int64_t P, int C, const int32_t*
         cid[r] = live ? (uint32_t)j : PAY_SENTINEL;
         lag_cur[r] = (live && j < P) ? lag_at((int64_t)j) : 0;
     }
+    bool prev_equal = false;
     for (int64_t base = 0; base < P; base += C) {
         // issue next round's loads before the dependent sort
         int64_t lag_nxt[EPTC];
@@ -50,7 +51,20 @@ __device__ __forceinline__ void warp_round_fill(int64_t P, int C, const int32_t*
             int64_t k = base + C + j;
             lag_nxt[r] = (j < C && k < P) ? lag_at(k) : 0;
         }
-        if (base > 0) warp_bitonic_sort<EPTC>(tkey, cid);  // round 0: all totals 0, already in id order
+        // first and last lag of THIS round, fetched now and compared after the round: were all its lags equal?
+        const int64_t eq_a = lag_at(base), eq_b = lag_at(min(base + (int64_t)C - 1, P - 1));
+        // Round 0 starts in id order with all totals 0. After a round that added the same
+        // lag to everyone (lags are sorted, so: first == last of the round; typically an idle
+        // topic with zero lag everywhere) the order usually survives: test before sorting.
+        if (base > 0) {
+            bool ok = prev_equal;
+#pragma unroll
+            for (int r = 0; r + 1 < EPTC; ++r) ok = ok && !elem_less(tkey[r + 1], cid[r + 1], tkey[r], cid[r]);
+            const uint64_t nk = __shfl_down_sync(0xffffffffu, tkey[0], 1);
+            const uint32_t nc = __shfl_down_sync(0xffffffffu, cid[0], 1);
+            if (lane < 31) ok = ok && !elem_less(nk, nc, tkey[EPTC - 1], cid[EPTC - 1]);
+            if (!__all_sync(0xffffffffu, ok)) warp_bitonic_sort<EPTC>(tkey, cid);
+        }
 #pragma unroll
         for (int r = 0; r < EPTC; ++r) {
             int j = (int)lane * EPTC + r;
@@ -60,6 +74,7 @@ __device__ __forceinline__ void warp_round_fill(int64_t P, int C, const int32_t*
             }
             lag_cur[r] = lag_nxt[r];
         }
+        prev_equal = (base + C <= P) && (eq_a == eq_b);
     }
     if (out_total != nullptr) {
         const int64_t full = P / C;
@@ -155,6 +170,7 @@ __device__ __forceinline__ void cta_round_fill_regs(int64_t P, int C, const int3
         w[0][r] = live ? (uint32_t)j : PAY_SENTINEL;
         lag_cur[r] = (live && j < P) ? lag_at((int64_t)j) : 0;
     }
+    bool prev_equal = false;
     for (int64_t base = 0; base < P; base += C) {
         int64_t lag_nxt[EPT];
 #pragma unroll
@@ -163,7 +179,27 @@ __device__ __forceinline__ void cta_round_fill_regs(int64_t P, int C, const int3
             const int64_t k = base + C + j;
             lag_nxt[r] = (j < C && k < P) ? lag_at(k) : 0;
         }
-        if (base > 0) cta_bitonic_sort_regs<EPT, NT>(w, xbuf);
+        // first and last lag of THIS round, fetched now and compared after the round: were all its lags equal?
+        const int64_t eq_a = lag_at(base), eq_b = lag_at(min(base + (int64_t)C - 1, P - 1));
+        if (base > 0) {
+            // After a round that added the same lag to every consumer (first == last lag of the
+            // round; typically zero) the (total, id) order usually survives: then skip the sort.
+            bool skip = false;
+            if (prev_equal) {      // uniform across the CTA
+                bool ok = true;
+#pragma unroll
+                for (int r = 0; r + 1 < EPT; ++r)
+                    ok = ok && !lt3(w[2][r + 1], w[1][r + 1], w[0][r + 1], w[2][r], w[1][r], w[0][r]);
+                // first element of the next thread (through shared memory: it may be in another warp)
+                __syncthreads();
+                xbuf[tid] = w[0][0]; xbuf[NT + tid] = w[1][0]; xbuf[2 * NT + tid] = w[2][0];
+                __syncthreads();
+                if (tid + 1 < NT)
+                    ok = ok && !lt3(xbuf[2 * NT + tid + 1], xbuf[NT + tid + 1], xbuf[tid + 1], w[2][EPT - 1], w[1][EPT - 1], w[0][EPT - 1]);
+                skip = __syncthreads_and(ok) != 0;
+            }
+            if (!skip) cta_bitonic_sort_regs<EPT, NT>(w, xbuf);
+        }
 #pragma unroll
         for (int r = 0; r < EPT; ++r) {
             const int j = tid * EPT + r;
@@ -176,6 +212,7 @@ __device__ __forceinline__ void cta_round_fill_regs(int64_t P, int C, const int3
             }
             lag_cur[r] = lag_nxt[r];
         }
+        prev_equal = (base + C <= P) && (eq_a == eq_b);
     }
     if (out_total != nullptr) {
         const int64_t full = P / C;

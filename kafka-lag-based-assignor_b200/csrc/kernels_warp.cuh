@@ -67,8 +67,10 @@ __device__ __noinline__ void warp_sort_general(uint64_t (&key)[EPT], uint32_t (&
     warp_bitonic_sort<EPT>(key, pay);
 }
 
+// Returns true when key[] holds the sorted keys on return; false when only pay[] (the
+// sorted positions) is valid, which happens on the truncated path below.
 template <int EPT>
-__device__ __forceinline__ void warp_sort_adaptive(uint64_t (&key)[EPT], uint32_t (&pay)[EPT], int P) {
+__device__ __forceinline__ bool warp_sort_adaptive(uint64_t (&key)[EPT], uint32_t (&pay)[EPT], int P, bool allow_trunc) {
     constexpr int B = Log2Slots<EPT>::value;
     const unsigned lane = lane_id();
     const uint64_t ref = __shfl_sync(0xffffffffu, key[0], 0);   // element 0 is live (P >= 1)
@@ -78,7 +80,6 @@ __device__ __forceinline__ void warp_sort_adaptive(uint64_t (&key)[EPT], uint32_
     const uint32_t xlo = __reduce_or_sync(0xffffffffu, (uint32_t)x);
     const uint32_t xhi = __reduce_or_sync(0xffffffffu, (uint32_t)(x >> 32));
     const int s = xhi ? 64 - __clz(xhi) : (xlo ? 32 - __clz(xlo) : 0);   // bits in which keys differ
-    (void)lane; (void)P;
     if (s + B <= 32) {
         const uint32_t mask = s ? (0xFFFFFFFFu >> (32 - s)) : 0u;   // s <= 27
         uint32_t w[1][EPT];
@@ -92,7 +93,37 @@ __device__ __forceinline__ void warp_sort_adaptive(uint64_t (&key)[EPT], uint32_
             pay[r] = w[0][r] & ((1u << B) - 1u);
             key[r] = hi | (uint64_t)(w[0][r] >> B);
         }
-    } else if (s + B <= 64) {
+        return true;
+    }
+    if (allow_trunc) {
+        // Optimistic one-word sort on the TOP 32-B of the s differing key bits. If no two
+        // neighbours of the result share that truncated key, the order is already the exact
+        // (key, position) order: for high-entropy lags (random 40-bit values, 256 per topic)
+        // that is ~99.8 % of topics, at a third of the instructions of the 64-bit sort.
+        // Otherwise fall through to the exact sort; key[] / pay[] are still untouched.
+        constexpr int KB = 32 - B;
+        const int sh = s - KB;                       // s > KB here
+        uint32_t w[1][EPT];
+#pragma unroll
+        for (int r = 0; r < EPT; ++r)
+            w[0][r] = (pay[r] != PAY_SENTINEL)
+                          ? ((((uint32_t)(key[r] >> sh) & ((1u << KB) - 1u)) << B) | pay[r]) : 0xFFFFFFFFu;
+        warp_bitonic_sort_words<1, EPT>(w);
+        bool dup = false;
+#pragma unroll
+        for (int r = 0; r + 1 < EPT; ++r) {
+            const int i = (int)lane * EPT + r;
+            dup |= (i + 1 < P) && ((w[0][r] >> B) == (w[0][r + 1] >> B));
+        }
+        const uint32_t nxt = __shfl_down_sync(0xffffffffu, w[0][0], 1);
+        dup |= (lane < 31) && ((int)lane * EPT + EPT < P) && ((w[0][EPT - 1] >> B) == (nxt >> B));
+        if (!__any_sync(0xffffffffu, dup)) {
+#pragma unroll
+            for (int r = 0; r < EPT; ++r) pay[r] = w[0][r] & ((1u << B) - 1u);
+            return false;
+        }
+    }
+    if (s + B <= 64) {
         const uint64_t mask = ~0ull >> (64 - s);   // 1 <= s <= 59
         uint32_t w[2][EPT];
 #pragma unroll
@@ -112,6 +143,7 @@ __device__ __forceinline__ void warp_sort_adaptive(uint64_t (&key)[EPT], uint32_
     } else {
         warp_sort_general<EPT>(key, pay);
     }
+    return true;
 }
 
 __device__ __noinline__ void warp_rounds_path(int P, int C, const int32_t* __restrict__ cset, WarpScratch& ws,
@@ -160,7 +192,7 @@ __device__ __forceinline__ void warp_topic(const DevBatch& b, int t, WarpScratch
                 k2[r] = live ? (uint64_t)((uint32_t)b.part[off + m] ^ 0x80000000u) : KEY_SENTINEL;
                 p2[r] = live ? (uint32_t)m : PAY_SENTINEL;
             }
-            warp_sort_adaptive<EPT>(k2, p2, P);
+            warp_sort_adaptive<EPT>(k2, p2, P, /*allow_trunc=*/false);
 #pragma unroll
             for (int r = 0; r < EPT; ++r) {
                 int i = (int)lane * EPT + r;
@@ -174,7 +206,8 @@ __device__ __forceinline__ void warp_topic(const DevBatch& b, int t, WarpScratch
         }
     }
 
-    warp_sort_adaptive<EPT>(key, pay, P);     // Main:228-235
+    // Main:228-235 (pay is the list position here unless the ids had to be ordered first)
+    const bool keys_exact = warp_sort_adaptive<EPT>(key, pay, P, /*allow_trunc=*/!use_tab);
 
     // out_partition, staged through shared memory so the global store is coalesced
     {
@@ -197,7 +230,7 @@ __device__ __forceinline__ void warp_topic(const DevBatch& b, int t, WarpScratch
 #pragma unroll
         for (int r = 0; r < EPT; ++r) {
             int i = (int)lane * EPT + r;
-            if (i < P) ws.lag_key[i] = key[r];
+            if (i < P) ws.lag_key[i] = keys_exact ? key[r] : ((uint64_t)b.lag[off + pay[r]] ^ LAG_KEY_MASK);
         }
     }
     __syncwarp();

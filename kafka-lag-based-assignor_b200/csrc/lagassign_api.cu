@@ -56,11 +56,12 @@ k_compute_lag(int64_t n, const int64_t* __restrict__ begin_off, const int64_t* _
 
 }  // namespace
 
-enum KernelKind { K_COMPUTE_LAG = 0, K_UNASSIGNED, K_WARP, K_CTA, K_ORDER, K_HIST, K_SCAN, K_PASS, K_FINALIZE,
-                  K_FILL, K_KINDS };
+enum KernelKind { K_COMPUTE_LAG = 0, K_UNASSIGNED, K_WARP, K_CTA, K_ORDER, K_HIST, K_SCAN, K_TILE_HIST, K_PASS_SCANS,
+                  K_SCATTER, K_FINALIZE, K_FILL, K_KINDS };
 static const char* const kKernelNames[K_KINDS] = {"k_compute_lag", "k_unassigned_topics", "k_warp_topics",
                                                   "k_cta_topics", "k_big_order_check", "k_big_hist",
-                                                  "k_big_scan", "k_big_pass", "k_big_finalize", "k_big_fill"};
+                                                  "k_big_scan", "k_big_tile_hist", "k_big_seg_scan+k_big_topic_scan",
+                                                  "k_big_scatter", "k_big_finalize", "k_big_fill"};
 struct ProfRec { int kind; cudaEvent_t a, b; };
 
 struct lagassign_ctx {
@@ -90,8 +91,8 @@ struct lagassign_ctx {
     DevBuf d_begin, d_end, d_committed, d_hascommitted;
     // plan lists
     DevBuf d_list_warp, d_list_cta, d_list_none, d_list_fill;
-    DevBuf d_bt_topic, d_bt_off, d_bt_P, d_bt_boff, d_bt_tile0, d_bt_chunk0, d_tile_bt, d_cstatus;
-    int n_chunks = 0;
+    DevBuf d_bt_topic, d_bt_off, d_bt_P, d_bt_boff, d_bt_tile0, d_bt_seg0, d_tile_bt, d_seg_bt, d_seg_total, d_tile_desc;
+    int n_segs = 0;
     // radix workspaces
     DevBuf d_keyA, d_keyB, d_payA, d_payB, d_ghist, d_gbase, d_sel, d_need_tie, d_status, d_ticket;
     // outputs
@@ -168,7 +169,8 @@ int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
                       std::vector<int32_t>& l_warp, std::vector<int32_t>& l_cta, std::vector<int32_t>& l_none,
                       std::vector<int32_t>& bt_topic, std::vector<int64_t>& bt_off, std::vector<int64_t>& bt_P,
                       std::vector<int64_t>& bt_boff, std::vector<int32_t>& bt_tile0, std::vector<int32_t>& tile_bt,
-                      std::vector<int32_t>& l_fill, std::vector<int64_t>& tc_off, std::vector<int32_t>& bt_chunk0) {
+                      std::vector<int32_t>& l_fill, std::vector<int64_t>& tc_off, std::vector<int32_t>& bt_seg0,
+                      std::vector<int32_t>& seg_bt, std::vector<TileDesc>& tile_desc) {
     if (!in) return fail(ctx, LAGASSIGN_ERR_ARG, "batch is NULL");
     const int64_t T = in->n_topics, S = in->n_csets;
     if (T < 0 || S < 0) return fail(ctx, LAGASSIGN_ERR_ARG, "negative n_topics / n_csets");
@@ -195,7 +197,7 @@ int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
     if (T > 0 && !in->topic_cset) return fail(ctx, LAGASSIGN_ERR_ARG, "topic_cset is NULL");
 
     tc_off.assign((size_t)T + 1, 0);
-    ctx->n_chunks = 0;
+    ctx->n_segs = 0;
     int64_t boff = 0, tiles = 0, assigned = 0;
     for (int64_t t = 0; t < T; ++t) {
         const int32_t s = in->topic_cset[t];
@@ -222,9 +224,21 @@ int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
             bt_P.push_back(P);
             bt_boff.push_back(boff);
             bt_tile0.push_back((int32_t)tiles);
-            bt_chunk0.push_back((int32_t)ctx->n_chunks);
-            ctx->n_chunks += (int)((nt + RT_CHUNK - 1) / RT_CHUNK);
-            for (int64_t k = 0; k < nt; ++k) tile_bt.push_back(b);
+            bt_seg0.push_back((int32_t)ctx->n_segs);
+            const int nseg = (int)((nt + RT_SEG - 1) / RT_SEG);
+            for (int k = 0; k < nseg; ++k) seg_bt.push_back(b);
+            ctx->n_segs += nseg;
+            for (int64_t k = 0; k < nt; ++k) {
+                tile_bt.push_back(b);
+                TileDesc d;
+                d.b = b;
+                d.tile_in_topic = (int32_t)k;
+                d.n_valid = (int32_t)std::min<int64_t>(RT_TILE, P - k * RT_TILE);
+                d.seg = (int32_t)(bt_seg0.back() + k / RT_SEG);
+                d.buf_off = boff + k * RT_TILE;
+                d.raw_off = in->topic_off[t] + k * RT_TILE;
+                tile_desc.push_back(d);
+            }
             if (P > C) l_fill.push_back(b);
             boff += P;
             tiles += nt;
@@ -263,6 +277,7 @@ BigTopics make_big(lagassign_ctx* ctx) {
     bt.boff = ctx->d_bt_boff.as<int64_t>();
     bt.tile0 = ctx->d_bt_tile0.as<int32_t>();
     bt.tile_bt = ctx->d_tile_bt.as<int32_t>();
+    bt.tile_desc = ctx->d_tile_desc.as<int4>();
     bt.keyA = ctx->d_keyA.as<uint64_t>(); bt.keyB = ctx->d_keyB.as<uint64_t>();
     bt.payA = ctx->d_payA.as<uint32_t>(); bt.payB = ctx->d_payB.as<uint32_t>();
     bt.ghist = ctx->d_ghist.as<uint32_t>();
@@ -272,10 +287,11 @@ BigTopics make_big(lagassign_ctx* ctx) {
     bt.sel_dst = sel + (size_t)ctx->n_big * N_PASS;
     bt.sel_final = sel + (size_t)ctx->n_big * N_PASS * 2;
     bt.need_tie = ctx->d_need_tie.as<int32_t>();
-    bt.status = ctx->d_status.as<uint32_t>();
-    bt.chunk0 = ctx->d_bt_chunk0.as<int32_t>();
-    bt.n_chunks = ctx->n_chunks;
-    bt.cstatus = ctx->d_cstatus.as<uint32_t>();
+    bt.tile_hist = ctx->d_status.as<uint32_t>();
+    bt.seg0 = ctx->d_bt_seg0.as<int32_t>();
+    bt.seg_bt = ctx->d_seg_bt.as<int32_t>();
+    bt.n_segs = ctx->n_segs;
+    bt.seg_total = ctx->d_seg_total.as<uint32_t>();
     bt.ticket = ctx->d_ticket.as<uint32_t>();
     bt.passes_run = reinterpret_cast<int32_t*>(ctx->d_ticket.as<uint32_t>() + N_PASS);
     bt.pass_any = ctx->d_ticket.as<uint32_t>() + N_PASS + 1;
@@ -287,7 +303,8 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
     ctx->uploaded = ctx->executed = false;
     ctx->stats = lagassign_stats{};
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    std::vector<int32_t> l_warp, l_cta, l_none, bt_topic, bt_tile0, tile_bt, l_fill, bt_chunk0;
+    std::vector<int32_t> l_warp, l_cta, l_none, bt_topic, bt_tile0, tile_bt, l_fill, bt_seg0, seg_bt;
+    std::vector<TileDesc> tile_desc;
     std::vector<int64_t> bt_off, bt_P, bt_boff, tc_off;
     lagassign_batch tmp;
     if (offs) {
@@ -299,7 +316,7 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
         tmp.lag = &dummy;   // not dereferenced by the planner
         in = &tmp;
     }
-    TRY(validate_and_plan(ctx, in, l_warp, l_cta, l_none, bt_topic, bt_off, bt_P, bt_boff, bt_tile0, tile_bt, l_fill, tc_off, bt_chunk0));
+    TRY(validate_and_plan(ctx, in, l_warp, l_cta, l_none, bt_topic, bt_off, bt_P, bt_boff, bt_tile0, tile_bt, l_fill, tc_off, bt_seg0, seg_bt, tile_desc));
     const int64_t T = ctx->T, N = ctx->N;
     ctx->has_part = in->partition != nullptr;
     ctx->has_offsets = offs != nullptr;
@@ -334,7 +351,9 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
     TRY(upload_vec(ctx, ctx->d_bt_P, bt_P.data(), bt_P.size()));
     TRY(upload_vec(ctx, ctx->d_bt_boff, bt_boff.data(), bt_boff.size()));
     TRY(upload_vec(ctx, ctx->d_bt_tile0, bt_tile0.data(), bt_tile0.size()));
-    TRY(upload_vec(ctx, ctx->d_bt_chunk0, bt_chunk0.data(), bt_chunk0.size()));
+    TRY(upload_vec(ctx, ctx->d_bt_seg0, bt_seg0.data(), bt_seg0.size()));
+    TRY(upload_vec(ctx, ctx->d_seg_bt, seg_bt.data(), seg_bt.size()));
+    TRY(upload_vec(ctx, ctx->d_tile_desc, tile_desc.data(), tile_desc.size()));
     TRY(upload_vec(ctx, ctx->d_tile_bt, tile_bt.data(), tile_bt.size()));
 
     // outputs and workspaces
@@ -355,8 +374,8 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
         CUDA_TRY(ctx, ctx->d_gbase.ensure(hb));
         CUDA_TRY(ctx, ctx->d_sel.ensure((size_t)ctx->n_big * (2 * N_PASS + 1)));
         CUDA_TRY(ctx, ctx->d_need_tie.ensure((size_t)ctx->n_big * sizeof(int32_t)));
-        CUDA_TRY(ctx, ctx->d_status.ensure((size_t)N_PASS * ctx->n_tiles * 256 * sizeof(uint32_t)));
-        CUDA_TRY(ctx, ctx->d_cstatus.ensure((size_t)N_PASS * ctx->n_chunks * 256 * sizeof(uint32_t)));
+        CUDA_TRY(ctx, ctx->d_status.ensure((size_t)ctx->n_tiles * 256 * sizeof(uint32_t)));       // tile_hist
+        CUDA_TRY(ctx, ctx->d_seg_total.ensure((size_t)ctx->n_segs * 256 * sizeof(uint32_t)));
         CUDA_TRY(ctx, ctx->d_ticket.ensure((2 * N_PASS + 1) * sizeof(uint32_t)));
     }
     // the host vectors above must outlive the copies; also honours "the library
@@ -539,7 +558,7 @@ void lagassign_destroy(lagassign_ctx* ctx) {
                       &ctx->d_list_fill, &ctx->d_bt_topic, &ctx->d_bt_off, &ctx->d_bt_P, &ctx->d_bt_boff,
                       &ctx->d_bt_tile0, &ctx->d_tile_bt, &ctx->d_keyA, &ctx->d_keyB, &ctx->d_payA,
                       &ctx->d_payB, &ctx->d_ghist, &ctx->d_gbase, &ctx->d_sel, &ctx->d_need_tie,
-                      &ctx->d_status, &ctx->d_cstatus, &ctx->d_bt_chunk0, &ctx->d_ticket, &ctx->d_out_part, &ctx->d_out_cons,
+                      &ctx->d_status, &ctx->d_seg_total, &ctx->d_bt_seg0, &ctx->d_seg_bt, &ctx->d_tile_desc, &ctx->d_ticket, &ctx->d_out_part, &ctx->d_out_cons,
                       &ctx->d_out_total, &ctx->d_out_count};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -620,12 +639,6 @@ int lagassign_execute(lagassign_ctx* ctx) {
         const size_t hb = (size_t)ctx->n_big * N_PASS * 256 * sizeof(uint32_t);
         CUDA_TRY(ctx, cudaMemsetAsync(bt.ghist, 0, hb, st));
         CUDA_TRY(ctx, cudaMemsetAsync(bt.need_tie, 0, (size_t)ctx->n_big * sizeof(int32_t), st));
-        {   // look-back words of the passes that can run (tie passes only with explicit ids)
-            const int fp = ctx->has_part ? 0 : N_TIE_PASS;
-            const size_t per_pass = (size_t)ctx->n_tiles * 256, cper_pass = (size_t)ctx->n_chunks * 256;
-            CUDA_TRY(ctx, cudaMemsetAsync(bt.status + fp * per_pass, 0, (N_PASS - fp) * per_pass * sizeof(uint32_t), st));
-            CUDA_TRY(ctx, cudaMemsetAsync(bt.cstatus + fp * cper_pass, 0, (N_PASS - fp) * cper_pass * sizeof(uint32_t), st));
-        }
         CUDA_TRY(ctx, cudaMemsetAsync(bt.ticket, 0, (2 * N_PASS + 1) * sizeof(uint32_t), st));
         const int first_pass = ctx->has_part ? 0 : N_TIE_PASS;
         if (ctx->has_part) {
@@ -644,9 +657,19 @@ int lagassign_execute(lagassign_ctx* ctx) {
             ++launches;
         }
         for (int p = first_pass; p < N_PASS; ++p) {
-            ProfScope ps(ctx, K_PASS);
-            launch_big_pass(bt, p, b.lag, b.part, sms, st);
-            ++launches;
+            {
+                ProfScope ps(ctx, K_TILE_HIST);
+                launch_big_tile_hist(bt, p, b.lag, b.part, sms, st);
+            }
+            {
+                ProfScope ps(ctx, K_PASS_SCANS);
+                launch_big_pass_scans(bt, p, st);
+            }
+            {
+                ProfScope ps(ctx, K_SCATTER);
+                launch_big_scatter(bt, p, b.lag, b.part, sms, st);
+            }
+            launches += 4;
         }
         {
             ProfScope ps(ctx, K_FINALIZE);

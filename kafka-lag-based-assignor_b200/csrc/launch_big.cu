@@ -5,17 +5,16 @@
 
 namespace lagassign {
 
-static int g_pass_ctas_per_sm[2] = {1, 1};   // resident CTAs per SM of k_big_pass<false/true>
+static int g_scatter_ctas_per_sm[2] = {1, 1};   // resident CTAs per SM of k_big_scatter<false/true>
 
 cudaError_t configure_big_kernels() {
-    cudaError_t e = cudaFuncSetAttribute(k_big_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
+    cudaError_t e = cudaFuncSetAttribute(k_big_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_big_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
+    e = cudaFuncSetAttribute(k_big_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
     if (e != cudaSuccess) return e;
-    // the pass kernel is persistent (tiles are handed out by a ticket counter): one wave of resident CTAs
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_pass_ctas_per_sm[0], k_big_pass<false>, RT_THREADS, sizeof(PassSmem));
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_scatter_ctas_per_sm[0], k_big_scatter<false>, RT_THREADS, sizeof(PassSmem));
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_pass_ctas_per_sm[1], k_big_pass<true>, RT_THREADS, sizeof(PassSmem));
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_scatter_ctas_per_sm[1], k_big_scatter<true>, RT_THREADS, sizeof(PassSmem));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_big_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIGFILL_SMEM);
 }
@@ -25,7 +24,7 @@ void launch_big_order_check(const BigTopics& bt, const int32_t* part, int sms, c
 }
 
 void launch_big_hist(const BigTopics& bt, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st) {
-    const int grid = std::min(bt.n_tiles, sms * 2);
+    const int grid = std::min(bt.n_tiles, sms * 6);
     if (part) k_big_hist<true><<<grid, RT_THREADS, 0, st>>>(bt, lag, part);
     else k_big_hist<false><<<grid, RT_THREADS, 0, st>>>(bt, lag, nullptr);
 }
@@ -34,14 +33,21 @@ void launch_big_scan(const BigTopics& bt, int first_pass, cudaStream_t st) {
     k_big_scan<<<bt.n_big, 256, 0, st>>>(bt, first_pass);
 }
 
-void launch_big_pass(const BigTopics& bt, int pass, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st) {
-    // exactly one resident wave, launched cooperatively so that co-residency (which the
-    // static tile striding relies on) is checked by the runtime instead of assumed
-    const int grid = std::min(bt.n_tiles, sms * std::max(1, g_pass_ctas_per_sm[part ? 1 : 0]));
-    BigTopics bt_arg = bt;
-    void* args[] = {&bt_arg, &pass, &lag, &part};
-    const void* fn = part ? (const void*)k_big_pass<true> : (const void*)k_big_pass<false>;
-    cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(RT_THREADS), args, sizeof(PassSmem), st);
+void launch_big_tile_hist(const BigTopics& bt, int pass, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st) {
+    const int grid = std::min(bt.n_tiles, sms * 8);
+    if (part) k_big_tile_hist<true><<<grid, RT_THREADS, 0, st>>>(bt, pass, lag, part);
+    else k_big_tile_hist<false><<<grid, RT_THREADS, 0, st>>>(bt, pass, lag, nullptr);
+}
+
+void launch_big_pass_scans(const BigTopics& bt, int pass, cudaStream_t st) {
+    k_big_seg_scan<<<bt.n_segs, 256, 0, st>>>(bt, pass);
+    k_big_topic_scan<<<bt.n_big, 256, 0, st>>>(bt, pass);
+}
+
+void launch_big_scatter(const BigTopics& bt, int pass, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st) {
+    const int grid = std::min(bt.n_tiles, sms * std::max(1, g_scatter_ctas_per_sm[part ? 1 : 0]));
+    if (part) k_big_scatter<true><<<grid, RT_THREADS, sizeof(PassSmem), st>>>(bt, pass, lag, part);
+    else k_big_scatter<false><<<grid, RT_THREADS, sizeof(PassSmem), st>>>(bt, pass, lag, nullptr);
 }
 
 void launch_big_finalize(const BigTopics& bt, const DevBatch& b, int sms, cudaStream_t st) {

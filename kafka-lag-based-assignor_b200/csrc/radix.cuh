@@ -1,13 +1,12 @@
 // radix.cuh — device-wide path for topics too large for one CTA (P > 4096):
 // a segmented, stable, least-significant-digit radix sort (8-bit digits, 64-bit
-// key + 32-bit payload) in the "onesweep" style — one histogram kernel for all
-// digit positions, then one pass per digit whose tiles obtain their global
-// offsets by decoupled look-back over the previous tiles OF THE SAME TOPIC —
-// followed by the finalize / round-fill kernels.
+// key + 32-bit payload): one histogram kernel for all digit positions (digit
+// bases and skip decisions), then per digit a counting kernel, two small scans
+// and a scatter kernel, followed by the finalize / round-fill kernels.
 //
-// Segmentation: a tile never straddles topics, histograms and look-back chains
-// are per topic, and scatter destinations stay inside the topic's own range, so
-// any number of large topics share one sequence of launches with no topic digit.
+// Segmentation: a tile never straddles topics, histograms and offset scans are
+// per topic, and scatter destinations stay inside the topic's own range, so any
+// number of large topics share one sequence of launches with no topic digit.
 //
 // Pass skipping is decided on the device per (topic, pass): if one digit value
 // holds all P elements of a topic the pass cannot reorder anything and its tiles
@@ -25,19 +24,6 @@
 #include <cstdio>
 
 namespace lagassign {
-
-// Look-back status words are polled by other CTAs while they are being written:
-// the accesses must be real memory operations every time (never hoisted, merged
-// or speculated by the compiler), at gpu scope. Flag and value share one 32-bit
-// word, so relaxed ordering is sufficient.
-__device__ __forceinline__ uint32_t ld_status(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
 
 __device__ __forceinline__ uint32_t digit_of(uint64_t key, int lag_pass) {
     return (uint32_t)(key >> (8 * lag_pass)) & 0xFFu;
@@ -91,13 +77,14 @@ k_big_hist(BigTopics bt, const int64_t* __restrict__ lag, const int32_t* __restr
         const bool tie = HAS_PART && bt.need_tie[b] != 0;
 #pragma unroll 4
         for (int k = 0; k < RT_IPT; ++k) {
-            int64_t e = t0 + k * RT_THREADS + threadIdx.x;
-            if (e < P) {
-                uint64_t key = (uint64_t)ld_stream(lg + e) ^ LAG_KEY_MASK;
+            const int64_t e = t0 + k * RT_THREADS + threadIdx.x;
+            const bool live = e < P;
+            if (live) {
+                const uint64_t key = (uint64_t)ld_stream(lg + e) ^ LAG_KEY_MASK;
 #pragma unroll
                 for (int d = 0; d < N_LAG_PASS; ++d) atomicAdd(&h[N_TIE_PASS + d][digit_of(key, d)], 1u);
                 if (tie) {
-                    uint32_t pk = (uint32_t)part[bt.off[b] + e] ^ 0x80000000u;
+                    const uint32_t pk = (uint32_t)part[bt.off[b] + e] ^ 0x80000000u;
 #pragma unroll
                     for (int d = 0; d < N_TIE_PASS; ++d) atomicAdd(&h[d][(pk >> (8 * d)) & 0xFFu], 1u);
                 }
@@ -154,37 +141,23 @@ k_big_scan(BigTopics bt, int first_pass) {
     }
 }
 
-// ---- 4. one digit pass ------------------------------------------------------------------
-// Persistent CTAs of 256 threads (one thread per digit value). A CTA draws its rank r
-// from a counter when it starts and then owns tiles r, r+G, r+2G, ... (G = grid
-// size = exactly one resident wave, launched cooperatively): the tiles in flight at
-// any moment are consecutive, so the look-back of a tile only ever waits for tiles
-// that are being processed right now, even though every CTA has fetched further
-// tiles ahead. (Handing out tiles one by one from a ticket counter would let a CTA
-// sit on a prefetched ticket whose successors then stall.) Tile data is fetched with
-// cp.async (LDGSTS) into a ring of RT_STAGES shared-memory stages, RT_STAGES-1
-// tiles ahead, so HBM loads stay in flight while the current tile is ranked and
-// scattered; a thread only ever reads back the elements it fetched itself, so
-// cp.async.wait_group is the only synchronisation the ring needs. The stage being
-// processed doubles as the staging buffer of the tile-local scatter.
+// ---- 4. one digit pass = four kernels, no inter-CTA waiting ------------------------------
+//   4a k_big_tile_hist   digit counts of every tile                    (reads 8 B/element)
+//   4b k_big_seg_scan    exclusive scan over the tiles of a segment (RT_SEG tiles), per digit
+//   4c k_big_topic_scan  exclusive scan over a topic's segments, seeded with the digit base
+//   4d k_big_scatter     rank inside the tile, scatter                 (reads 12, writes 12 B/element)
+// An earlier version of this pass was a single "onesweep" kernel whose tiles obtained
+// their offsets by decoupled look-back (one- and two-level, windowed). On B200 it stayed
+// near 25 % of HBM peak regardless of tile shape, prefetch depth or look-back window:
+// with ~450 tiles in flight, per-tile cycle counters showed a third of the time spent
+// waiting for predecessor tiles (the chain forces completion in tile order, so every
+// tile runs at the pace of the slowest CTA ahead of it). Paying 8 B/element for a
+// separate counting kernel removes every dependency between CTAs.
 #ifndef LAGASSIGN_RT_STAGES
 #define LAGASSIGN_RT_STAGES 2
 #endif
 constexpr int RT_STAGES = LAGASSIGN_RT_STAGES;
-#ifndef LAGASSIGN_RT_LOOKBACK
-#define LAGASSIGN_RT_LOOKBACK 8
-#endif
-constexpr int RT_LOOKBACK = LAGASSIGN_RT_LOOKBACK;
-static_assert(RT_THREADS == 256, "k_big_pass maps one thread to one digit value");
-
-struct PassSmem {
-    uint64_t key[RT_STAGES][RT_TILE];
-    uint32_t pay[RT_STAGES][RT_TILE];
-    uint32_t whist[RT_WARPS][256];   // per-warp digit counts, then tile-local offsets per (warp, digit)
-    int64_t dst_base[256];           // global index of the tile's first element of each digit, minus its tile-local offset
-    uint32_t wsum[RT_WARPS];
-    int rank;                        // this CTA's arrival rank
-};
+static_assert(RT_THREADS == 256, "the pass kernels map one thread to one digit value");
 
 __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -196,6 +169,116 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// 4a ------------------------------------------------------------------------------------------
+template <bool HAS_PART>
+__global__ void __launch_bounds__(RT_THREADS)
+k_big_tile_hist(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int32_t* __restrict__ part) {
+    __shared__ uint32_t whist[RT_WARPS][256];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (bt.pass_any[pass] == 0) return;
+    for (int g = blockIdx.x; g < bt.n_tiles; g += gridDim.x) {
+        const int b = bt.tile_bt[g];
+        const int src = bt.sel_src[b * N_PASS + pass];
+        if (src == SEL_SKIP) continue;
+        const int64_t t0 = (int64_t)(g - bt.tile0[b]) * RT_TILE;
+        const int n_valid = (int)min((int64_t)RT_TILE, bt.P[b] - t0);
+        const int64_t boff = bt.boff[b];
+        const uint64_t* skey = ((src == SEL_A) ? bt.keyA : bt.keyB) + boff + t0;
+        const uint32_t* spay = ((src == SEL_A) ? bt.payA : bt.payB) + boff + t0;
+        const int64_t* lg = lag + bt.off[b] + t0;
+        const int32_t* pt = HAS_PART ? part + bt.off[b] : nullptr;
+#pragma unroll
+        for (int w = 0; w < RT_WARPS; ++w) whist[w][tid] = 0;
+        __syncthreads();
+        uint32_t dig[RT_IPT];
+#pragma unroll
+        for (int k = 0; k < RT_IPT; ++k) {
+            const int i = k * RT_THREADS + tid;
+            dig[k] = 0xFFFFFFFFu;
+            if (i < n_valid) {
+                if (HAS_PART && pass < N_TIE_PASS) {
+                    const uint32_t pp = (src == SEL_RAW) ? (uint32_t)(t0 + i) : spay[i];
+                    dig[k] = (((uint32_t)pt[pp] ^ 0x80000000u) >> (8 * pass)) & 0xFFu;
+                } else {
+                    const uint64_t key = (src == SEL_RAW) ? ((uint64_t)lg[i] ^ LAG_KEY_MASK) : skey[i];
+                    dig[k] = digit_of(key, pass - N_TIE_PASS);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RT_IPT; ++k)
+            if (dig[k] != 0xFFFFFFFFu) atomicAdd(&whist[warp][dig[k]], 1u);
+        __syncthreads();
+        uint32_t c = 0;
+#pragma unroll
+        for (int w = 0; w < RT_WARPS; ++w) c += whist[w][tid];
+        bt.tile_hist[(size_t)g * 256 + tid] = c;
+        __syncthreads();
+    }
+}
+
+// 4b: one CTA per segment; tile_hist becomes the exclusive prefix inside the segment ------------
+__global__ void __launch_bounds__(256)
+k_big_seg_scan(BigTopics bt, int pass) {
+    const int seg = blockIdx.x, tid = threadIdx.x;
+    if (bt.pass_any[pass] == 0) return;
+    const int b = bt.seg_bt[seg];
+    if (bt.sel_src[b * N_PASS + pass] == SEL_SKIP) return;
+    const int n_tiles_topic = (int)((bt.P[b] + RT_TILE - 1) / RT_TILE);
+    const int first_in_topic = (seg - bt.seg0[b]) * RT_SEG;
+    const int n = min(RT_SEG, n_tiles_topic - first_in_topic);
+    uint32_t* h = bt.tile_hist + (size_t)(bt.tile0[b] + first_in_topic) * 256 + tid;
+    uint32_t run = 0;
+    for (int t = 0; t < n; t += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (t + q < n) ? h[(size_t)(t + q) * 256] : 0u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (t + q < n) h[(size_t)(t + q) * 256] = run;
+            run += v[q];
+        }
+    }
+    bt.seg_total[(size_t)seg * 256 + tid] = run;
+}
+
+// 4c: one CTA per topic; seg_total becomes the global start of (segment, digit) in the topic ----
+__global__ void __launch_bounds__(256)
+k_big_topic_scan(BigTopics bt, int pass) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (bt.pass_any[pass] == 0) return;
+    if (bt.sel_src[b * N_PASS + pass] == SEL_SKIP) return;
+    const int n_tiles_topic = (int)((bt.P[b] + RT_TILE - 1) / RT_TILE);
+    const int n = (n_tiles_topic + RT_SEG - 1) / RT_SEG;
+    uint32_t* s = bt.seg_total + (size_t)bt.seg0[b] * 256 + tid;
+    uint32_t run = bt.gbase[((size_t)b * N_PASS + pass) * 256 + tid];
+    for (int t = 0; t < n; t += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (t + q < n) ? s[(size_t)(t + q) * 256] : 0u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (t + q < n) s[(size_t)(t + q) * 256] = run;
+            run += v[q];
+        }
+    }
+}
+
+// 4d ------------------------------------------------------------------------------------------
+// CTAs of 256 threads (one per digit value) walk the tiles with a grid stride. Tile data is
+// fetched with cp.async (LDGSTS) into a ring of RT_STAGES shared-memory stages, RT_STAGES-1
+// tiles ahead, so HBM loads stay in flight while the current tile is ranked and scattered; a
+// thread only reads back the elements it fetched itself, so cp.async.wait_group is the only
+// synchronisation the ring needs. The stage being processed doubles as the staging buffer of
+// the tile-local scatter.
+struct PassSmem {
+    uint64_t key[RT_STAGES][RT_TILE];
+    uint32_t pay[RT_STAGES][RT_TILE];
+    uint32_t whist[RT_WARPS][256];   // per-warp digit counts, then tile-local offsets per (warp, digit)
+    int64_t dst_base[256];           // index in the topic of the tile's first element of each digit, minus its tile-local offset
+    uint32_t wsum[RT_WARPS];
+};
+
 #ifdef LAGASSIGN_RT_TIMING
 #define RT_TICK(slot) do { if (tid == 0) { long long _t = clock64(); t_acc[slot] += _t - t_last; t_last = _t; } } while (0)
 #else
@@ -204,37 +287,49 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 template <bool HAS_PART>
 __global__ void __launch_bounds__(RT_THREADS, LAGASSIGN_RT_MINBLOCKS)
-k_big_pass(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int32_t* __restrict__ part) {
+k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int32_t* __restrict__ part) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PassSmem& sm = *reinterpret_cast<PassSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (bt.pass_any[pass] == 0) return;   // every topic's digit is constant: nothing to move
-    uint32_t* status = bt.status + (size_t)pass * bt.n_tiles * 256;
-    uint32_t* cstatus = bt.cstatus + (size_t)pass * bt.n_chunks * 256;
     const int n_tiles = bt.n_tiles;
+#ifdef LAGASSIGN_RT_TIMING
+    long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_last = clock64();
+    int t_tiles = 0;
+#endif
 
-    // fetch this thread's elements of tile g into ring stage `stage` (one commit group per call)
-    auto issue_loads = [&](int stage, int g) {
+    // A tile's geometry is one 32-byte record; the record also remembers which buffer the
+    // topic reads in this pass (-1: pass skipped for the topic, or no such tile).
+    struct Tile { TileDesc d; int src; };
+    auto load_tile = [&](int g) {
+        Tile t;
+        t.src = SEL_SKIP;
+        t.d.b = -1;
         if (g < n_tiles) {
-            const int b = bt.tile_bt[g];
-            const int src = bt.sel_src[b * N_PASS + pass];
-            if (src != SEL_SKIP) {
-                const int64_t t0 = (int64_t)(g - bt.tile0[b]) * RT_TILE;
-                const int n_valid = (int)min((int64_t)RT_TILE, bt.P[b] - t0);
-                const int64_t boff = bt.boff[b];
-                const uint64_t* skey = ((src == SEL_A) ? bt.keyA : bt.keyB) + boff + t0;
-                const uint32_t* spay = ((src == SEL_A) ? bt.payA : bt.payB) + boff + t0;
-                const int64_t* lg = lag + bt.off[b] + t0;
+            const int4 a = __ldg(bt.tile_desc + 2 * (size_t)g), c = __ldg(bt.tile_desc + 2 * (size_t)g + 1);
+            t.d.b = a.x; t.d.tile_in_topic = a.y; t.d.n_valid = a.z; t.d.seg = a.w;
+            t.d.buf_off = ((int64_t)(uint32_t)c.y << 32) | (uint32_t)c.x;
+            t.d.raw_off = ((int64_t)(uint32_t)c.w << 32) | (uint32_t)c.z;
+            t.src = bt.sel_src[t.d.b * N_PASS + pass];
+        }
+        return t;
+    };
+    // fetch this thread's elements of a tile into ring stage `stage` (one commit group per call)
+    auto issue_loads = [&](int stage, const Tile& t) {
+        if (t.src != SEL_SKIP) {
+            const uint64_t* skey = ((t.src == SEL_A) ? bt.keyA : bt.keyB) + t.d.buf_off;
+            const uint32_t* spay = ((t.src == SEL_A) ? bt.payA : bt.payB) + t.d.buf_off;
+            const int64_t* lg = lag + t.d.raw_off;
 #pragma unroll
-                for (int k = 0; k < RT_IPT; ++k) {
-                    const int i = warp * (32 * RT_IPT) + k * 32 + lane;
-                    if (i < n_valid) {
-                        if (src == SEL_RAW) {
-                            cp_async_8(&sm.key[stage][i], lg + i);
-                        } else {
-                            cp_async_8(&sm.key[stage][i], skey + i);
-                            cp_async_4(&sm.pay[stage][i], spay + i);
-                        }
+            for (int k = 0; k < RT_IPT; ++k) {
+                const int i = warp * (32 * RT_IPT) + k * 32 + lane;
+                if (i < t.d.n_valid) {
+                    if (t.src == SEL_RAW) {
+                        cp_async_8(&sm.key[stage][i], lg + i);
+                    } else {
+                        cp_async_8(&sm.key[stage][i], skey + i);
+                        cp_async_4(&sm.pay[stage][i], spay + i);
                     }
                 }
             }
@@ -242,50 +337,44 @@ k_big_pass(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int32_
         cp_async_commit();
     };
 
-#ifdef LAGASSIGN_RT_TIMING
-    long long t_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    long long t_last = clock64();
-    int t_tiles = 0;
-#endif
-    if (tid == 0) sm.rank = (int)atomicAdd(&bt.ticket[pass], 1u);
-    __syncthreads();
+    static_assert(RT_STAGES == 2, "the descriptor pipeline below is written for a two-stage ring");
     const int G = (int)gridDim.x;
-    const int g0 = sm.rank;
-    // prologue: the first RT_STAGES-1 tiles of this CTA start loading now
-#pragma unroll
-    for (int q = 0; q < RT_STAGES - 1; ++q) issue_loads(q, g0 + q * G);
+    const int g0 = (int)blockIdx.x;
+    Tile cur = load_tile(g0);              // tile being processed
+    issue_loads(0, cur);
+    Tile pre = load_tile(g0 + G);          // next tile: its loads are issued at the top of the iteration
 
     for (int it = 0;; ++it) {
-        const int s = it % RT_STAGES;
-        const int sp = (it + RT_STAGES - 1) % RT_STAGES;   // stage freed by the previous iteration
-        __syncthreads();   // previous tile fully stored
-        RT_TICK(0);
+        const int s = it & 1;
         const int g = g0 + it * G;
-        issue_loads(sp, g + (RT_STAGES - 1) * G);
-        RT_TICK(1);
+        __syncthreads();   // previous tile fully stored: its stage may be refilled
+        const Tile nxt = pre;
+        issue_loads(s ^ 1, nxt);
+        pre = load_tile(g + 2 * G);        // consumed by the next iteration
+        RT_TICK(0);
         if (g >= n_tiles) break;
+        if (cur.src == SEL_SKIP) { cur = nxt; continue; }   // this topic's digit is constant in this pass
 
-        const int b = bt.tile_bt[g];
-        const int src = bt.sel_src[b * N_PASS + pass];
-        if (src == SEL_SKIP) continue;   // this topic's digit is constant in this pass
+        const int b = cur.d.b;
+        const int src = cur.src;
         const int dst = bt.sel_dst[b * N_PASS + pass];
-        const int64_t P = bt.P[b];
-        const int tile_in_topic = g - bt.tile0[b];
+        const int tile_in_topic = cur.d.tile_in_topic;
         const int64_t t0 = (int64_t)tile_in_topic * RT_TILE;
-        const int n_valid = (int)min((int64_t)RT_TILE, P - t0);
-        const int64_t boff = bt.boff[b];
+        const int n_valid = cur.d.n_valid;
+        const int64_t boff = cur.d.buf_off - t0;
         uint64_t* dkey = (dst == SEL_A) ? bt.keyA + boff : bt.keyB + boff;
         uint32_t* dpay = (dst == SEL_A) ? bt.payA + boff : bt.payB + boff;
-        const int32_t* pt = HAS_PART ? part + bt.off[b] : nullptr;
-        const uint32_t gb = bt.gbase[((size_t)b * N_PASS + pass) * 256 + tid];   // needed after the look-back
+        const int32_t* pt = HAS_PART ? part + (cur.d.raw_off - t0) : nullptr;
+        // where this tile's elements of digit `tid` start in the topic (4b + 4c)
+        const uint32_t base_d = bt.tile_hist[(size_t)g * 256 + tid] + bt.seg_total[(size_t)cur.d.seg * 256 + tid];
+        cur = nxt;
 
 #pragma unroll
         for (int w = 0; w < RT_WARPS; ++w) sm.whist[w][tid] = 0;
+        RT_TICK(1);
 
-        RT_TICK(2);
         // this thread's elements: item k of lane l in warp w is tile element w*32*IPT + k*32 + l
         cp_async_wait<RT_STAGES - 1>();
-        RT_TICK(3);
         uint64_t key[RT_IPT];
         uint32_t pay[RT_IPT];
         uint32_t dig[RT_IPT];
@@ -304,7 +393,7 @@ k_big_pass(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int32_
             }
         }
         __syncthreads();   // counters zeroed; every thread holds its elements in registers
-        RT_TICK(4);
+        RT_TICK(2);
 
         // rank inside the warp: elements with equal digit keep memory order
         uint32_t rank[RT_IPT];
@@ -318,9 +407,9 @@ k_big_pass(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int32_
             rank[k] = pre + __popc(peers & ((1u << lane) - 1u));
         }
         __syncthreads();
-        RT_TICK(5);
+        RT_TICK(3);
 
-        // thread d owns digit value d: offsets over warps, tile count, look-back
+        // thread d owns digit value d: offsets over warps and over digits inside the tile
         {
             uint32_t cnt = 0;
 #pragma unroll
@@ -329,12 +418,7 @@ k_big_pass(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int32_
                 sm.whist[w][tid] = cnt;
                 cnt += v;
             }
-            uint32_t valid_cnt = cnt;
-            if (tid == 255) valid_cnt -= (uint32_t)(RT_TILE - n_valid);   // padding is not data
-            uint32_t* st = status + (size_t)g * 256 + tid;
-            st_status(st, ST_AGG | valid_cnt);   // this tile's own count: later tiles can proceed
-            // exclusive scan of cnt over digits (tile-local positions; padding is last)
-            uint32_t x = cnt;
+            uint32_t x = cnt;   // padding elements are counted in digit 255, which is last
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
@@ -347,81 +431,10 @@ k_big_pass(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int32_
             const uint32_t excl = x - cnt + add;
 #pragma unroll
             for (int w = 0; w < RT_WARPS; ++w) sm.whist[w][tid] += excl;
-
-            RT_TICK(6);
-            // Two-level decoupled look-back. Tiles of a topic are grouped in chunks of
-            // RT_CHUNK. A tile sums the published counts of the earlier tiles of its own
-            // chunk (independent loads); the chunk's last tile also publishes the chunk
-            // aggregate, walks back over earlier CHUNK words (RT_LOOKBACK at a time) to the
-            // nearest inclusive prefix and publishes the chunk's inclusive prefix, which is
-            // all the other tiles of the next chunk wait for. A one-level walk costs about
-            // G/(4*window) dependent L2 round trips per tile with G tiles in flight, and
-            // that chain, not HBM, bounded the pass.
-            const int p_in = tile_in_topic % RT_CHUNK;
-            const int chunk = tile_in_topic / RT_CHUNK;
-            const bool leader = (p_in == RT_CHUNK - 1) || (t0 + RT_TILE >= P);
-            uint32_t* cst_base = cstatus + (size_t)bt.chunk0[b] * 256 + tid;
-            uint32_t in_chunk = 0;
-            {
-                const uint32_t* first_in_chunk = status + (size_t)(g - p_in) * 256 + tid;
-#pragma unroll
-                for (int q0 = 0; q0 < RT_CHUNK - 1; q0 += 8) {
-                    if (q0 < p_in) {
-                        uint32_t v[8];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            v[q] = (q0 + q < p_in) ? ld_status(first_in_chunk + (size_t)(q0 + q) * 256) : ST_AGG;
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            while ((v[q] >> 30) == 0) v[q] = ld_status(first_in_chunk + (size_t)(q0 + q) * 256);
-                            in_chunk += v[q] & ST_VAL;
-                        }
-                    }
-                }
-            }
-            uint32_t prefix_chunks = 0;
-            if (leader) {
-                const uint32_t chunk_total = in_chunk + valid_cnt;
-                uint32_t* cst = cst_base + (size_t)chunk * 256;
-                if (chunk == 0) {
-                    st_status(cst, ST_INC | chunk_total);
-                } else {
-                    st_status(cst, ST_AGG | chunk_total);
-                    int look = chunk - 1;
-                    bool done = false;
-                    while (!done) {
-                        uint32_t v[RT_LOOKBACK];
-#pragma unroll
-                        for (int q = 0; q < RT_LOOKBACK; ++q)
-                            v[q] = (look - q >= 0) ? ld_status(cst_base + (size_t)(look - q) * 256) : ST_INC;
-                        int used = RT_LOOKBACK;
-#pragma unroll
-                        for (int q = 0; q < RT_LOOKBACK; ++q) {
-                            if (!done && used == RT_LOOKBACK) {
-                                const uint32_t state = v[q] >> 30;
-                                if (state == 0) {
-                                    used = q;                // not published yet: poll again from here
-                                } else {
-                                    prefix_chunks += v[q] & ST_VAL;
-                                    if (state == 2u) done = true;
-                                }
-                            }
-                        }
-                        look -= used;
-                    }
-                    st_status(cst, ST_INC | (prefix_chunks + chunk_total));
-                }
-            } else if (chunk > 0) {
-                const uint32_t* cprev = cst_base + (size_t)(chunk - 1) * 256;
-                uint32_t v;
-                do { v = ld_status(cprev); } while ((v >> 30) != 2u);
-                prefix_chunks = v & ST_VAL;
-            }
-            const uint32_t prefix = prefix_chunks + in_chunk;
-            sm.dst_base[tid] = (int64_t)gb + (int64_t)prefix - (int64_t)excl;
+            sm.dst_base[tid] = (int64_t)base_d - (int64_t)excl;
         }
-        RT_TICK(7);
         __syncthreads();
+        RT_TICK(4);
 
         // scatter inside the tile (the consumed ring stage is the staging buffer) ...
 #pragma unroll
@@ -432,17 +445,31 @@ k_big_pass(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int32_
         }
         __syncthreads();
         // ... then out in digit runs (coalesced)
-        for (int i = tid; i < n_valid; i += RT_THREADS) {
-            const uint64_t kk = sm.key[s][i];
-            const uint32_t pp = sm.pay[s][i];
-            uint32_t d;
-            if (HAS_PART && pass < N_TIE_PASS) d = (((uint32_t)pt[pp] ^ 0x80000000u) >> (8 * pass)) & 0xFFu;
-            else d = digit_of(kk, pass - N_TIE_PASS);
-            const int64_t o = sm.dst_base[d] + i;
-            dkey[o] = kk;
-            dpay[o] = pp;
+        {
+            uint64_t kk[RT_IPT];
+            uint32_t pp[RT_IPT];
+            int64_t oo[RT_IPT];
+#pragma unroll
+            for (int k = 0; k < RT_IPT; ++k) {       // all shared-memory reads first, then the stores
+                const int i = k * RT_THREADS + tid;
+                kk[k] = sm.key[s][i];
+                pp[k] = sm.pay[s][i];
+            }
+#pragma unroll
+            for (int k = 0; k < RT_IPT; ++k) {
+                const int i = k * RT_THREADS + tid;
+                uint32_t d;
+                if (HAS_PART && pass < N_TIE_PASS) d = (i < n_valid) ? ((((uint32_t)pt[pp[k]] ^ 0x80000000u) >> (8 * pass)) & 0xFFu) : 255u;
+                else d = digit_of(kk[k], pass - N_TIE_PASS);
+                oo[k] = sm.dst_base[d] + i;
+            }
+#pragma unroll
+            for (int k = 0; k < RT_IPT; ++k) {
+                const int i = k * RT_THREADS + tid;
+                if (i < n_valid) { dkey[oo[k]] = kk[k]; dpay[oo[k]] = pp[k]; }
+            }
         }
-        RT_TICK(8);
+        RT_TICK(5);
 #ifdef LAGASSIGN_RT_TIMING
         ++t_tiles;
 #endif
@@ -450,9 +477,9 @@ k_big_pass(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int32_
     cp_async_wait<0>();
 #ifdef LAGASSIGN_RT_TIMING
     if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 200) && t_tiles > 0)
-        printf("pass %d cta %d tiles %d | per tile: topbar %lld issue %lld meta %lld cpwait %lld lds+bar %lld rank+bar %lld scan %lld lookback %lld scatter+store %lld\n",
+        printf("pass %d cta %d tiles %d | cycles per tile: top+issue %lld meta %lld cpwait+lds+bar %lld rank+bar %lld scan+bar %lld scatter+store %lld\n",
                pass, (int)blockIdx.x, t_tiles, t_acc[0] / t_tiles, t_acc[1] / t_tiles, t_acc[2] / t_tiles, t_acc[3] / t_tiles,
-               t_acc[4] / t_tiles, t_acc[5] / t_tiles, t_acc[6] / t_tiles, t_acc[7] / t_tiles, t_acc[8] / t_tiles);
+               t_acc[4] / t_tiles, t_acc[5] / t_tiles);
 #endif
 }
 

@@ -26,10 +26,10 @@ struct DevBatch {
 #define LAGASSIGN_RT_THREADS 256
 #endif
 #ifndef LAGASSIGN_RT_IPT
-#define LAGASSIGN_RT_IPT 8
+#define LAGASSIGN_RT_IPT 16
 #endif
 #ifndef LAGASSIGN_RT_MINBLOCKS
-#define LAGASSIGN_RT_MINBLOCKS 3
+#define LAGASSIGN_RT_MINBLOCKS 2
 #endif
 constexpr int RT_THREADS = LAGASSIGN_RT_THREADS;
 constexpr int RT_IPT = LAGASSIGN_RT_IPT;
@@ -39,12 +39,24 @@ constexpr int N_TIE_PASS = 4;
 constexpr int N_LAG_PASS = 8;
 constexpr int N_PASS = N_TIE_PASS + N_LAG_PASS;
 
-constexpr int RT_CHUNK = 16;            // tiles per look-back chunk
+constexpr int RT_SEG = 64;              // tiles per scan segment
 constexpr uint32_t ST_AGG = 1u << 30;   // tile's own count is published
 constexpr uint32_t ST_INC = 2u << 30;   // inclusive prefix over the topic's tiles so far
 constexpr uint32_t ST_VAL = (1u << 30) - 1;
 
 enum : int { SEL_RAW = 0, SEL_A = 1, SEL_B = 2, SEL_SKIP = -1 };
+
+// One 32-byte record per tile, built on the host, so a tile's geometry is one load
+// instead of a chain of dependent ones (tile -> topic -> five per-topic arrays).
+struct TileDesc {
+    int32_t b;               // large-topic index
+    int32_t tile_in_topic;
+    int32_t n_valid;         // elements in this tile (RT_TILE except for a topic's last tile)
+    int32_t seg;             // global scan-segment id
+    int64_t buf_off;         // boff + tile start: element offset in the compact sort buffers
+    int64_t raw_off;         // topic_off + tile start: element offset in the caller's arrays
+};
+static_assert(sizeof(TileDesc) == 32, "TileDesc is loaded as two 16-byte words");
 
 struct BigTopics {
     int n_big;                 // B
@@ -55,6 +67,7 @@ struct BigTopics {
     const int64_t* boff;       // [B] offset in the compact sort buffers
     const int32_t* tile0;      // [B] first tile of the topic
     const int32_t* tile_bt;    // [G] tile -> b
+    const int4* tile_desc;     // [G][2] per-tile descriptor, see TileDesc
     uint64_t* keyA; uint64_t* keyB;   // [sum P]
     uint32_t* payA; uint32_t* payB;
     uint32_t* ghist;           // [B][N_PASS][256] digit counts
@@ -63,11 +76,12 @@ struct BigTopics {
     int8_t* sel_dst;           // [B][N_PASS]
     int8_t* sel_final;         // [B] where the sorted data of the topic ended up
     int32_t* need_tie;         // [B] partition ids not ascending
-    uint32_t* status;          // [N_PASS][G][256] per-tile digit counts for the look-back (zeroed per execute)
-    const int32_t* chunk0;     // [B] first look-back chunk of the topic (chunks of RT_CHUNK tiles)
-    int n_chunks;
-    uint32_t* cstatus;         // [N_PASS][n_chunks][256] per-chunk aggregate / inclusive prefix
-    uint32_t* ticket;          // [N_PASS] dynamic tile ids (zeroed per execute)
+    uint32_t* tile_hist;       // [G][256] digit counts of each tile, then exclusive prefix inside its segment
+    const int32_t* seg0;       // [B] first scan segment of the topic (segments of RT_SEG tiles)
+    const int32_t* seg_bt;     // [n_segs] segment -> b
+    int n_segs;
+    uint32_t* seg_total;       // [n_segs][256] segment totals, then start of (segment, digit) inside the topic
+    uint32_t* ticket;          // [N_PASS] unused counters (zeroed per execute)
     int32_t* passes_run;       // [1] max over topics of executed passes (stat)
     uint32_t* pass_any;        // [N_PASS] does any topic run this pass? (else the launch returns at once)
 };
@@ -87,7 +101,9 @@ void launch_cta_topics(const DevBatch& b, const int32_t* list, int n, int sms, c
 void launch_big_order_check(const BigTopics& bt, const int32_t* part, int sms, cudaStream_t st);
 void launch_big_hist(const BigTopics& bt, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st);
 void launch_big_scan(const BigTopics& bt, int first_pass, cudaStream_t st);
-void launch_big_pass(const BigTopics& bt, int pass, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st);
+void launch_big_tile_hist(const BigTopics& bt, int pass, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st);
+void launch_big_pass_scans(const BigTopics& bt, int pass, cudaStream_t st);   // two kernels
+void launch_big_scatter(const BigTopics& bt, int pass, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st);
 void launch_big_finalize(const BigTopics& bt, const DevBatch& b, int sms, cudaStream_t st);
 void launch_big_fill(const BigTopics& bt, const int32_t* fill_list, int n_fill, const DevBatch& b, int sms, cudaStream_t st);
 
