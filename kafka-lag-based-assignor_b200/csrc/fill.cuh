@@ -41,7 +41,6 @@ __device__ __forceinline__ void warp_round_fill(int64_t P, int C, const int32_t*
         cid[r] = live ? (uint32_t)j : PAY_SENTINEL;
         lag_cur[r] = (live && j < P) ? lag_at((int64_t)j) : 0;
     }
-    bool prev_equal = false;
     for (int64_t base = 0; base < P; base += C) {
         // issue next round's loads before the dependent sort
         int64_t lag_nxt[EPTC];
@@ -51,13 +50,11 @@ __device__ __forceinline__ void warp_round_fill(int64_t P, int C, const int32_t*
             int64_t k = base + C + j;
             lag_nxt[r] = (j < C && k < P) ? lag_at(k) : 0;
         }
-        // first and last lag of THIS round, fetched now and compared after the round: were all its lags equal?
-        const int64_t eq_a = lag_at(base), eq_b = lag_at(min(base + (int64_t)C - 1, P - 1));
-        // Round 0 starts in id order with all totals 0. After a round that added the same
-        // lag to everyone (lags are sorted, so: first == last of the round; typically an idle
-        // topic with zero lag everywhere) the order usually survives: test before sorting.
+        // Round 0 starts in id order with all totals 0. After rounds that added the same lag to
+        // everyone (typically zero: an idle topic, or the zero-lag tail of a busy one) the
+        // order survives: test before sorting.
         if (base > 0) {
-            bool ok = prev_equal;
+            bool ok = true;
 #pragma unroll
             for (int r = 0; r + 1 < EPTC; ++r) ok = ok && !elem_less(tkey[r + 1], cid[r + 1], tkey[r], cid[r]);
             const uint64_t nk = __shfl_down_sync(0xffffffffu, tkey[0], 1);
@@ -74,7 +71,6 @@ __device__ __forceinline__ void warp_round_fill(int64_t P, int C, const int32_t*
             }
             lag_cur[r] = lag_nxt[r];
         }
-        prev_equal = (base + C <= P) && (eq_a == eq_b);
     }
     if (out_total != nullptr) {
         const int64_t full = P / C;
@@ -170,7 +166,6 @@ __device__ __forceinline__ void cta_round_fill_regs(int64_t P, int C, const int3
         w[0][r] = live ? (uint32_t)j : PAY_SENTINEL;
         lag_cur[r] = (live && j < P) ? lag_at((int64_t)j) : 0;
     }
-    bool prev_equal = false;
     for (int64_t base = 0; base < P; base += C) {
         int64_t lag_nxt[EPT];
 #pragma unroll
@@ -179,13 +174,12 @@ __device__ __forceinline__ void cta_round_fill_regs(int64_t P, int C, const int3
             const int64_t k = base + C + j;
             lag_nxt[r] = (j < C && k < P) ? lag_at(k) : 0;
         }
-        // first and last lag of THIS round, fetched now and compared after the round: were all its lags equal?
-        const int64_t eq_a = lag_at(base), eq_b = lag_at(min(base + (int64_t)C - 1, P - 1));
         if (base > 0) {
-            // After a round that added the same lag to every consumer (first == last lag of the
-            // round; typically zero) the (total, id) order usually survives: then skip the sort.
+            // After rounds that added the same lag to every consumer (typically zero: an idle
+            // topic, or the zero-lag tail of a busy one) the (total, id) order survives: test
+            // (two barriers, ~5 % of a sort) and skip the sort when it holds.
             bool skip = false;
-            if (prev_equal) {      // uniform across the CTA
+            {
                 bool ok = true;
 #pragma unroll
                 for (int r = 0; r + 1 < EPT; ++r)
@@ -212,7 +206,6 @@ __device__ __forceinline__ void cta_round_fill_regs(int64_t P, int C, const int3
             }
             lag_cur[r] = lag_nxt[r];
         }
-        prev_equal = (base + C <= P) && (eq_a == eq_b);
     }
     if (out_total != nullptr) {
         const int64_t full = P / C;

@@ -286,6 +286,7 @@ BigTopics make_big(lagassign_ctx* ctx) {
     bt.sel_src = sel;
     bt.sel_dst = sel + (size_t)ctx->n_big * N_PASS;
     bt.sel_final = sel + (size_t)ctx->n_big * N_PASS * 2;
+    bt.all_equal = sel + (size_t)ctx->n_big * (N_PASS * 2 + 1);
     bt.need_tie = ctx->d_need_tie.as<int32_t>();
     bt.tile_hist = ctx->d_status.as<uint32_t>();
     bt.seg0 = ctx->d_bt_seg0.as<int32_t>();
@@ -372,7 +373,7 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
         const size_t hb = (size_t)ctx->n_big * N_PASS * 256 * sizeof(uint32_t);
         CUDA_TRY(ctx, ctx->d_ghist.ensure(hb));
         CUDA_TRY(ctx, ctx->d_gbase.ensure(hb));
-        CUDA_TRY(ctx, ctx->d_sel.ensure((size_t)ctx->n_big * (2 * N_PASS + 1)));
+        CUDA_TRY(ctx, ctx->d_sel.ensure((size_t)ctx->n_big * (2 * N_PASS + 2)));
         CUDA_TRY(ctx, ctx->d_need_tie.ensure((size_t)ctx->n_big * sizeof(int32_t)));
         CUDA_TRY(ctx, ctx->d_status.ensure((size_t)ctx->n_tiles * 256 * sizeof(uint32_t)));       // tile_hist
         CUDA_TRY(ctx, ctx->d_seg_total.ensure((size_t)ctx->n_segs * 256 * sizeof(uint32_t)));

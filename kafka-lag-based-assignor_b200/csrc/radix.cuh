@@ -98,10 +98,10 @@ k_big_hist(BigTopics bt, const int64_t* __restrict__ lag, const int32_t* __restr
 __global__ void __launch_bounds__(256)
 k_big_scan(BigTopics bt, int first_pass) {
     __shared__ uint32_t wsum[8];
-    __shared__ int s_cur, s_run;
+    __shared__ int s_cur, s_run, s_lagconst;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t P = bt.P[b];
-    if (tid == 0) { s_cur = SEL_RAW; s_run = 0; }
+    if (tid == 0) { s_cur = SEL_RAW; s_run = 0; s_lagconst = 0; }
     __syncthreads();
     for (int p = 0; p < N_PASS; ++p) {
         const size_t base = ((size_t)b * N_PASS + p) * 256;
@@ -121,6 +121,7 @@ k_big_scan(BigTopics bt, int first_pass) {
         for (int w = 0; w < warp; ++w) add += wsum[w];
         bt.gbase[base + tid] = x - c + add;
         if (tid == 0) {
+            if (p >= N_TIE_PASS && constant) s_lagconst += 1;
             if (off || constant) {
                 bt.sel_src[b * N_PASS + p] = SEL_SKIP;
                 bt.sel_dst[b * N_PASS + p] = SEL_SKIP;
@@ -137,6 +138,7 @@ k_big_scan(BigTopics bt, int first_pass) {
     }
     if (tid == 0) {
         bt.sel_final[b] = (int8_t)s_cur;
+        bt.all_equal[b] = (int8_t)(s_lagconst == N_LAG_PASS);
         atomicMax(bt.passes_run, s_run);
     }
 }
@@ -500,6 +502,10 @@ k_big_finalize(BigTopics bt, const int64_t* __restrict__ lag, const int32_t* __r
         const int s = topic_cset[t];
         const int64_t coff = cset_off[s], C = cset_off[s + 1] - coff;
         const bool single_round = P <= C;
+        // All lags equal (an idle topic: zero everywhere): every round starts with equal
+        // totals, so its picks are the members in id order and the sorted partition k goes to
+        // member k mod C. No sequential fill is needed.
+        const bool cyclic = !single_round && bt.all_equal[b] != 0;
         const int64_t t0 = (int64_t)(g - bt.tile0[b]) * RT_TILE;
         for (int i = threadIdx.x; i < RT_TILE; i += blockDim.x) {
             const int64_t e = t0 + i;
@@ -512,6 +518,13 @@ k_big_finalize(BigTopics bt, const int64_t* __restrict__ lag, const int32_t* __r
                     int64_t lg = (sel == SEL_RAW) ? lag[off + e] : (int64_t)(fkey[e] ^ LAG_KEY_MASK);
                     out_total[tc_off[t] + e] = lg;
                     out_count[tc_off[t] + e] = 1;
+                }
+            } else if (cyclic) {
+                out_cons[off + e] = cset_rank[coff + e % C];
+                if (out_total && e < C) {
+                    const int64_t cnt = P / C + (e < P % C ? 1 : 0);
+                    out_total[tc_off[t] + e] = (int64_t)((uint64_t)cnt * (uint64_t)lag[off]);   // wraps like repeated addition
+                    out_count[tc_off[t] + e] = (int32_t)cnt;
                 }
             }
         }
@@ -531,6 +544,7 @@ k_big_fill(BigTopics bt, const int32_t* __restrict__ fill_list, int n_fill,
     uint32_t* cidx = reinterpret_cast<uint32_t*>(smem_raw + sizeof(uint64_t) * FILL_CTA_MAX_C);
     for (int li = blockIdx.x; li < n_fill; li += gridDim.x) {
         const int b = fill_list[li];
+        if (bt.all_equal[b]) continue;   // assigned in closed form by k_big_finalize
         const int t = bt.topic[b];
         const int64_t P = bt.P[b], off = bt.off[b], boff = bt.boff[b];
         const int sel = bt.sel_final[b];

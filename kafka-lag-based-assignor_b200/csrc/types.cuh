@@ -75,6 +75,7 @@ struct BigTopics {
     int8_t* sel_src;           // [B][N_PASS]  SEL_* (SEL_SKIP = pass skipped for this topic)
     int8_t* sel_dst;           // [B][N_PASS]
     int8_t* sel_final;         // [B] where the sorted data of the topic ended up
+    int8_t* all_equal;         // [B] every lag of the topic has the same value (all eight digit passes constant)
     int32_t* need_tie;         // [B] partition ids not ascending
     uint32_t* tile_hist;       // [G][256] digit counts of each tile, then exclusive prefix inside its segment
     const int32_t* seg0;       // [B] first scan segment of the topic (segments of RT_SEG tiles)

@@ -1,0 +1,26 @@
+#!/bin/bash
+# Round-end measurement pass, run on a B200 through gpurun:
+#   gpurun --timeout 2400 -- 'bash scripts/measure_round.sh'
+# Writes everything under gpurun_out/ (copied into profiles/ afterwards).
+mkdir -p gpurun_out
+cat MEASURED_PEAKS.json 2>/dev/null
+nproc
+for c in 4 2 3 5 6; do
+  timeout -s KILL 400 python bench.py --config $c > gpurun_out/bench_c$c.json 2> gpurun_out/bench_c$c.err
+  tail -c 300 gpurun_out/bench_c$c.err
+done
+for c in 4 6 2; do
+  timeout -s KILL 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+    --log-file gpurun_out/launches_c$c.csv python bench.py --config $c --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+done
+cap() {  # kernel regex, config, skip, output name
+  timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:$1 -s $3 -c 1 \
+    -o gpurun_out/$4 python bench.py --config $2 --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+}
+cap k_warp_topics 4 3 prof_warp_c4
+cap k_big_scatter 6 10 prof_scatter_c6
+cap k_big_tile_hist 6 10 prof_tilehist_c6
+cap k_big_fill 2 1 prof_fill_c2
+LAGASSIGN_LIBRARY=$PWD/variants/liblagassign_timing.so timeout -s KILL 300 python bench.py --config 6 --steps 1 --warmup 3 \
+  --no-cpu-baseline 2>&1 | grep "^pass" > gpurun_out/scatter_phase_cycles.txt
+ls -la gpurun_out
