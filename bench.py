@@ -184,7 +184,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4, 5, 6])
+    ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4, 5, 6, 7])
     ap.add_argument("--scale", type=float, default=1.0, help="scale the workload down (debugging only)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")

@@ -109,6 +109,15 @@ def baseline_config(n, scale=1.0):
         P = 1 << 20
         lag = (splitmix64(np.uint64(0xB200) + np.arange(T * P, dtype=np.uint64)) >> np.uint64(1)).astype(np.int64)
         return uniform_batch(T, P, P, lag), f"{T} topics x {P} partitions, {P} consumers, uniform int64 lag (sort-only variant)"
+    if n == 7:
+        # not a BASELINE config: a "typical deployment" shape for the multi-round fill — many
+        # topics with more partitions than consumers, small lags, half of the partitions idle
+        T = max(1, int(20000 * scale))
+        P, C = 200, 16
+        rng = np.random.default_rng(7)
+        lag = rng.integers(0, 1 << 20, size=T * P, dtype=np.int64)
+        lag[rng.random(T * P) < 0.5] = 0
+        return uniform_batch(T, P, C, lag), f"{T} topics x {P} partitions, {C} consumers, small lags, 50% zero (multi-round fill)"
     raise ValueError(n)
 
 

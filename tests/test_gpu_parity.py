@@ -347,3 +347,59 @@ def test_config5_full_closed_form(pkg):
     assert np.array_equal(got["out_partition"], local.astype(np.int32))
     assert np.array_equal(got["out_consumer_rank"], (local % 1024).astype(np.int32))
     assert st["radix_passes_run"] == 0 and st["topics_device"] > 0
+
+
+# ---- remaining C-ABI entry points -------------------------------------------------------------------
+
+def test_profile_option_and_stats(pkg):
+    """LAGASSIGN_OPT_PROFILE: per-kernel CUDA-event times of the last execute()."""
+    b, _ = baseline_config(5, scale=0.02)
+    with pkg.FlatAssignor(0) as f:
+        f.set_option(pkg.OPT_PROFILE, 1)
+        f.upload(*args_of(b))
+        f.execute()
+        prof = f.profile()
+        st = f.stats()
+        assert "k_warp_topics" in prof and all(ms >= 0 and n >= 1 for ms, n in prof.values())
+        assert 0 < sum(n for _, n in prof.values()) <= st["kernel_launches"]   # the two scan kernels share one scope
+        f.set_option(pkg.OPT_PROFILE, 0)
+        f.execute()
+        assert f.profile() == {}
+        got = f.download()
+    exp = oracle.assign_batch(*args_of(b))
+    assert np.array_equal(got["out_partition"], exp["out_partition"])
+    assert np.array_equal(got["out_consumer_rank"], exp["out_consumer_rank"])
+
+
+def test_bind_device_outputs(pkg):
+    """execute() can write straight into caller-owned device memory (what the all-gather uses)."""
+    import torch
+    rng = np.random.default_rng(3)
+    b = random_flat(rng, T=50, pmin=0, pmax=9000, C=30, lag_kind="u40", n_sets=2)
+    N = len(b["lag"])
+    dp = torch.full((N + 8,), -7, dtype=torch.int32, device="cuda")
+    dc = torch.full((N + 8,), -7, dtype=torch.int32, device="cuda")
+    with pkg.FlatAssignor(0) as f:
+        f.upload(*args_of(b))
+        f.bind_device_outputs(dp.data_ptr() + 16, dc.data_ptr() + 16)
+        f.execute()
+        f.sync()
+        got = f.download()          # download follows the binding
+        f.bind_device_outputs(None, None)
+    exp = oracle.assign_batch(*args_of(b))
+    assert np.array_equal(dp[4:4 + N].cpu().numpy(), exp["out_partition"])
+    assert np.array_equal(dc[4:4 + N].cpu().numpy(), exp["out_consumer_rank"])
+    assert (dp[:4] == -7).all() and (dp[4 + N:] == -7).all()
+    assert np.array_equal(got["out_partition"], exp["out_partition"])
+
+
+def test_realistic_many_rounds(flat):
+    """The common real-world shape: more partitions than consumers (several rounds per topic),
+    small lags with zero tails and duplicates, a few dozen consumers."""
+    rng = np.random.default_rng(99)
+    for C, pmax in ((3, 40), (16, 200), (40, 256), (200, 256), (300, 3000), (700, 9000)):
+        b = random_flat(rng, T=300 if pmax <= 256 else 12, pmin=1, pmax=pmax, C=C, lag_kind="small",
+                        n_sets=3, full_sets=True)
+        z = rng.random(len(b["lag"])) < 0.5          # half of the partitions are caught up
+        b["lag"] = np.where(z, 0, b["lag"]).astype(np.int64)
+        check(flat, b)
