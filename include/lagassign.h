@@ -157,8 +157,10 @@ int  lagassign_assign_batch(lagassign_ctx *ctx, const lagassign_batch *in,
                             const lagassign_result *out);
 
 /* Split form. upload: validate, plan (bin topics by size), copy inputs to HBM.
- * execute: enqueue the kernels (asynchronous). download: wait and copy results
- * to host. execute may be repeated on the same uploaded batch. */
+ * execute: enqueue the kernels (asynchronous, except that batches with topics of
+ * more than 4096 partitions wait once for the digit histograms to decide which radix
+ * passes to launch). download: wait and copy results to host. execute may be repeated
+ * on the same uploaded batch. */
 int  lagassign_upload(lagassign_ctx *ctx, const lagassign_batch *in);
 int  lagassign_upload_offsets(lagassign_ctx *ctx, const lagassign_batch *in,
                               const lagassign_offsets *offs);

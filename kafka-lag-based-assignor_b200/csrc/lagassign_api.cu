@@ -657,7 +657,14 @@ int lagassign_execute(lagassign_ctx* ctx) {
             launch_big_scan(bt, first_pass, st);
             ++launches;
         }
+        // Which digit passes does any topic need? Twelve words back to the host (one short
+        // stream synchronisation, after the histogram + scan kernels) save the four launches
+        // of every pass that would return at once: with low-entropy lags most passes do.
+        uint32_t pass_any[N_PASS];
+        CUDA_TRY(ctx, cudaMemcpyAsync(pass_any, bt.pass_any, sizeof pass_any, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
         for (int p = first_pass; p < N_PASS; ++p) {
+            if (pass_any[p] == 0) continue;
             {
                 ProfScope ps(ctx, K_TILE_HIST);
                 launch_big_tile_hist(bt, p, b.lag, b.part, sms, st);

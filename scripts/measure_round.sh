@@ -1,11 +1,12 @@
 #!/bin/bash
+timeout -s KILL 600 python -m pytest tests -m gpu -q --timeout=600 2>&1 | tail -2
 # Round-end measurement pass, run on a B200 through gpurun:
 #   gpurun --timeout 2400 -- 'bash scripts/measure_round.sh'
 # Writes everything under gpurun_out/ (copied into profiles/ afterwards).
 mkdir -p gpurun_out
 cat MEASURED_PEAKS.json 2>/dev/null
 nproc
-for c in 4 2 3 5 6; do
+for c in 4 2 3 5 6 7; do
   timeout -s KILL 400 python bench.py --config $c > gpurun_out/bench_c$c.json 2> gpurun_out/bench_c$c.err
   tail -c 300 gpurun_out/bench_c$c.err
 done
