@@ -20,6 +20,13 @@
 
 namespace lagassign {
 
+template <int E> struct Log2E;
+template <> struct Log2E<1> { static constexpr int value = 0; };
+template <> struct Log2E<2> { static constexpr int value = 1; };
+template <> struct Log2E<4> { static constexpr int value = 2; };
+template <> struct Log2E<8> { static constexpr int value = 3; };
+template <> struct Log2E<16> { static constexpr int value = 4; };
+
 // One warp, C <= 32*EPTC consumers in registers (position j = lane*EPTC + r).
 //   lag_at(k)        -> int64 lag of the k-th partition in sorted order
 //   put(k, rank)     -> record that sorted partition k goes to global member `rank`
@@ -179,20 +186,74 @@ __device__ __forceinline__ void cta_round_fill_regs(int64_t P, int C, const int3
             // topic, or the zero-lag tail of a busy one) the (total, id) order survives: test
             // (two barriers, ~5 % of a sort) and skip the sort when it holds.
             bool skip = false;
+            constexpr int NW = NT / 32;
+            uint32_t* mm = xbuf + 3 * NT;     // [NW][4]: per-warp min / max of the totals
+            uint64_t gmin = ~0ull, gmax = 0;
             {
                 bool ok = true;
 #pragma unroll
                 for (int r = 0; r + 1 < EPT; ++r)
                     ok = ok && !lt3(w[2][r + 1], w[1][r + 1], w[0][r + 1], w[2][r], w[1][r], w[0][r]);
+                // smallest and largest total of this warp's live consumers (64-bit, hi then lo)
+                uint64_t lmin = ~0ull, lmax = 0;
+#pragma unroll
+                for (int r = 0; r < EPT; ++r) {
+                    if (tid * EPT + r < C) {
+                        const uint64_t tk = ((uint64_t)w[2][r] << 32) | w[1][r];
+                        lmin = tk < lmin ? tk : lmin;
+                        lmax = tk > lmax ? tk : lmax;
+                    }
+                }
+                const uint32_t mnh = __reduce_min_sync(0xffffffffu, (uint32_t)(lmin >> 32));
+                const uint32_t mnl = __reduce_min_sync(0xffffffffu, ((uint32_t)(lmin >> 32) == mnh) ? (uint32_t)lmin : 0xFFFFFFFFu);
+                const uint32_t mxh = __reduce_max_sync(0xffffffffu, (uint32_t)(lmax >> 32));
+                const uint32_t mxl = __reduce_max_sync(0xffffffffu, ((uint32_t)(lmax >> 32) == mxh) ? (uint32_t)lmax : 0u);
                 // first element of the next thread (through shared memory: it may be in another warp)
                 __syncthreads();
                 xbuf[tid] = w[0][0]; xbuf[NT + tid] = w[1][0]; xbuf[2 * NT + tid] = w[2][0];
+                if ((tid & 31) == 0) { uint32_t* row = mm + (tid >> 5) * 4; row[0] = mnh; row[1] = mnl; row[2] = mxh; row[3] = mxl; }
                 __syncthreads();
                 if (tid + 1 < NT)
                     ok = ok && !lt3(xbuf[2 * NT + tid + 1], xbuf[NT + tid + 1], xbuf[tid + 1], w[2][EPT - 1], w[1][EPT - 1], w[0][EPT - 1]);
+                // (read the per-warp rows before the barrier below: the sort reuses this memory)
+#pragma unroll
+                for (int q = 0; q < NW; ++q) {
+                    const uint64_t a = ((uint64_t)mm[q * 4] << 32) | mm[q * 4 + 1];
+                    const uint64_t b2 = ((uint64_t)mm[q * 4 + 2] << 32) | mm[q * 4 + 3];
+                    gmin = a < gmin ? a : gmin;
+                    gmax = b2 > gmax ? b2 : gmax;
+                }
                 skip = __syncthreads_and(ok) != 0;
             }
-            if (!skip) cta_bitonic_sort_regs<EPT, NT>(w, xbuf);
+            if (!skip) {
+                // Totals of one round lie close together (that is what the greedy fill is for):
+                // if (total - smallest total) fits above the index bits of one 64-bit word, sort
+                // that word (6 instructions per compare-exchange instead of 10); else three words.
+                constexpr int B = 8 + Log2E<EPT>::value;          // log2(NT*EPT), NT = 256
+                static_assert(NT == 256, "B assumes 256 threads");
+                if (((gmax - gmin) >> (64 - B)) == 0) {
+                    uint32_t w2[2][EPT];
+#pragma unroll
+                    for (int r = 0; r < EPT; ++r) {
+                        const bool live = w[0][r] != PAY_SENTINEL;
+                        const uint64_t tk = ((uint64_t)w[2][r] << 32) | w[1][r];
+                        const uint64_t v = live ? (((tk - gmin) << B) | w[0][r]) : ~0ull;
+                        w2[0][r] = (uint32_t)v; w2[1][r] = (uint32_t)(v >> 32);
+                    }
+                    cta_bitonic_sort_regs<2, EPT, NT>(w2, xbuf);
+#pragma unroll
+                    for (int r = 0; r < EPT; ++r) {
+                        const uint64_t v = ((uint64_t)w2[1][r] << 32) | w2[0][r];
+                        const bool live = tid * EPT + r < C;       // padding sorts last
+                        const uint64_t tk = (v >> B) + gmin;
+                        w[0][r] = live ? (uint32_t)v & ((1u << B) - 1u) : PAY_SENTINEL;
+                        w[1][r] = live ? (uint32_t)tk : 0xFFFFFFFFu;
+                        w[2][r] = live ? (uint32_t)(tk >> 32) : 0xFFFFFFFFu;
+                    }
+                } else {
+                    cta_bitonic_sort_regs<3, EPT, NT>(w, xbuf);
+                }
+            }
         }
 #pragma unroll
         for (int r = 0; r < EPT; ++r) {

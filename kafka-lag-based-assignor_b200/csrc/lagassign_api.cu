@@ -215,7 +215,7 @@ int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
         if (P <= WARP_MAX_P) l_warp.push_back((int32_t)t);
         else if (P <= CTA_MAX_P) l_cta.push_back((int32_t)t);
         else {
-            if (P >= (int64_t)ST_VAL) return fail(ctx, LAGASSIGN_ERR_UNSUPPORTED, "topic %lld has 2^30 or more partitions", (long long)t);
+            if (P > RT_MAX_P) return fail(ctx, LAGASSIGN_ERR_UNSUPPORTED, "topic %lld has 2^31 or more partitions", (long long)t);
             const int64_t nt = (P + RT_TILE - 1) / RT_TILE;
             if (tiles + nt > 0x7FFFFFFF) return fail(ctx, LAGASSIGN_ERR_UNSUPPORTED, "too many radix tiles");
             const int32_t b = (int32_t)bt_topic.size();

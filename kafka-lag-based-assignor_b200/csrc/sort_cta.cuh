@@ -47,16 +47,23 @@ __device__ __forceinline__ void cta_bitonic_sort(uint64_t* key, uint32_t* pay, i
 }
 
 // ---- register-resident variant -----------------------------------------------------------
-// n = NT*EPT three-word elements (see sort_warp.cuh) held in registers by a CTA of
-// NT threads, logical index i = tid*EPT + r. Strides below EPT are in-register,
-// below 32*EPT warp shuffles, and only the log2(NT/32) highest index bits cross
-// warps: those stages exchange through shared memory (one __syncthreads() each,
-// two alternating buffers). A 1024-element sort is 49 barrier-free stages + 6
-// exchanges instead of 20 barriers in cta_bitonic_sort().
+// n = NT*EPT elements of W words (see sort_warp.cuh; W = 1 or 3 here) held in registers by a
+// CTA of NT threads, logical index i = tid*EPT + r. Strides below EPT are in-register, below
+// 32*EPT warp shuffles, and only the log2(NT/32) highest index bits cross warps: those
+// stages exchange through shared memory (one __syncthreads() each, two alternating
+// buffers). A 1024-element sort is 49 barrier-free stages + 6 exchanges instead of the 20
+// barriers of cta_bitonic_sort().
 //
-// xbuf: 2 * 3 * n words of shared memory. All NT threads must call.
-template <int EPT, int NT>
-__device__ __forceinline__ void cta_bitonic_sort_regs(uint32_t (&w)[3][EPT], uint32_t* xbuf) {
+// xbuf: 2 * W * n words of shared memory. All NT threads must call.
+template <int W>
+__device__ __forceinline__ bool words_less(const uint32_t (&a)[W], const uint32_t (&b)[W]) {
+    if (W == 1) return a[0] < b[0];
+    if (W == 2) return lt2(a[1], a[0], b[1], b[0]);
+    return lt3(a[W - 1], a[W - 2], a[0], b[W - 1], b[W - 2], b[0]);
+}
+
+template <int W, int EPT, int NT>
+__device__ __forceinline__ void cta_bitonic_sort_regs(uint32_t (&w)[W][EPT], uint32_t* xbuf) {
     constexpr int N = NT * EPT;
     constexpr int WARP_SPAN = 32 * EPT;
     const unsigned tid = threadIdx.x, lane = tid & 31u;
@@ -72,38 +79,36 @@ __device__ __forceinline__ void cta_bitonic_sort_regs(uint32_t (&w)[3][EPT], uin
             if (j >= WARP_SPAN) {
                 // partner element lives in another warp: same lane, same slot
                 const unsigned tj = (unsigned)(j / EPT);
-                uint32_t* buf = xbuf + flip * (3 * N);
+                uint32_t* buf = xbuf + flip * (W * N);
                 flip ^= 1;
 #pragma unroll
                 for (int r = 0; r < EPT; ++r) {
 #pragma unroll
-                    for (int x = 0; x < 3; ++x) buf[(x * EPT + r) * NT + tid] = w[x][r];
+                    for (int x = 0; x < W; ++x) buf[(x * EPT + r) * NT + tid] = w[x][r];
                 }
                 __syncthreads();
                 const bool keep_max = (((tid & tj) == 0) != asc_hi);
                 const unsigned pt = tid ^ tj;
 #pragma unroll
                 for (int r = 0; r < EPT; ++r) {
-                    uint32_t o[3];
+                    uint32_t o[W], m[W];
 #pragma unroll
-                    for (int x = 0; x < 3; ++x) o[x] = buf[(x * EPT + r) * NT + pt];
-                    const bool lt = lt3(o[2], o[1], o[0], w[2][r], w[1][r], w[0][r]);
-                    const bool take = (lt != keep_max);
+                    for (int x = 0; x < W; ++x) { o[x] = buf[(x * EPT + r) * NT + pt]; m[x] = w[x][r]; }
+                    const bool take = (words_less<W>(o, m) != keep_max);
 #pragma unroll
-                    for (int x = 0; x < 3; ++x) w[x][r] = take ? o[x] : w[x][r];
+                    for (int x = 0; x < W; ++x) w[x][r] = take ? o[x] : m[x];
                 }
             } else if (j >= EPT) {
                 const unsigned lj = (unsigned)(j / EPT);
                 const bool keep_max = (((lane & lj) == 0) != asc_hi);
 #pragma unroll
                 for (int r = 0; r < EPT; ++r) {
-                    uint32_t o[3];
+                    uint32_t o[W], m[W];
 #pragma unroll
-                    for (int x = 0; x < 3; ++x) o[x] = __shfl_xor_sync(0xffffffffu, w[x][r], lj);
-                    const bool lt = lt3(o[2], o[1], o[0], w[2][r], w[1][r], w[0][r]);
-                    const bool take = (lt != keep_max);
+                    for (int x = 0; x < W; ++x) { o[x] = __shfl_xor_sync(0xffffffffu, w[x][r], lj); m[x] = w[x][r]; }
+                    const bool take = (words_less<W>(o, m) != keep_max);
 #pragma unroll
-                    for (int x = 0; x < 3; ++x) w[x][r] = take ? o[x] : w[x][r];
+                    for (int x = 0; x < W; ++x) w[x][r] = take ? o[x] : m[x];
                 }
             } else {
 #pragma unroll
@@ -111,13 +116,14 @@ __device__ __forceinline__ void cta_bitonic_sort_regs(uint32_t (&w)[3][EPT], uin
                     if ((r & j) == 0) {
                         const bool asc = (k < EPT) ? ((r & k) == 0) : asc_hi;
                         const int q = r | j;
-                        const bool lt = lt3(w[2][q], w[1][q], w[0][q], w[2][r], w[1][r], w[0][r]);
-                        const bool swap = (lt == asc);
+                        uint32_t a[W], b[W];
 #pragma unroll
-                        for (int x = 0; x < 3; ++x) {
-                            const uint32_t a = w[x][r], b = w[x][q];
-                            w[x][r] = swap ? b : a;
-                            w[x][q] = swap ? a : b;
+                        for (int x = 0; x < W; ++x) { a[x] = w[x][r]; b[x] = w[x][q]; }
+                        const bool swap = (words_less<W>(b, a) == asc);
+#pragma unroll
+                        for (int x = 0; x < W; ++x) {
+                            w[x][r] = swap ? b[x] : a[x];
+                            w[x][q] = swap ? a[x] : b[x];
                         }
                     }
                 }

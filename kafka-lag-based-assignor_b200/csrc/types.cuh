@@ -40,9 +40,7 @@ constexpr int N_LAG_PASS = 8;
 constexpr int N_PASS = N_TIE_PASS + N_LAG_PASS;
 
 constexpr int RT_SEG = 64;              // tiles per scan segment
-constexpr uint32_t ST_AGG = 1u << 30;   // tile's own count is published
-constexpr uint32_t ST_INC = 2u << 30;   // inclusive prefix over the topic's tiles so far
-constexpr uint32_t ST_VAL = (1u << 30) - 1;
+constexpr int64_t RT_MAX_P = (1ll << 31) - 1;   // positions and digit counts are 32-bit
 
 enum : int { SEL_RAW = 0, SEL_A = 1, SEL_B = 2, SEL_SKIP = -1 };
 
@@ -82,7 +80,7 @@ struct BigTopics {
     const int32_t* seg_bt;     // [n_segs] segment -> b
     int n_segs;
     uint32_t* seg_total;       // [n_segs][256] segment totals, then start of (segment, digit) inside the topic
-    uint32_t* ticket;          // [N_PASS] unused counters (zeroed per execute)
+    uint32_t* ticket;          // [2*N_PASS+1] small per-execute words: [N_PASS] = passes_run, then pass_any[N_PASS]
     int32_t* passes_run;       // [1] max over topics of executed passes (stat)
     uint32_t* pass_any;        // [N_PASS] does any topic run this pass? (else the launch returns at once)
 };
