@@ -101,7 +101,8 @@ typedef struct lagassign_result {
  * Main:376-404, called per partition at Main:344-356). When given to
  * lagassign_upload_offsets() the device computes
  *   lag = max(end - (has_committed ? committed : (reset_latest ? end : begin)), 0)
- * with wrapping int64 subtraction, in the same pass that builds the sort keys. */
+ * with wrapping int64 subtraction (one elementwise kernel ahead of the sort; the lags
+ * never exist on the host). */
 typedef struct lagassign_offsets {
     const int64_t *begin_offset;  /* [N]  topicBeginOffsets.getOrDefault(p, 0)  Main:350 */
     const int64_t *end_offset;    /* [N]  topicEndOffsets.getOrDefault(p, 0)    Main:351 */

@@ -403,3 +403,40 @@ def test_realistic_many_rounds(flat):
         z = rng.random(len(b["lag"])) < 0.5          # half of the partitions are caught up
         b["lag"] = np.where(z, 0, b["lag"]).astype(np.int64)
         check(flat, b)
+
+
+def test_random_shape_sweep(flat):
+    """Many random (P, C) shapes in ONE batch per seed: every bin, every fill path, random
+    consumer-set sharing, mixed lag distributions. Bit-exact against the oracle."""
+    for seed in range(6):
+        rng = np.random.default_rng(1000 + seed)
+        T = 400
+        # log-uniform partition counts from 1 to ~20000, a few empty topics
+        P = np.floor(2.0 ** (rng.random(T) * 14.3)).astype(np.int64)
+        P[rng.random(T) < 0.03] = 0
+        topic_off = np.concatenate([[0], np.cumsum(P)]).astype(np.int64)
+        N = int(topic_off[-1])
+        kinds = rng.integers(0, 4, size=T)
+        lag = np.empty(N, np.int64)
+        for t in range(T):
+            lo, hi = int(topic_off[t]), int(topic_off[t + 1])
+            n = hi - lo
+            if kinds[t] == 0:
+                lag[lo:hi] = rng.integers(0, 1 << 20, size=n)
+            elif kinds[t] == 1:
+                lag[lo:hi] = rng.integers(0, 3, size=n)
+            elif kinds[t] == 2:
+                lag[lo:hi] = rng.integers(-(1 << 63), (1 << 63) - 1, size=n, dtype=np.int64, endpoint=True)
+            else:
+                v = rng.integers(0, 1 << 45, size=n)
+                v[rng.random(n) < 0.6] = 0
+                lag[lo:hi] = v
+        sizes = [0, 1, 2, 3, 17, 32, 33, 100, 256, 257, 600, 1024, 2000, 5000]
+        M = 6000
+        sets = [np.sort(rng.choice(M, size=c, replace=False)).astype(np.int32) for c in sizes]
+        cset_off = np.concatenate([[0], np.cumsum([len(x) for x in sets])]).astype(np.int64)
+        b = dict(topic_off=topic_off, lag=lag, partition=None if seed % 2 == 0 else
+                 np.concatenate([rng.permutation(int(p)) for p in P] + [np.zeros(0, np.int64)]).astype(np.int32),
+                 topic_cset=rng.integers(0, len(sets), size=T).astype(np.int32), cset_off=cset_off,
+                 cset_rank=np.concatenate(sets).astype(np.int32))
+        check(flat, b)
