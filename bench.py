@@ -309,6 +309,43 @@ def main():
     st2 = f2.stats()
     parity_ok = parity_ok and bool(np.array_equal(h_op[:n_el], exp["out_partition"][:n_el]))
 
+    # ---- the two "next" rows of SURVEY 8(f) that are built, measured beside the hot path (N = 1) ----
+    next_rows = None
+    if world == 1:
+        def timed(fa, steps=5):
+            for _ in range(2):
+                flush(); fa.execute()
+            torch.cuda.synchronize()
+            tot = 0.0
+            for _ in range(steps):
+                flush()
+                a = torch.cuda.Event(enable_timing=True); z = torch.cuda.Event(enable_timing=True)
+                a.record(stream); fa.execute(); z.record(stream); torch.cuda.synchronize()
+                tot += a.elapsed_time(z)
+            return tot / steps
+        fg = pkg.FlatAssignor(local_rank, stream=stream.cuda_stream)
+        fg.set_option(pkg.OPT_GROUP, 1)
+        fg.upload(*args_of(batch))
+        ms_group = timed(fg)
+        g = fg.download_grouping()
+        grouped_ok = bool(g["member_off"][-1] == fg.stats()["n_assigned"])
+        fg.close()
+        fo = pkg.FlatAssignor(local_rank, stream=stream.cuda_stream)
+        fo.set_option(pkg.OPT_PROFILE, 1)
+        lagv = np.maximum(batch["lag"], 0)
+        zeros = np.zeros(len(lagv), np.int64)
+        fo.upload_offsets(batch["topic_off"], zeros, lagv, zeros, np.ones(len(lagv), np.uint8), 1, batch["partition"],
+                          batch["topic_cset"], batch["cset_off"], batch["cset_rank"])
+        ms_off = timed(fo)
+        lag_kernel_ms = fo.profile().get("k_compute_lag", (None, 0))[0]
+        fo.close()
+        next_rows = {"grouping_by_member": {"ms_per_step_with_grouping": ms_group, "ms_per_step_without": t_compute_ms / args.steps,
+                                            "check": "ok" if grouped_ok else "MISMATCH",
+                                            "note": "SURVEY 8f row 2: stable partition of the flat result by member rank on the device"},
+                     "device_lag_computation": {"ms_per_step_with_offsets": ms_off, "k_compute_lag_ms": lag_kernel_ms,
+                                                "note": "SURVEY 8f row 1: computePartitionLag (Main:376-404) as an elementwise kernel, "
+                                                        "33 B/partition"}}
+
     # ---- reduce over ranks --------------------------------------------------------------------
     times = torch.tensor([t_total_ms, t_compute_ms, t_e2e * 1e3, 0.0 if parity_ok else 1.0],
                          dtype=torch.float64, device="cuda")
@@ -367,6 +404,7 @@ def main():
             "compute_ms_per_step": step_ms,
             "gather_ms_per_step": (t_total_ms - t_compute_ms) / args.steps,
             "parity_spot_check": "ok" if bad == 0.0 else "MISMATCH",
+            "next_rows": next_rows,
             "stats": stats,
         }
         if not args.no_cpu_baseline and args.config == 6:

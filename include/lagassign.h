@@ -128,6 +128,7 @@ typedef struct lagassign_stats {
 
 #define LAGASSIGN_OPT_TOTALS  1  /* produce out_total / out_count (default 0) */
 #define LAGASSIGN_OPT_PROFILE 2  /* bracket every kernel launch with CUDA events (default 0) */
+#define LAGASSIGN_OPT_GROUP   3  /* also group the result by member on the device (default 0) */
 
 int  lagassign_abi_version(void);
 
@@ -180,6 +181,23 @@ int  lagassign_bind_device_outputs(lagassign_ctx *ctx, int32_t *d_out_partition,
 int  lagassign_download_lags(lagassign_ctx *ctx, int64_t *lag_out);
 
 int  lagassign_get_stats(const lagassign_ctx *ctx, lagassign_stats *stats);
+
+/* Per-member view of the result (enabled by LAGASSIGN_OPT_GROUP before upload), i.e. the
+ * reference's return value Map<member, List<TopicPartition>> (Main:166-188) in CSR form: the
+ * list of the member with global rank m is
+ *     (topic[i], partition[i])  for i in [member_off[m], member_off[m+1])
+ * with topic[] = index of the topic in the batch, in the order the reference appends them
+ * (Main:264: topics in batch order, inside a topic in assignment order). n_members =
+ * 1 + the largest rank in cset_rank; member_off has n_members + 1 entries; topic and
+ * partition have one entry per assigned partition (lagassign_stats.n_assigned). A JVM caller
+ * only has to wrap slices instead of scattering 8 bytes per partition into per-member lists. */
+typedef struct lagassign_grouping {
+    int64_t *member_off;   /* [n_members + 1] */
+    int32_t *topic;        /* [n_assigned] */
+    int32_t *partition;    /* [n_assigned] */
+} lagassign_grouping;
+int  lagassign_group_sizes(const lagassign_ctx *ctx, int64_t *n_members, int64_t *n_assigned);
+int  lagassign_download_grouping(lagassign_ctx *ctx, const lagassign_grouping *out);
 
 /* Per-kernel device times of the last execute() when LAGASSIGN_OPT_PROFILE is on
  * (CUDA events on the context's stream around each launch). Entries are kernel

@@ -27,6 +27,7 @@ ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_OOM", -4: "ERR_STA
              -5: "ERR_NO_DEVICE", -6: "ERR_UNSUPPORTED"}
 OPT_TOTALS = 1
 OPT_PROFILE = 2
+OPT_GROUP = 3
 
 
 class LagAssignError(RuntimeError):
@@ -50,6 +51,10 @@ class _Offsets(ctypes.Structure):
     _fields_ = [("begin_offset", ctypes.c_void_p), ("end_offset", ctypes.c_void_p),
                 ("committed", ctypes.c_void_p), ("has_committed", ctypes.c_void_p),
                 ("reset_latest", ctypes.c_int32)]
+
+
+class _Grouping(ctypes.Structure):
+    _fields_ = [("member_off", ctypes.c_void_p), ("topic", ctypes.c_void_p), ("partition", ctypes.c_void_p)]
 
 
 class Stats(ctypes.Structure):
@@ -98,6 +103,8 @@ def load_library() -> ctypes.CDLL:
     L.lagassign_bind_device_outputs.argtypes = [vp, vp, vp]
     L.lagassign_download_lags.argtypes = [vp, vp]
     L.lagassign_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    L.lagassign_group_sizes.argtypes = [vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+    L.lagassign_download_grouping.argtypes = [vp, ctypes.POINTER(_Grouping)]
     L.lagassign_profile_count.argtypes = [vp, ctypes.POINTER(ctypes.c_int)]
     L.lagassign_profile_entry.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_char_p),
                                           ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]
@@ -108,6 +115,7 @@ def load_library() -> ctypes.CDLL:
                  "lagassign_upload_offsets", "lagassign_execute", "lagassign_sync", "lagassign_download",
                  "lagassign_bind_device_outputs", "lagassign_download_lags", "lagassign_get_stats",
                  "lagassign_profile_count", "lagassign_profile_entry",
+                 "lagassign_group_sizes", "lagassign_download_grouping",
                  "lagassign_host_alloc", "lagassign_host_free"):
         getattr(L, name).restype = i32
     _lib = L
@@ -266,6 +274,19 @@ class FlatAssignor:
         r = _Result(_ptr(op), _ptr(oc), _ptr(ot), _ptr(on))
         self._check(self._L.lagassign_download(self._ctx, ctypes.byref(r)))
         return dict(out_partition=op, out_consumer_rank=oc, out_total=ot, out_count=on)
+
+    def download_grouping(self):
+        """Per-member CSR view of the result (OPT_GROUP enabled before upload):
+        dict(member_off[M+1], topic[n_assigned], partition[n_assigned])."""
+        m = ctypes.c_int64(0)
+        a = ctypes.c_int64(0)
+        self._check(self._L.lagassign_group_sizes(self._ctx, ctypes.byref(m), ctypes.byref(a)))
+        off = np.empty(m.value + 1, np.int64)
+        topic = np.empty(a.value, np.int32)
+        part = np.empty(a.value, np.int32)
+        g = _Grouping(_ptr(off), _ptr(topic), _ptr(part))
+        self._check(self._L.lagassign_download_grouping(self._ctx, ctypes.byref(g)))
+        return dict(member_off=off, topic=topic, partition=part)
 
     def download_lags(self):
         T, N, _ = self._shape

@@ -57,11 +57,12 @@ k_compute_lag(int64_t n, const int64_t* __restrict__ begin_off, const int64_t* _
 }  // namespace
 
 enum KernelKind { K_COMPUTE_LAG = 0, K_UNASSIGNED, K_WARP, K_CTA, K_ORDER, K_HIST, K_SCAN, K_TILE_HIST, K_PASS_SCANS,
-                  K_SCATTER, K_FINALIZE, K_FILL, K_KINDS };
+                  K_SCATTER, K_FINALIZE, K_FILL, K_GROUP, K_KINDS };
 static const char* const kKernelNames[K_KINDS] = {"k_compute_lag", "k_unassigned_topics", "k_warp_topics",
                                                   "k_cta_topics", "k_big_order_check", "k_big_hist",
                                                   "k_big_scan", "k_big_tile_hist", "k_big_seg_scan+k_big_topic_scan",
-                                                  "k_big_scatter", "k_big_finalize", "k_big_fill"};
+                                                  "k_big_scatter", "k_big_finalize", "k_big_fill",
+                                                  "k_group_keys+finalize+offsets"};
 struct ProfRec { int kind; cudaEvent_t a, b; };
 
 struct lagassign_ctx {
@@ -104,6 +105,13 @@ struct lagassign_ctx {
     std::vector<int32_t> h_list_warp, h_list_cta, h_list_none;
     cudaStream_t stream_in = nullptr, stream_out = nullptr;
     std::vector<cudaEvent_t> pipe_events;
+
+    // grouping of the result by member (LAGASSIGN_OPT_GROUP): an internal child context runs the
+    // radix sort of the flat result by member rank (sort_only = the child's mode)
+    bool want_group = false, sort_only = false;
+    lagassign_ctx* grp = nullptr;
+    int64_t n_members = 0;
+    DevBuf d_grp_topic, d_grp_part, d_member_start, d_member_off;
 
     lagassign_stats stats{};
 };
@@ -181,10 +189,12 @@ int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
         if (in->cset_off[s + 1] < in->cset_off[s]) return fail(ctx, LAGASSIGN_ERR_ARG, "cset_off not monotone at %lld", (long long)s);
     }
     const int64_t R = in->cset_off[S];
+    int64_t n_members = 0;
     if (R > 0 && !in->cset_rank) return fail(ctx, LAGASSIGN_ERR_ARG, "cset_rank is NULL");
     for (int64_t s = 0; s < S; ++s) {
         for (int64_t j = in->cset_off[s]; j < in->cset_off[s + 1]; ++j) {
             if (in->cset_rank[j] < 0) return fail(ctx, LAGASSIGN_ERR_ARG, "negative member rank in set %lld", (long long)s);
+            n_members = std::max<int64_t>(n_members, (int64_t)in->cset_rank[j] + 1);
             if (j > in->cset_off[s] && in->cset_rank[j] <= in->cset_rank[j - 1])
                 return fail(ctx, LAGASSIGN_ERR_ARG, "member ranks of set %lld are not strictly ascending", (long long)s);
         }
@@ -206,14 +216,14 @@ int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
         const int64_t C = in->cset_off[s + 1] - in->cset_off[s];
         tc_off[(size_t)t + 1] = tc_off[(size_t)t] + C;
         if (P == 0) continue;
-        if (C == 0) { l_none.push_back((int32_t)t); continue; }
+        if (C == 0 && !ctx->sort_only) { l_none.push_back((int32_t)t); continue; }
         assigned += P;
         if (P > C && C > FILL_CTA_MAX_C)
             return fail(ctx, LAGASSIGN_ERR_UNSUPPORTED,
                         "topic %lld: %lld partitions over %lld consumers needs multi-round fill with more than %d consumers",
                         (long long)t, (long long)P, (long long)C, FILL_CTA_MAX_C);
-        if (P <= WARP_MAX_P) l_warp.push_back((int32_t)t);
-        else if (P <= CTA_MAX_P) l_cta.push_back((int32_t)t);
+        if (P <= WARP_MAX_P && !ctx->sort_only) l_warp.push_back((int32_t)t);
+        else if (P <= CTA_MAX_P && !ctx->sort_only) l_cta.push_back((int32_t)t);
         else {
             if (P > RT_MAX_P) return fail(ctx, LAGASSIGN_ERR_UNSUPPORTED, "topic %lld has 2^31 or more partitions", (long long)t);
             const int64_t nt = (P + RT_TILE - 1) / RT_TILE;
@@ -245,6 +255,7 @@ int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
         }
     }
     ctx->T = T; ctx->N = N; ctx->S = S; ctx->R = R;
+    ctx->n_members = n_members;
     ctx->total_tc = tc_off[(size_t)T];
     ctx->n_assigned = assigned;
     ctx->big_elems = boff;
@@ -358,8 +369,35 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
     TRY(upload_vec(ctx, ctx->d_tile_bt, tile_bt.data(), tile_bt.size()));
 
     // outputs and workspaces
-    CUDA_TRY(ctx, ctx->d_out_part.ensure(std::max<size_t>((size_t)N, 1) * sizeof(int32_t)));
-    CUDA_TRY(ctx, ctx->d_out_cons.ensure(std::max<size_t>((size_t)N, 1) * sizeof(int32_t)));
+    if (!ctx->sort_only) {
+        CUDA_TRY(ctx, ctx->d_out_part.ensure(std::max<size_t>((size_t)N, 1) * sizeof(int32_t)));
+        CUDA_TRY(ctx, ctx->d_out_cons.ensure(std::max<size_t>((size_t)N, 1) * sizeof(int32_t)));
+    }
+    if (ctx->want_group && N > 0) {
+        // the flat result as ONE topic of N elements, sorted by the child context
+        if (N > RT_MAX_P) return fail(ctx, LAGASSIGN_ERR_UNSUPPORTED, "grouping needs fewer than 2^31 partitions per batch");
+        if (!ctx->grp) {
+            lagassign_ctx* child = new (std::nothrow) lagassign_ctx();
+            if (!child) return fail(ctx, LAGASSIGN_ERR_OOM, "out of host memory");
+            child->device = ctx->device; child->stream = ctx->stream; child->own_stream = false;
+            child->sm_count = ctx->sm_count; child->sort_only = true;
+            ctx->grp = child;
+        }
+        const int64_t g_topic_off[2] = {0, N};
+        const int64_t g_cset_off[2] = {0, 0};
+        const int32_t g_topic_cset[1] = {0};
+        static const int64_t dummy_lag = 0;
+        lagassign_batch gb{};
+        gb.n_topics = 1; gb.topic_off = g_topic_off; gb.lag = &dummy_lag; gb.partition = nullptr;
+        gb.topic_cset = g_topic_cset; gb.n_csets = 1; gb.cset_off = g_cset_off; gb.cset_rank = nullptr;
+        int rc = do_upload(ctx->grp, &gb, nullptr, /*defer_data=*/true);      // plan only: its lags are written on the device
+        if (rc != LAGASSIGN_OK) return fail(ctx, rc, "grouping plan: %s", ctx->grp->err.c_str());
+        ctx->grp->uploaded = true;
+        CUDA_TRY(ctx, ctx->d_grp_topic.ensure(std::max<size_t>((size_t)ctx->n_assigned, 1) * sizeof(int32_t)));
+        CUDA_TRY(ctx, ctx->d_grp_part.ensure(std::max<size_t>((size_t)ctx->n_assigned, 1) * sizeof(int32_t)));
+        CUDA_TRY(ctx, ctx->d_member_start.ensure((size_t)(ctx->n_members + 1) * sizeof(int64_t)));
+        CUDA_TRY(ctx, ctx->d_member_off.ensure((size_t)(ctx->n_members + 1) * sizeof(int64_t)));
+    }
     if (ctx->want_totals) {
         CUDA_TRY(ctx, ctx->d_out_total.ensure(std::max<size_t>((size_t)ctx->total_tc, 1) * sizeof(int64_t)));
         CUDA_TRY(ctx, ctx->d_out_count.ensure(std::max<size_t>((size_t)ctx->total_tc, 1) * sizeof(int32_t)));
@@ -562,6 +600,9 @@ void lagassign_destroy(lagassign_ctx* ctx) {
                       &ctx->d_status, &ctx->d_seg_total, &ctx->d_bt_seg0, &ctx->d_seg_bt, &ctx->d_tile_desc, &ctx->d_ticket, &ctx->d_out_part, &ctx->d_out_cons,
                       &ctx->d_out_total, &ctx->d_out_count};
     for (DevBuf* b : bufs) b->release();
+    if (ctx->grp) { lagassign_destroy(ctx->grp); ctx->grp = nullptr; }
+    DevBuf* gbufs[] = {&ctx->d_grp_topic, &ctx->d_grp_part, &ctx->d_member_start, &ctx->d_member_off};
+    for (DevBuf* gb : gbufs) gb->release();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->pipe_events) cudaEventDestroy(e);
     if (ctx->stream_in) cudaStreamDestroy(ctx->stream_in);
@@ -579,6 +620,10 @@ int lagassign_set_option(lagassign_ctx* ctx, int option, int64_t value) {
     switch (option) {
         case LAGASSIGN_OPT_PROFILE:
             ctx->profile = value != 0;
+            return LAGASSIGN_OK;
+        case LAGASSIGN_OPT_GROUP:
+            ctx->want_group = value != 0;
+            ctx->uploaded = false;   // the grouping plan and buffers are set up at upload
             return LAGASSIGN_OK;
         case LAGASSIGN_OPT_TOTALS:
             ctx->want_totals = value != 0;
@@ -679,16 +724,34 @@ int lagassign_execute(lagassign_ctx* ctx) {
             }
             launches += 4;
         }
-        {
+        if (!ctx->sort_only) {
             ProfScope ps(ctx, K_FINALIZE);
             launch_big_finalize(bt, b, sms, st);
             ++launches;
         }
-        if (ctx->n_fill > 0) {
+        if (ctx->n_fill > 0 && !ctx->sort_only) {
             ProfScope ps(ctx, K_FILL);
             launch_big_fill(bt, ctx->d_list_fill.as<int32_t>(), ctx->n_fill, b, sms, st);
             ++launches;
         }
+    }
+    if (ctx->want_group && ctx->N > 0 && ctx->grp) {
+        // stable partition of the flat result by member rank, see radix.cuh section 7
+        lagassign_ctx* child = ctx->grp;
+        {
+            ProfScope ps(ctx, K_GROUP);
+            launch_group_keys(ctx->N, b.out_cons, ctx->n_members, child->d_lag.as<int64_t>(), sms, st);
+        }
+        int rc = lagassign_execute(child);
+        if (rc != LAGASSIGN_OK) return fail(ctx, rc, "grouping sort: %s", child->err.c_str());
+        {
+            ProfScope ps(ctx, K_GROUP);
+            launch_group_finalize(make_big(child), child->d_lag.as<int64_t>(), ctx->n_members, ctx->N - ctx->n_assigned,
+                                  b.out_part, b.topic_off, ctx->T, ctx->d_grp_topic.as<int32_t>(),
+                                  ctx->d_grp_part.as<int32_t>(), ctx->d_member_start.as<int64_t>(),
+                                  ctx->d_member_off.as<int64_t>(), ctx->n_assigned, sms, st);
+        }
+        launches += 4 + child->stats.kernel_launches;
     }
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->stats.kernel_launches = launches;
@@ -744,7 +807,7 @@ int lagassign_assign_batch(lagassign_ctx* ctx, const lagassign_batch* in, const 
     if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
     if (!out) return fail(ctx, LAGASSIGN_ERR_ARG, "result is NULL");
     TRY(do_upload(ctx, in, nullptr, /*defer_data=*/true));     // plan + metadata; the large arrays follow
-    if (ctx->n_big == 0 && !ctx->want_totals && ctx->N >= PIPE_MIN_ELEMS && !out->out_total && !out->out_count)
+    if (ctx->n_big == 0 && !ctx->want_totals && !ctx->want_group && ctx->N >= PIPE_MIN_ELEMS && !out->out_total && !out->out_count)
         return assign_batch_pipelined(ctx, in, out);
     TRY(upload_data_now(ctx, in));
     TRY(lagassign_execute(ctx));
@@ -766,6 +829,31 @@ int lagassign_download_lags(lagassign_ctx* ctx, int64_t* lag_out) {
     if (!ctx->executed) return fail(ctx, LAGASSIGN_ERR_STATE, "download_lags() before execute()");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (ctx->N) CUDA_TRY(ctx, cudaMemcpyAsync(lag_out, ctx->d_lag.p, (size_t)ctx->N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return LAGASSIGN_OK;
+}
+
+int lagassign_group_sizes(const lagassign_ctx* ctx, int64_t* n_members, int64_t* n_assigned) {
+    if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
+    if (n_members) *n_members = ctx->n_members;
+    if (n_assigned) *n_assigned = ctx->n_assigned;
+    return LAGASSIGN_OK;
+}
+
+int lagassign_download_grouping(lagassign_ctx* ctx, const lagassign_grouping* out) {
+    if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
+    if (!out || !out->member_off) return fail(ctx, LAGASSIGN_ERR_ARG, "grouping output is NULL");
+    if (!ctx->want_group) return fail(ctx, LAGASSIGN_ERR_STATE, "LAGASSIGN_OPT_GROUP was not enabled before upload()");
+    if (!ctx->executed) return fail(ctx, LAGASSIGN_ERR_STATE, "download_grouping() before execute()");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t M = (size_t)ctx->n_members, NA = (size_t)ctx->n_assigned;
+    if (ctx->N == 0) {
+        for (size_t m = 0; m <= M; ++m) out->member_off[m] = 0;
+        return LAGASSIGN_OK;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(out->member_off, ctx->d_member_off.p, (M + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (NA && out->topic) CUDA_TRY(ctx, cudaMemcpyAsync(out->topic, ctx->d_grp_topic.p, NA * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (NA && out->partition) CUDA_TRY(ctx, cudaMemcpyAsync(out->partition, ctx->d_grp_part.p, NA * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return LAGASSIGN_OK;
 }

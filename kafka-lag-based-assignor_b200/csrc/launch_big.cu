@@ -60,4 +60,22 @@ void launch_big_fill(const BigTopics& bt, const int32_t* fill_list, int n_fill, 
         bt, fill_list, n_fill, b.lag, b.topic_cset, b.cset_off, b.cset_rank, b.tc_off, b.out_cons, b.out_total, b.out_count);
 }
 
+void launch_group_keys(int64_t n, const int32_t* out_cons, int64_t n_members, int64_t* glag, int sms, cudaStream_t st) {
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sms * 16);
+    k_group_keys<<<grid, 256, 0, st>>>(n, out_cons, n_members, glag);
+}
+
+void launch_group_finalize(const BigTopics& bt, const int64_t* glag, int64_t n_members, int64_t n_unassigned,
+                           const int32_t* out_part, const int64_t* topic_off, int64_t n_topics, int32_t* grp_topic,
+                           int32_t* grp_part, int64_t* member_start, int64_t* member_off, int64_t n_assigned, int sms,
+                           cudaStream_t st) {
+    cudaMemsetAsync(member_start, 0xFF, (size_t)(n_members + 1) * sizeof(int64_t), st);   // -1 = no partitions
+    if (n_assigned > 0) {
+        const int grid = (int)std::min<int64_t>((n_assigned + 255) / 256, (int64_t)sms * 16);
+        k_group_finalize<<<grid, 256, 0, st>>>(bt, glag, n_members, n_unassigned, out_part, topic_off, n_topics,
+                                               grp_topic, grp_part, member_start);
+    }
+    k_group_offsets<<<1, 1024, 0, st>>>(n_members, n_assigned, member_start, member_off);
+}
+
 }  // namespace lagassign

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "types.cuh"
 #include "fill.cuh"
+#include <cstdint>
 #include <cstdio>
 
 namespace lagassign {
@@ -575,6 +576,82 @@ k_big_fill(BigTopics bt, const int32_t* __restrict__ fill_list, int n_fill,
             cta_round_fill<BIGFILL_MAXJ>(P, C, max(64, 1 << (32 - __clz(C - 1))), cset, ckey, cidx,
                                          lag_at, put, tot, cnt);
         }
+        __syncthreads();
+    }
+}
+
+// ---- 7. grouping of the result by member -----------------------
+// The reference appends to one list per member (Main:264), so a member's list is ordered by
+// topic (iteration order), then by assignment order: exactly the flat result order, filtered
+// by member. Grouping is therefore a STABLE partition of the flat result by member rank, done
+// with the same radix machinery: the whole flat result is one "topic" whose lag is
+// M - rank (descending lag == ascending rank; unassigned elements get M + 1 and sort first).
+__global__ void __launch_bounds__(256)
+k_group_keys(int64_t n, const int32_t* __restrict__ out_cons, int64_t n_members, int64_t* __restrict__ glag) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t r = out_cons[e];
+        glag[e] = r < 0 ? n_members + 1 : n_members - r;
+    }
+}
+
+// sorted position i -> (topic index, partition) of the element, in the member-grouped arrays;
+// member_start[m] = first grouped position of member m (members without partitions stay unset)
+__global__ void __launch_bounds__(256)
+k_group_finalize(BigTopics bt, const int64_t* __restrict__ glag, int64_t n_members, int64_t n_unassigned,
+                 const int32_t* __restrict__ out_part, const int64_t* __restrict__ topic_off, int64_t n_topics,
+                 int32_t* __restrict__ grp_topic, int32_t* __restrict__ grp_part, int64_t* __restrict__ member_start) {
+    const int64_t n = bt.P[0];
+    const int sel = bt.sel_final[0];
+    const uint32_t* fpay = (sel == SEL_A) ? bt.payA : bt.payB;
+    for (int64_t i = n_unassigned + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = (sel == SEL_RAW) ? i : (int64_t)fpay[i];
+        const int64_t rank = n_members - glag[e];
+        const int64_t o = i - n_unassigned;
+        // topic of flat element e: last t with topic_off[t] <= e
+        int64_t lo = 0, hi = n_topics;
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (topic_off[mid] <= e) lo = mid; else hi = mid;
+        }
+        grp_topic[o] = (int32_t)lo;
+        grp_part[o] = out_part[e];
+        bool first = (i == n_unassigned);
+        if (!first) {
+            const int64_t ep = (sel == SEL_RAW) ? i - 1 : (int64_t)fpay[i - 1];
+            first = (n_members - glag[ep]) != rank;
+        }
+        if (first) member_start[rank] = o;
+    }
+}
+
+// member_off[m] = start of member m, members without partitions take the next member's start
+__global__ void __launch_bounds__(1024)
+k_group_offsets(int64_t n_members, int64_t n_assigned, const int64_t* __restrict__ member_start,
+                int64_t* __restrict__ member_off) {
+    __shared__ int64_t carry;
+    __shared__ int64_t wmin[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { carry = n_assigned; member_off[n_members] = n_assigned; }
+    __syncthreads();
+    // suffix minimum, chunks of blockDim.x from the end (starts increase with m where set; unset = -1)
+    for (int64_t hi = n_members; hi > 0; hi -= blockDim.x) {
+        const int64_t m = hi - 1 - tid;
+        int64_t v = INT64_MAX;
+        if (m >= 0) { const int64_t sv = member_start[m]; if (sv >= 0) v = sv; }
+        // inclusive suffix-min over the chunk in thread order (thread 0 = highest m)
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t o = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v = o < v ? o : v;
+        }
+        if (lane == 31) wmin[warp] = v;
+        __syncthreads();
+        int64_t pre = carry;
+        for (int w = 0; w < warp; ++w) pre = wmin[w] < pre ? wmin[w] : pre;
+        v = pre < v ? pre : v;
+        if (m >= 0) member_off[m] = v;
+        __syncthreads();
+        if (tid == blockDim.x - 1) carry = v;
         __syncthreads();
     }
 }

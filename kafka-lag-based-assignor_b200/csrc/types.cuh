@@ -105,5 +105,10 @@ void launch_big_pass_scans(const BigTopics& bt, int pass, cudaStream_t st);   //
 void launch_big_scatter(const BigTopics& bt, int pass, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st);
 void launch_big_finalize(const BigTopics& bt, const DevBatch& b, int sms, cudaStream_t st);
 void launch_big_fill(const BigTopics& bt, const int32_t* fill_list, int n_fill, const DevBatch& b, int sms, cudaStream_t st);
+void launch_group_keys(int64_t n, const int32_t* out_cons, int64_t n_members, int64_t* glag, int sms, cudaStream_t st);
+void launch_group_finalize(const BigTopics& bt, const int64_t* glag, int64_t n_members, int64_t n_unassigned,
+                           const int32_t* out_part, const int64_t* topic_off, int64_t n_topics, int32_t* grp_topic,
+                           int32_t* grp_part, int64_t* member_start, int64_t* member_off, int64_t n_assigned, int sms,
+                           cudaStream_t st);
 
 }  // namespace lagassign

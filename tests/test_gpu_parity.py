@@ -440,3 +440,61 @@ def test_random_shape_sweep(flat):
                  topic_cset=rng.integers(0, len(sets), size=T).astype(np.int32), cset_off=cset_off,
                  cset_rank=np.concatenate(sets).astype(np.int32))
         check(flat, b)
+
+
+def _expected_grouping(b, res):
+    """Reference list order (Main:264): per member, topics in batch order, then assignment order
+    = a stable partition of the flat result by member rank."""
+    off = b["topic_off"]
+    topic_of = np.repeat(np.arange(len(off) - 1, dtype=np.int32), np.diff(off))
+    cons = res["out_consumer_rank"]
+    keep = np.nonzero(cons >= 0)[0]
+    order = keep[np.argsort(cons[keep], kind="stable")]
+    M = int(b["cset_rank"].max()) + 1 if len(b["cset_rank"]) else 0
+    counts = np.bincount(cons[keep], minlength=M)
+    member_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return member_off, topic_of[order], res["out_partition"][order]
+
+
+@pytest.mark.parametrize("shape", ["small", "mixed", "config4"])
+def test_grouping_by_member(pkg, shape):
+    """LAGASSIGN_OPT_GROUP: the reference's Map<member, List<TopicPartition>> in CSR form,
+    built on the device."""
+    rng = np.random.default_rng(5)
+    if shape == "small":
+        b = random_flat(rng, T=7, pmin=0, pmax=30, C=5, lag_kind="dups", n_sets=3)
+    elif shape == "mixed":
+        b = random_flat(rng, T=300, pmin=0, pmax=6000, C=700, lag_kind="u40", explicit_ids="shuffled", n_sets=5)
+    else:
+        b, _ = baseline_config(4, scale=0.1)
+    with pkg.FlatAssignor(0) as f:
+        f.set_option(pkg.OPT_GROUP, 1)
+        f.upload(*args_of(b))
+        f.execute()
+        res = f.download()
+        g = f.download_grouping()
+        f.execute()                      # repeatable
+        g2 = f.download_grouping()
+    exp = oracle.assign_batch(*args_of(b), threads=8)
+    assert np.array_equal(res["out_partition"], exp["out_partition"])
+    assert np.array_equal(res["out_consumer_rank"], exp["out_consumer_rank"])
+    e_off, e_topic, e_part = _expected_grouping(b, exp)
+    assert np.array_equal(g["member_off"], e_off)
+    assert np.array_equal(g["topic"], e_topic)
+    assert np.array_equal(g["partition"], e_part)
+    for k in g:
+        assert np.array_equal(g[k], g2[k])
+
+
+def test_grouping_reference_vector(pkg):
+    """Test:112-125 of the reference, read from the grouped arrays: consumer-1 =
+    [topic1-0, topic1-2, topic2-0, topic2-1], consumer-2 = [topic1-1, topic1-3]."""
+    topic_off = np.array([0, 4, 6], np.int64)           # topic1, topic2 in HashMap order
+    lag = np.array([100000, 100000, 500, 1, 900000, 100000], np.int64)
+    with pkg.FlatAssignor(0) as f:
+        f.set_option(pkg.OPT_GROUP, 1)
+        f.upload(topic_off, lag, None, [0, 1], [0, 2, 3], [0, 1, 0])
+        f.execute()
+        g = f.download_grouping()
+    assert g["member_off"].tolist() == [0, 4, 6]
+    assert list(zip(g["topic"].tolist(), g["partition"].tolist())) == [(0, 0), (0, 2), (1, 0), (1, 1), (0, 1), (0, 3)]
