@@ -107,14 +107,17 @@ class ShardedAssignor:
         dev = torch.device("cuda", torch.cuda.current_device())
         self.equal = len(set(self.counts)) == 1
         self.start = int(sum(self.counts[:self.rank]))
-        self.full_part = torch.empty(total, dtype=torch.int32, device=dev)
-        self.full_cons = torch.empty(total, dtype=torch.int32, device=dev)
+        n = self.counts[self.rank]
         if self.equal:
-            # kernels write into this rank's slice; the all-gather is then in place
-            self.f.bind_device_outputs(self.full_part.data_ptr() + 4 * self.start,
-                                       self.full_cons.data_ptr() + 4 * self.start)
+            # One buffer [rank][partition | consumer][n]: the kernels write into this rank's block and
+            # ONE in-place all-gather moves both result arrays (a second collective launch costs more
+            # than the extra bytes).
+            self.buf = torch.empty((self.world, 2, max(n, 1)), dtype=torch.int32, device=dev)
+            self.f.bind_device_outputs(self.buf[self.rank, 0].data_ptr(), self.buf[self.rank, 1].data_ptr())
+            self.full_part = self.full_cons = None
         else:
-            n = self.counts[self.rank]
+            self.full_part = torch.empty(total, dtype=torch.int32, device=dev)
+            self.full_cons = torch.empty(total, dtype=torch.int32, device=dev)
             self.loc_part = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
             self.loc_cons = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
             self.f.bind_device_outputs(self.loc_part.data_ptr(), self.loc_cons.data_ptr())
@@ -131,13 +134,14 @@ class ShardedAssignor:
             return
         n = self.counts[self.rank]
         if self.equal:
-            dist.all_gather_into_tensor(self.full_part, self.full_part[self.start:self.start + n], group=self.group)
-            dist.all_gather_into_tensor(self.full_cons, self.full_cons[self.start:self.start + n], group=self.group)
+            dist.all_gather_into_tensor(self.buf.view(-1), self.buf[self.rank].view(-1), group=self.group)
         else:
             self.full_part, self.full_cons = all_gather_results(self.loc_part[:n], self.loc_cons[:n],
                                                                 self.counts, self.group)
 
     def results(self):
-        if self.world == 1 and not self.equal:
-            return self.loc_part, self.loc_cons
+        """(out_partition, out_consumer_rank) of the whole batch as contiguous 1-D tensors."""
+        if self.equal:
+            n = self.counts[self.rank]
+            return self.buf[:, 0, :n].reshape(-1), self.buf[:, 1, :n].reshape(-1)
         return self.full_part, self.full_cons
