@@ -31,6 +31,12 @@ __device__ __forceinline__ bool elem_less(uint64_t ka, uint32_t pa, uint64_t kb,
     return ka < kb || (ka == kb && pa < pb);
 }
 
+// number of significant bits of x (0 for x == 0)
+__device__ __forceinline__ int bits_of(uint64_t x) {
+    const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
+    return hi ? 64 - __clz(hi) : (lo ? 32 - __clz(lo) : 0);
+}
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 
 // Streaming loads/stores: inputs are read once and outputs written once.

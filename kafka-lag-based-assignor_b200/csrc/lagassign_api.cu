@@ -84,14 +84,14 @@ struct lagassign_ctx {
     bool uploaded = false, executed = false, has_part = false, has_offsets = false;
     int reset_latest = 0;
     int64_t T = 0, N = 0, S = 0, R = 0, total_tc = 0, n_assigned = 0;
-    int n_warp = 0, n_cta = 0, n_none = 0, n_big = 0, n_tiles = 0, n_fill = 0;
+    int n_warp = 0, n_cta[N_CTA_CLASSES] = {0, 0, 0, 0}, n_none = 0, n_big = 0, n_tiles = 0, n_fill = 0;
     int64_t big_elems = 0;
 
     // inputs in HBM
     DevBuf d_topic_off, d_lag, d_part, d_topic_cset, d_cset_off, d_cset_rank, d_tc_off;
     DevBuf d_begin, d_end, d_committed, d_hascommitted;
     // plan lists
-    DevBuf d_list_warp, d_list_cta, d_list_none, d_list_fill;
+    DevBuf d_list_warp, d_list_cta[N_CTA_CLASSES], d_list_none, d_list_fill;
     DevBuf d_bt_topic, d_bt_off, d_bt_P, d_bt_boff, d_bt_tile0, d_bt_seg0, d_tile_bt, d_seg_bt, d_seg_total, d_tile_desc;
     int n_segs = 0;
     // radix workspaces
@@ -102,7 +102,7 @@ struct lagassign_ctx {
     int32_t* bound_cons = nullptr;
 
     // host copies of the bin lists (ascending topic ids) for the chunked assign_batch() pipeline
-    std::vector<int32_t> h_list_warp, h_list_cta, h_list_none;
+    std::vector<int32_t> h_list_warp, h_list_cta[N_CTA_CLASSES], h_list_none;
     cudaStream_t stream_in = nullptr, stream_out = nullptr;
     std::vector<cudaEvent_t> pipe_events;
 
@@ -174,7 +174,7 @@ struct ProfScope {   // records an event pair around one launch when profiling i
 };
 
 int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
-                      std::vector<int32_t>& l_warp, std::vector<int32_t>& l_cta, std::vector<int32_t>& l_none,
+                      std::vector<int32_t>& l_warp, std::vector<int32_t> (&l_cta)[N_CTA_CLASSES], std::vector<int32_t>& l_none,
                       std::vector<int32_t>& bt_topic, std::vector<int64_t>& bt_off, std::vector<int64_t>& bt_P,
                       std::vector<int64_t>& bt_boff, std::vector<int32_t>& bt_tile0, std::vector<int32_t>& tile_bt,
                       std::vector<int32_t>& l_fill, std::vector<int64_t>& tc_off, std::vector<int32_t>& bt_seg0,
@@ -223,7 +223,7 @@ int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
                         "topic %lld: %lld partitions over %lld consumers needs multi-round fill with more than %d consumers",
                         (long long)t, (long long)P, (long long)C, FILL_CTA_MAX_C);
         if (P <= WARP_MAX_P && !ctx->sort_only) l_warp.push_back((int32_t)t);
-        else if (P <= CTA_MAX_P && !ctx->sort_only) l_cta.push_back((int32_t)t);
+        else if (P <= CTA_MAX_P && !ctx->sort_only) l_cta[cta_class_of(P)].push_back((int32_t)t);
         else {
             if (P > RT_MAX_P) return fail(ctx, LAGASSIGN_ERR_UNSUPPORTED, "topic %lld has 2^31 or more partitions", (long long)t);
             const int64_t nt = (P + RT_TILE - 1) / RT_TILE;
@@ -315,7 +315,7 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
     ctx->uploaded = ctx->executed = false;
     ctx->stats = lagassign_stats{};
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    std::vector<int32_t> l_warp, l_cta, l_none, bt_topic, bt_tile0, tile_bt, l_fill, bt_seg0, seg_bt;
+    std::vector<int32_t> l_warp, l_cta[N_CTA_CLASSES], l_none, bt_topic, bt_tile0, tile_bt, l_fill, bt_seg0, seg_bt;
     std::vector<TileDesc> tile_desc;
     std::vector<int64_t> bt_off, bt_P, bt_boff, tc_off;
     lagassign_batch tmp;
@@ -332,7 +332,8 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
     const int64_t T = ctx->T, N = ctx->N;
     ctx->has_part = in->partition != nullptr;
     ctx->has_offsets = offs != nullptr;
-    ctx->n_warp = (int)l_warp.size(); ctx->n_cta = (int)l_cta.size(); ctx->n_none = (int)l_none.size();
+    ctx->n_warp = (int)l_warp.size(); ctx->n_none = (int)l_none.size();
+    for (int c = 0; c < N_CTA_CLASSES; ++c) ctx->n_cta[c] = (int)l_cta[c].size();
     ctx->n_big = (int)bt_topic.size(); ctx->n_tiles = (int)tile_bt.size(); ctx->n_fill = (int)l_fill.size();
 
     TRY(upload_vec(ctx, ctx->d_topic_off, in->topic_off, (size_t)T + 1));
@@ -355,7 +356,7 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
     TRY(upload_vec(ctx, ctx->d_cset_rank, in->cset_rank, (size_t)ctx->R));
     TRY(upload_vec(ctx, ctx->d_tc_off, tc_off.data(), tc_off.size()));
     TRY(upload_vec(ctx, ctx->d_list_warp, l_warp.data(), l_warp.size()));
-    TRY(upload_vec(ctx, ctx->d_list_cta, l_cta.data(), l_cta.size()));
+    for (int c = 0; c < N_CTA_CLASSES; ++c) TRY(upload_vec(ctx, ctx->d_list_cta[c], l_cta[c].data(), l_cta[c].size()));
     TRY(upload_vec(ctx, ctx->d_list_none, l_none.data(), l_none.size()));
     TRY(upload_vec(ctx, ctx->d_list_fill, l_fill.data(), l_fill.size()));
     TRY(upload_vec(ctx, ctx->d_bt_topic, bt_topic.data(), bt_topic.size()));
@@ -423,12 +424,12 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
     ctx->stats.n_partitions = N;
     ctx->stats.n_assigned = ctx->n_assigned;
     ctx->stats.topics_warp = ctx->n_warp;
-    ctx->stats.topics_cta = ctx->n_cta;
+    ctx->stats.topics_cta = (int64_t)ctx->n_cta[0] + ctx->n_cta[1] + ctx->n_cta[2] + ctx->n_cta[3];
     ctx->stats.topics_device = ctx->n_big;
     ctx->stats.topics_unassigned = ctx->n_none;
     ctx->stats.device_sort_elems = ctx->big_elems;
     ctx->h_list_warp.swap(l_warp);
-    ctx->h_list_cta.swap(l_cta);
+    for (int c = 0; c < N_CTA_CLASSES; ++c) ctx->h_list_cta[c].swap(l_cta[c]);
     ctx->h_list_none.swap(l_none);
     ctx->uploaded = !defer_data;
     return LAGASSIGN_OK;
@@ -504,8 +505,10 @@ int assign_batch_pipelined(lagassign_ctx* ctx, const lagassign_batch* in, const 
         if (hi > lo) { launch_unassigned_topics(b, ctx->d_list_none.as<int32_t>() + lo, hi - lo, ctx->stream); ++launches; }
         slice(ctx->h_list_warp, lo, hi);
         if (hi > lo) { launch_warp_topics(b, ctx->d_list_warp.as<int32_t>() + lo, hi - lo, ctx->stream); ++launches; }
-        slice(ctx->h_list_cta, lo, hi);
-        if (hi > lo) { launch_cta_topics(b, ctx->d_list_cta.as<int32_t>() + lo, hi - lo, ctx->sm_count, ctx->stream); ++launches; }
+        for (int c2 = 0; c2 < N_CTA_CLASSES; ++c2) {
+            slice(ctx->h_list_cta[c2], lo, hi);
+            if (hi > lo) { launch_cta_topics(b, ctx->d_list_cta[c2].as<int32_t>() + lo, hi - lo, c2, ctx->sm_count, ctx->stream); ++launches; }
+        }
         CUDA_TRY(ctx, cudaEventRecord(ev_out, ctx->stream));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_out, ev_out, 0));
         if (n && out->out_partition) {
@@ -593,7 +596,7 @@ void lagassign_destroy(lagassign_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_topic_off, &ctx->d_lag, &ctx->d_part, &ctx->d_topic_cset, &ctx->d_cset_off,
                       &ctx->d_cset_rank, &ctx->d_tc_off, &ctx->d_begin, &ctx->d_end, &ctx->d_committed,
-                      &ctx->d_hascommitted, &ctx->d_list_warp, &ctx->d_list_cta, &ctx->d_list_none,
+                      &ctx->d_hascommitted, &ctx->d_list_warp, &ctx->d_list_cta[0], &ctx->d_list_cta[1], &ctx->d_list_cta[2], &ctx->d_list_cta[3], &ctx->d_list_none,
                       &ctx->d_list_fill, &ctx->d_bt_topic, &ctx->d_bt_off, &ctx->d_bt_P, &ctx->d_bt_boff,
                       &ctx->d_bt_tile0, &ctx->d_tile_bt, &ctx->d_keyA, &ctx->d_keyB, &ctx->d_payA,
                       &ctx->d_payB, &ctx->d_ghist, &ctx->d_gbase, &ctx->d_sel, &ctx->d_need_tie,
@@ -675,10 +678,12 @@ int lagassign_execute(lagassign_ctx* ctx) {
         launch_warp_topics(b, ctx->d_list_warp.as<int32_t>(), ctx->n_warp, st);
         ++launches;
     }
-    if (ctx->n_cta > 0) {
-        ProfScope ps(ctx, K_CTA);
-        launch_cta_topics(b, ctx->d_list_cta.as<int32_t>(), ctx->n_cta, sms, st);
-        ++launches;
+    for (int c = 0; c < N_CTA_CLASSES; ++c) {
+        if (ctx->n_cta[c] > 0) {
+            ProfScope ps(ctx, K_CTA);
+            launch_cta_topics(b, ctx->d_list_cta[c].as<int32_t>(), ctx->n_cta[c], c, sms, st);
+            ++launches;
+        }
     }
     if (ctx->n_big > 0) {
         BigTopics bt = make_big(ctx);

@@ -96,7 +96,9 @@ cudaError_t configure_cta_kernels();
 cudaError_t configure_big_kernels();
 void launch_unassigned_topics(const DevBatch& b, const int32_t* list, int n, cudaStream_t st);
 void launch_warp_topics(const DevBatch& b, const int32_t* list, int n, cudaStream_t st);
-void launch_cta_topics(const DevBatch& b, const int32_t* list, int n, int sms, cudaStream_t st);
+constexpr int N_CTA_CLASSES = 4;   // topics of 257..512 / ..1024 / ..2048 / ..4096 partitions
+inline int cta_class_of(int64_t P) { return P <= 512 ? 0 : P <= 1024 ? 1 : P <= 2048 ? 2 : 3; }
+void launch_cta_topics(const DevBatch& b, const int32_t* list, int n, int cls, int sms, cudaStream_t st);
 void launch_big_order_check(const BigTopics& bt, const int32_t* part, int sms, cudaStream_t st);
 void launch_big_hist(const BigTopics& bt, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st);
 void launch_big_scan(const BigTopics& bt, int first_pass, cudaStream_t st);
