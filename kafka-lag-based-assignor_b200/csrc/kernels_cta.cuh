@@ -65,6 +65,16 @@ __device__ __forceinline__ bool cta_sort_adaptive(uint64_t (&key)[EPT], uint32_t
     const uint64_t diff = (((uint64_t)(o_hi ^ a_hi)) << 32) | (o_lo ^ a_lo);
     const int s = bits_of(diff);
     const uint64_t common = (((uint64_t)a_hi) << 32) | a_lo;      // bits shared by all live keys (above s)
+    if (s == 0) {
+        // every lag equal (an idle topic, typically all zero): list order is the sorted order
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            const int i = tid * EPT + r;
+            pay[r] = i < P ? (uint32_t)i : PAY_SENTINEL;
+            key[r] = i < P ? common : KEY_SENTINEL;
+        }
+        return true;
+    }
     if (s + B <= 32 || allow_trunc) {
         const int sh = max(0, s + B - 32);
         uint32_t w[1][EPT];

@@ -80,8 +80,18 @@ __device__ __forceinline__ bool warp_sort_adaptive(uint64_t (&key)[EPT], uint32_
     const uint32_t xlo = __reduce_or_sync(0xffffffffu, (uint32_t)x);
     const uint32_t xhi = __reduce_or_sync(0xffffffffu, (uint32_t)(x >> 32));
     const int s = xhi ? 64 - __clz(xhi) : (xlo ? 32 - __clz(xlo) : 0);   // bits in which keys differ
+    if (s == 0) {
+        // every lag equal (an idle topic, typically all zero): list order is the sorted order
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            const int i = (int)lane * EPT + r;
+            pay[r] = i < P ? (uint32_t)i : PAY_SENTINEL;
+            key[r] = i < P ? ref : KEY_SENTINEL;
+        }
+        return true;
+    }
     if (s + B <= 32) {
-        const uint32_t mask = s ? (0xFFFFFFFFu >> (32 - s)) : 0u;   // s <= 27
+        const uint32_t mask = 0xFFFFFFFFu >> (32 - s);   // 1 <= s <= 27
         uint32_t w[1][EPT];
 #pragma unroll
         for (int r = 0; r < EPT; ++r)

@@ -68,65 +68,63 @@ __device__ __forceinline__ void cta_bitonic_sort_regs(uint32_t (&w)[W][EPT], uin
     constexpr int WARP_SPAN = 32 * EPT;
     const unsigned tid = threadIdx.x, lane = tid & 31u;
     int flip = 0;
+    // exchange through shared memory with thread tid ^ tmask; mirror: the partner's slot EPT-1-r
+    auto cross_warp = [&](unsigned tmask, bool mirror, bool keep_max) {
+        uint32_t* buf = xbuf + flip * (W * N);
+        flip ^= 1;
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+#pragma unroll
+            for (int x = 0; x < W; ++x) buf[(x * EPT + r) * NT + tid] = w[x][r];
+        }
+        __syncthreads();
+        const unsigned pt = tid ^ tmask;
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            uint32_t o[W];
+#pragma unroll
+            for (int x = 0; x < W; ++x) o[x] = buf[(x * EPT + (mirror ? EPT - 1 - r : r)) * NT + pt];
+            cx_remote<W, EPT>(w, r, o, keep_max);
+        }
+    };
 #pragma unroll
     for (int k = 2; k <= N; k <<= 1) {
+        // mirror stage of the size-k merge (see sort_warp.cuh): i against i ^ (k-1)
+        if (k <= EPT) {
 #pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            // direction of the size-k block holding this thread's elements (k > j)
-            bool asc_hi;   // valid when k >= EPT
-            if (k == N) asc_hi = true;
-            else asc_hi = ((tid & (unsigned)(k / EPT)) == 0);
+            for (int r = 0; r < EPT; ++r)
+                if (r < (r ^ (k - 1))) cx_local<W, EPT>(w, r, r ^ (k - 1));
+        } else if (k <= WARP_SPAN) {
+            const unsigned lm = (unsigned)(k / EPT - 1);
+            const bool keep_max = (lane & (unsigned)(k / EPT / 2)) != 0;
+            uint32_t o[EPT][W];
+#pragma unroll
+            for (int r = 0; r < EPT; ++r)
+#pragma unroll
+                for (int x = 0; x < W; ++x) o[r][x] = __shfl_xor_sync(0xffffffffu, w[x][EPT - 1 - r], lm);
+#pragma unroll
+            for (int r = 0; r < EPT; ++r) cx_remote<W, EPT>(w, r, o[r], keep_max);
+        } else {
+            cross_warp((unsigned)(k / EPT - 1), true, (tid & (unsigned)(k / EPT / 2)) != 0);
+        }
+#pragma unroll
+        for (int j = k >> 2; j > 0; j >>= 1) {
             if (j >= WARP_SPAN) {
-                // partner element lives in another warp: same lane, same slot
-                const unsigned tj = (unsigned)(j / EPT);
-                uint32_t* buf = xbuf + flip * (W * N);
-                flip ^= 1;
-#pragma unroll
-                for (int r = 0; r < EPT; ++r) {
-#pragma unroll
-                    for (int x = 0; x < W; ++x) buf[(x * EPT + r) * NT + tid] = w[x][r];
-                }
-                __syncthreads();
-                const bool keep_max = (((tid & tj) == 0) != asc_hi);
-                const unsigned pt = tid ^ tj;
-#pragma unroll
-                for (int r = 0; r < EPT; ++r) {
-                    uint32_t o[W], m[W];
-#pragma unroll
-                    for (int x = 0; x < W; ++x) { o[x] = buf[(x * EPT + r) * NT + pt]; m[x] = w[x][r]; }
-                    const bool take = (words_less<W>(o, m) != keep_max);
-#pragma unroll
-                    for (int x = 0; x < W; ++x) w[x][r] = take ? o[x] : m[x];
-                }
+                cross_warp((unsigned)(j / EPT), false, (tid & (unsigned)(j / EPT)) != 0);
             } else if (j >= EPT) {
                 const unsigned lj = (unsigned)(j / EPT);
-                const bool keep_max = (((lane & lj) == 0) != asc_hi);
+                const bool keep_max = (lane & lj) != 0;
 #pragma unroll
                 for (int r = 0; r < EPT; ++r) {
-                    uint32_t o[W], m[W];
+                    uint32_t o[W];
 #pragma unroll
-                    for (int x = 0; x < W; ++x) { o[x] = __shfl_xor_sync(0xffffffffu, w[x][r], lj); m[x] = w[x][r]; }
-                    const bool take = (words_less<W>(o, m) != keep_max);
-#pragma unroll
-                    for (int x = 0; x < W; ++x) w[x][r] = take ? o[x] : m[x];
+                    for (int x = 0; x < W; ++x) o[x] = __shfl_xor_sync(0xffffffffu, w[x][r], lj);
+                    cx_remote<W, EPT>(w, r, o, keep_max);
                 }
             } else {
 #pragma unroll
-                for (int r = 0; r < EPT; ++r) {
-                    if ((r & j) == 0) {
-                        const bool asc = (k < EPT) ? ((r & k) == 0) : asc_hi;
-                        const int q = r | j;
-                        uint32_t a[W], b[W];
-#pragma unroll
-                        for (int x = 0; x < W; ++x) { a[x] = w[x][r]; b[x] = w[x][q]; }
-                        const bool swap = (words_less<W>(b, a) == asc);
-#pragma unroll
-                        for (int x = 0; x < W; ++x) {
-                            w[x][r] = swap ? b[x] : a[x];
-                            w[x][q] = swap ? a[x] : b[x];
-                        }
-                    }
-                }
+                for (int r = 0; r < EPT; ++r)
+                    if ((r & j) == 0) cx_local<W, EPT>(w, r, r | j);
             }
         }
     }

@@ -34,63 +34,85 @@ __device__ __forceinline__ bool lt2(uint32_t a1, uint32_t a0, uint32_t b1, uint3
     return (((uint64_t)a1 << 32) | a0) < (((uint64_t)b1 << 32) | b0);
 }
 
+// Compare-exchange building blocks shared with the CTA-wide sort (sort_cta.cuh).
+// Local pair, ascending: w[.][r] <- smaller, w[.][q] <- larger.
+template <int W, int EPT>
+__device__ __forceinline__ void cx_local(uint32_t (&w)[W][EPT], int r, int q) {
+    if (W == 1) {
+        const uint32_t lo = min(w[0][r], w[0][q]), hi = max(w[0][r], w[0][q]);
+        w[0][r] = lo;
+        w[0][q] = hi;
+    } else {
+        bool swap;   // w[q] < w[r]
+        if (W == 2) swap = lt2(w[1][q], w[0][q], w[1][r], w[0][r]);
+        else swap = lt3(w[W - 1][q], w[W - 2][q], w[0][q], w[W - 1][r], w[W - 2][r], w[0][r]);
+#pragma unroll
+        for (int x = 0; x < W; ++x) {
+            const uint32_t a = w[x][r], b = w[x][q];
+            w[x][r] = swap ? b : a;
+            w[x][q] = swap ? a : b;
+        }
+    }
+}
+// Remote partner element o[]: keep the larger of (mine, other) if keep_max else the smaller.
+template <int W, int EPT>
+__device__ __forceinline__ void cx_remote(uint32_t (&w)[W][EPT], int r, const uint32_t (&o)[W], bool keep_max) {
+    if (W == 1) {
+        const uint32_t lo = min(w[0][r], o[0]), hi = max(w[0][r], o[0]);
+        w[0][r] = keep_max ? hi : lo;       // SASS: VIMNMX + predicated VIMNMX
+    } else {
+        bool lt;   // other < mine
+        if (W == 2) lt = lt2(o[1], o[0], w[1][r], w[0][r]);
+        else lt = lt3(o[W - 1], o[W - 2], o[0], w[W - 1][r], w[W - 2][r], w[0][r]);
+        const bool take = (lt != keep_max);   // equal elements are identical: either choice is the same
+#pragma unroll
+        for (int x = 0; x < W; ++x) w[x][r] = take ? o[x] : w[x][r];
+    }
+}
+
+// The network is the direction-free form of the bitonic sorter: the merge of two ascending
+// runs of k/2 starts with the MIRROR stage (i against i ^ (k-1)) and continues with the
+// half-cleaners i against i ^ j, j = k/4 .. 1; every compare-exchange puts the smaller element
+// at the smaller index. With no per-block direction a local pair costs two min/max (one word)
+// and no select, and the per-lane predicates are plain lane bits.
 template <int W, int EPT>
 __device__ __forceinline__ void warp_bitonic_sort_words(uint32_t (&w)[W][EPT]) {
     constexpr int N = 32 * EPT;
     const unsigned lane = lane_id();
 #pragma unroll
     for (int k = 2; k <= N; k <<= 1) {
+        if (k <= EPT) {
 #pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int r = 0; r < EPT; ++r)
+                if (r < (r ^ (k - 1))) cx_local<W, EPT>(w, r, r ^ (k - 1));
+        } else {
+            // mirror across lanes: partner lane ^ (k/EPT - 1), register slot EPT-1-r
+            const unsigned lm = (unsigned)(k / EPT - 1);
+            const bool keep_max = (lane & (unsigned)(k / EPT / 2)) != 0;
+            uint32_t o[EPT][W];
+#pragma unroll
+            for (int r = 0; r < EPT; ++r)
+#pragma unroll
+                for (int x = 0; x < W; ++x) o[r][x] = __shfl_xor_sync(0xffffffffu, w[x][EPT - 1 - r], lm);
+#pragma unroll
+            for (int r = 0; r < EPT; ++r) cx_remote<W, EPT>(w, r, o[r], keep_max);
+        }
+#pragma unroll
+        for (int j = k >> 2; j > 0; j >>= 1) {
             if (j >= EPT) {
-                // partner lives in another lane, same register slot
                 const unsigned lj = (unsigned)(j / EPT);
-                const bool asc = (k == N) ? true : ((lane & (unsigned)(k / EPT)) == 0);
-                const bool keep_max = (((lane & lj) == 0) != asc);
+                const bool keep_max = (lane & lj) != 0;
 #pragma unroll
                 for (int r = 0; r < EPT; ++r) {
                     uint32_t o[W];
 #pragma unroll
                     for (int x = 0; x < W; ++x) o[x] = __shfl_xor_sync(0xffffffffu, w[x][r], lj);
-                    if (W == 1) {
-                        const uint32_t lo = min(w[0][r], o[0]), hi = max(w[0][r], o[0]);
-                        w[0][r] = keep_max ? hi : lo;
-                    } else {
-                        bool lt;   // other < mine
-                        if (W == 2) lt = lt2(o[1], o[0], w[1][r], w[0][r]);
-                        else lt = lt3(o[W - 1], o[W - 2], o[0], w[W - 1][r], w[W - 2][r], w[0][r]);
-                        const bool take = (lt != keep_max);   // equal elements are identical: either choice is the same
-#pragma unroll
-                        for (int x = 0; x < W; ++x) w[x][r] = take ? o[x] : w[x][r];
-                    }
+                    cx_remote<W, EPT>(w, r, o, keep_max);
                 }
             } else {
 #pragma unroll
-                for (int r = 0; r < EPT; ++r) {
-                    if ((r & j) == 0) {
-                        bool asc;
-                        if (k == N) asc = true;
-                        else if (k < EPT) asc = ((r & k) == 0);
-                        else asc = ((lane & (unsigned)(k / EPT)) == 0);
-                        const int q = r | j;
-                        if (W == 1) {
-                            const uint32_t lo = min(w[0][r], w[0][q]), hi = max(w[0][r], w[0][q]);
-                            w[0][r] = asc ? lo : hi;
-                            w[0][q] = asc ? hi : lo;
-                        } else {
-                            bool lt;   // w[q] < w[r]
-                            if (W == 2) lt = lt2(w[1][q], w[0][q], w[1][r], w[0][r]);
-                            else lt = lt3(w[W - 1][q], w[W - 2][q], w[0][q], w[W - 1][r], w[W - 2][r], w[0][r]);
-                            const bool swap = (lt == asc);
-#pragma unroll
-                            for (int x = 0; x < W; ++x) {
-                                const uint32_t a = w[x][r], b = w[x][q];
-                                w[x][r] = swap ? b : a;
-                                w[x][q] = swap ? a : b;
-                            }
-                        }
-                    }
-                }
+                for (int r = 0; r < EPT; ++r)
+                    if ((r & j) == 0) cx_local<W, EPT>(w, r, r | j);
             }
         }
     }
