@@ -54,39 +54,47 @@ template <> struct Log2Slots<2> { static constexpr int value = 6; };
 template <> struct Log2Slots<4> { static constexpr int value = 7; };
 template <> struct Log2Slots<8> { static constexpr int value = 8; };
 
-// Sort (key, pay) ascending, pay < 32*EPT distinct for live elements, padding =
-// (KEY_SENTINEL, PAY_SENTINEL). Keys of one topic usually share most of their
-// high bits (real lags are small numbers), so the sort runs on the narrowest
-// element that still orders them: the s significant key bits above the B payload
-// bits, in one 32-bit word (s + B <= 32), one 64-bit word (s + B <= 64) or the
-// general three words. The choice is uniform across the warp.
+// Sort (key, pay) ascending, pay < 32*EPT distinct for live elements. Padding elements
+// carry pay = PAY_SENTINEL and key = ref, the key of some live element (so they are neutral
+// in the width analysis below; pay all-ones makes every packed form of a padding element
+// all-ones without a select). Keys of one topic usually share most of their high bits (real
+// lags are small numbers), so the sort runs on the narrowest element that still orders them:
+// the s significant key bits above the B payload bits, in one 32-bit word (s + B <= 32), one
+// 64-bit word (s + B <= 64) or the general three words. The choice is uniform across the warp.
 // The general three-word sort and the multi-round fill are kept out of line so
 // that their register needs do not set the occupancy of the common path.
 template <int EPT>
-__device__ __noinline__ void warp_sort_general(uint64_t (&key)[EPT], uint32_t (&pay)[EPT]) {
+static __device__ __noinline__ void warp_sort_general(uint64_t (&key)[EPT], uint32_t (&pay)[EPT]) {
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) key[r] = (pay[r] != PAY_SENTINEL) ? key[r] : KEY_SENTINEL;
     warp_bitonic_sort<EPT>(key, pay);
 }
 
 // Returns true when key[] holds the sorted keys on return; false when only pay[] (the
-// sorted positions) is valid, which happens on the truncated path below.
+// sorted positions) is valid, which happens on the truncated path below. On return slot r of
+// lane l is sorted position l*EPT + r; slots at positions >= P hold padding (pay then is NOT
+// the sentinel any more: test the position, not pay).
 template <int EPT>
-__device__ __forceinline__ bool warp_sort_adaptive(uint64_t (&key)[EPT], uint32_t (&pay)[EPT], int P, bool allow_trunc) {
+__device__ __forceinline__ bool warp_sort_adaptive(uint64_t (&key)[EPT], uint32_t (&pay)[EPT], uint64_t ref, int P,
+                                                   bool allow_trunc) {
     constexpr int B = Log2Slots<EPT>::value;
+    constexpr uint32_t PAYMASK = (1u << B) - 1u;
     const unsigned lane = lane_id();
-    const uint64_t ref = __shfl_sync(0xffffffffu, key[0], 0);   // element 0 is live (P >= 1)
-    uint64_t x = 0;
+    uint32_t x_lo = 0, x_hi = 0;
 #pragma unroll
-    for (int r = 0; r < EPT; ++r) x |= (pay[r] != PAY_SENTINEL) ? (key[r] ^ ref) : 0ull;
-    const uint32_t xlo = __reduce_or_sync(0xffffffffu, (uint32_t)x);
-    const uint32_t xhi = __reduce_or_sync(0xffffffffu, (uint32_t)(x >> 32));
+    for (int r = 0; r < EPT; ++r) {
+        x_lo |= (uint32_t)key[r] ^ (uint32_t)ref;
+        x_hi |= (uint32_t)(key[r] >> 32) ^ (uint32_t)(ref >> 32);
+    }
+    const uint32_t xlo = __reduce_or_sync(0xffffffffu, x_lo);
+    const uint32_t xhi = __reduce_or_sync(0xffffffffu, x_hi);
     const int s = xhi ? 64 - __clz(xhi) : (xlo ? 32 - __clz(xlo) : 0);   // bits in which keys differ
     if (s == 0) {
         // every lag equal (an idle topic, typically all zero): list order is the sorted order
 #pragma unroll
         for (int r = 0; r < EPT; ++r) {
-            const int i = (int)lane * EPT + r;
-            pay[r] = i < P ? (uint32_t)i : PAY_SENTINEL;
-            key[r] = i < P ? ref : KEY_SENTINEL;
+            pay[r] = (uint32_t)((int)lane * EPT + r);
+            key[r] = ref;
         }
         return true;
     }
@@ -94,13 +102,12 @@ __device__ __forceinline__ bool warp_sort_adaptive(uint64_t (&key)[EPT], uint32_
         const uint32_t mask = 0xFFFFFFFFu >> (32 - s);   // 1 <= s <= 27
         uint32_t w[1][EPT];
 #pragma unroll
-        for (int r = 0; r < EPT; ++r)
-            w[0][r] = (pay[r] != PAY_SENTINEL) ? ((((uint32_t)key[r] & mask) << B) | pay[r]) : 0xFFFFFFFFu;
+        for (int r = 0; r < EPT; ++r) w[0][r] = (((uint32_t)key[r] & mask) << B) | pay[r];   // padding: all ones
         warp_bitonic_sort_words<1, EPT>(w);
         const uint64_t hi = ref & ~(uint64_t)mask;
 #pragma unroll
         for (int r = 0; r < EPT; ++r) {
-            pay[r] = w[0][r] & ((1u << B) - 1u);
+            pay[r] = w[0][r] & PAYMASK;
             key[r] = hi | (uint64_t)(w[0][r] >> B);
         }
         return true;
@@ -111,25 +118,22 @@ __device__ __forceinline__ bool warp_sort_adaptive(uint64_t (&key)[EPT], uint32_
         // (key, position) order: for high-entropy lags (random 40-bit values, 256 per topic)
         // that is ~99.8 % of topics, at a third of the instructions of the 64-bit sort.
         // Otherwise fall through to the exact sort; key[] / pay[] are still untouched.
-        constexpr int KB = 32 - B;
-        const int sh = s - KB;                       // s > KB here
+        const int sh = s - (32 - B);                 // s > 32 - B here
         uint32_t w[1][EPT];
 #pragma unroll
-        for (int r = 0; r < EPT; ++r)
-            w[0][r] = (pay[r] != PAY_SENTINEL)
-                          ? ((((uint32_t)(key[r] >> sh) & ((1u << KB) - 1u)) << B) | pay[r]) : 0xFFFFFFFFu;
+        for (int r = 0; r < EPT; ++r) w[0][r] = (((uint32_t)(key[r] >> sh)) << B) | pay[r];   // bits >= s drop out
         warp_bitonic_sort_words<1, EPT>(w);
         bool dup = false;
 #pragma unroll
         for (int r = 0; r + 1 < EPT; ++r) {
             const int i = (int)lane * EPT + r;
-            dup |= (i + 1 < P) && ((w[0][r] >> B) == (w[0][r + 1] >> B));
+            dup |= (i + 1 < P) && ((w[0][r] ^ w[0][r + 1]) <= PAYMASK);
         }
         const uint32_t nxt = __shfl_down_sync(0xffffffffu, w[0][0], 1);
-        dup |= (lane < 31) && ((int)lane * EPT + EPT < P) && ((w[0][EPT - 1] >> B) == (nxt >> B));
+        dup |= (lane < 31) && ((int)lane * EPT + EPT < P) && ((w[0][EPT - 1] ^ nxt) <= PAYMASK);
         if (!__any_sync(0xffffffffu, dup)) {
 #pragma unroll
-            for (int r = 0; r < EPT; ++r) pay[r] = w[0][r] & ((1u << B) - 1u);
+            for (int r = 0; r < EPT; ++r) pay[r] = w[0][r] & PAYMASK;
             return false;
         }
     }
@@ -138,7 +142,7 @@ __device__ __forceinline__ bool warp_sort_adaptive(uint64_t (&key)[EPT], uint32_
         uint32_t w[2][EPT];
 #pragma unroll
         for (int r = 0; r < EPT; ++r) {
-            const uint64_t v = (pay[r] != PAY_SENTINEL) ? (((key[r] & mask) << B) | pay[r]) : ~0ull;
+            const uint64_t v = ((key[r] & mask) << B) | (uint64_t)(int64_t)(int32_t)pay[r];   // padding: all ones
             w[0][r] = (uint32_t)v;
             w[1][r] = (uint32_t)(v >> 32);
         }
@@ -147,7 +151,7 @@ __device__ __forceinline__ bool warp_sort_adaptive(uint64_t (&key)[EPT], uint32_
 #pragma unroll
         for (int r = 0; r < EPT; ++r) {
             const uint64_t v = ((uint64_t)w[1][r] << 32) | w[0][r];
-            pay[r] = (uint32_t)v & ((1u << B) - 1u);
+            pay[r] = (uint32_t)v & PAYMASK;
             key[r] = hi | (v >> B);
         }
     } else {
@@ -156,10 +160,14 @@ __device__ __forceinline__ bool warp_sort_adaptive(uint64_t (&key)[EPT], uint32_
     return true;
 }
 
-__device__ __noinline__ void warp_rounds_path(int P, int C, const int32_t* __restrict__ cset, WarpScratch& ws,
-                                              int64_t* tot, int32_t* cnt);
+static __device__ __noinline__ void warp_rounds_path(int P, int C, const int32_t* __restrict__ cset, WarpScratch& ws,
+                                                     int64_t* tot, int32_t* cnt);
 
-template <int EPT>
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// PLAIN: the batch has no explicit partition ids and no totals/counts outputs (the common
+// call); the paths for those are compiled out.
+template <int EPT, bool PLAIN>
 __device__ __forceinline__ void warp_topic(const DevBatch& b, int t, WarpScratch& ws) {
     const unsigned lane = lane_id();
     const int64_t off = b.topic_off[t];
@@ -168,122 +176,178 @@ __device__ __forceinline__ void warp_topic(const DevBatch& b, int t, WarpScratch
     const int64_t coff = b.cset_off[s];
     const int64_t C64 = b.cset_off[s + 1] - coff;
     const int32_t* __restrict__ cset = b.cset_rank + coff;
+    const int64_t* __restrict__ lagp = b.lag + off;
 
     uint64_t key[EPT];
     uint32_t pay[EPT];
     // Coalesced load; which register slot an element lands in does not matter,
     // the payload carries its list position (Main:228 sorts the whole list).
+    const uint64_t ref = (uint64_t)__ldg(lagp) ^ LAG_KEY_MASK;   // element 0 is live (P >= 1)
 #pragma unroll
     for (int r = 0; r < EPT; ++r) {
-        int m = r * 32 + (int)lane;
-        bool live = m < P;
-        key[r] = live ? ((uint64_t)ld_stream(b.lag + off + m) ^ LAG_KEY_MASK) : KEY_SENTINEL;
+        const int m = r * 32 + (int)lane;
+        const bool live = m < P;
+        key[r] = live ? ((uint64_t)ld_stream(lagp + m) ^ LAG_KEY_MASK) : ref;
         pay[r] = live ? (uint32_t)m : PAY_SENTINEL;
     }
 
     bool use_tab = false;
-    if (b.part != nullptr) {
-        // Ties on lag break on partition id ascending (Main:230-231). A list that
-        // is already ascending in partition id lets the position stand in for it;
-        // otherwise order it by partition id first (stable by position).
-        bool bad = false;
-#pragma unroll
-        for (int r = 0; r < EPT; ++r) {
-            int m = r * 32 + (int)lane;
-            if (m + 1 < P) bad |= b.part[off + m] > b.part[off + m + 1];
-        }
-        if (__any_sync(0xffffffffu, bad)) {
-            uint64_t k2[EPT];
-            uint32_t p2[EPT];
+    if constexpr (!PLAIN) {
+        if (b.part != nullptr) {
+            // Ties on lag break on partition id ascending (Main:230-231). A list that
+            // is already ascending in partition id lets the position stand in for it;
+            // otherwise order it by partition id first (stable by position).
+            const int32_t* __restrict__ partp = b.part + off;
+            bool bad = false;
 #pragma unroll
             for (int r = 0; r < EPT; ++r) {
-                int m = r * 32 + (int)lane;
-                bool live = m < P;
-                k2[r] = live ? (uint64_t)((uint32_t)b.part[off + m] ^ 0x80000000u) : KEY_SENTINEL;
-                p2[r] = live ? (uint32_t)m : PAY_SENTINEL;
+                const int m = r * 32 + (int)lane;
+                if (m + 1 < P) bad |= partp[m] > partp[m + 1];
             }
-            warp_sort_adaptive<EPT>(k2, p2, P, /*allow_trunc=*/false);
+            if (__any_sync(0xffffffffu, bad)) {
+                uint64_t k2[EPT];
+                uint32_t p2[EPT];
+                const uint64_t ref2 = (uint64_t)((uint32_t)partp[0] ^ 0x80000000u);
 #pragma unroll
-            for (int r = 0; r < EPT; ++r) {
-                int i = (int)lane * EPT + r;
-                bool live = i < P;
-                if (live) ws.part_tab[i] = (uint32_t)k2[r] ^ 0x80000000u;
-                key[r] = live ? ((uint64_t)b.lag[off + p2[r]] ^ LAG_KEY_MASK) : KEY_SENTINEL;
-                pay[r] = live ? (uint32_t)i : PAY_SENTINEL;
+                for (int r = 0; r < EPT; ++r) {
+                    const int m = r * 32 + (int)lane;
+                    const bool live = m < P;
+                    k2[r] = live ? (uint64_t)((uint32_t)partp[m] ^ 0x80000000u) : ref2;
+                    p2[r] = live ? (uint32_t)m : PAY_SENTINEL;
+                }
+                warp_sort_adaptive<EPT>(k2, p2, ref2, P, /*allow_trunc=*/false);
+#pragma unroll
+                for (int r = 0; r < EPT; ++r) {
+                    const int i = (int)lane * EPT + r;
+                    const bool live = i < P;
+                    if (live) ws.part_tab[i] = (uint32_t)k2[r] ^ 0x80000000u;
+                    key[r] = live ? ((uint64_t)lagp[p2[r]] ^ LAG_KEY_MASK) : ref;
+                    pay[r] = live ? (uint32_t)i : PAY_SENTINEL;
+                }
+                use_tab = true;
+                __syncwarp();
             }
-            use_tab = true;
-            __syncwarp();
         }
     }
 
     // Main:228-235 (pay is the list position here unless the ids had to be ordered first)
-    const bool keys_exact = warp_sort_adaptive<EPT>(key, pay, P, /*allow_trunc=*/!use_tab);
+    const bool keys_exact = warp_sort_adaptive<EPT>(key, pay, ref, P, /*allow_trunc=*/!use_tab);
 
-    // out_partition, staged through shared memory so the global store is coalesced
-    {
-        uint32_t v[EPT];
+    // out_partition: lane l now holds sorted positions l*EPT .. l*EPT+EPT-1
+    uint32_t v[EPT];
 #pragma unroll
-        for (int r = 0; r < EPT; ++r) {
-            int i = (int)lane * EPT + r;
-            v[r] = 0;
-            if (i < P) {
-                if (b.part == nullptr) v[r] = pay[r];
-                else if (use_tab) v[r] = ws.part_tab[pay[r]];
-                else v[r] = (uint32_t)b.part[off + pay[r]];
+    for (int r = 0; r < EPT; ++r) {
+        v[r] = pay[r];
+        if constexpr (!PLAIN) {
+            if (b.part != nullptr) {
+                const int i = (int)lane * EPT + r;
+                v[r] = 0;
+                if (i < P) v[r] = use_tab ? ws.part_tab[pay[r]] : (uint32_t)b.part[off + pay[r]];
             }
         }
-        stage_store<EPT>(ws.out_a, lane, v);
     }
     const bool rounds = (int64_t)P > C64;
-    const bool need_keys = rounds || b.out_total != nullptr;
+    const bool need_keys = rounds || (!PLAIN && b.out_total != nullptr);
     if (need_keys) {
 #pragma unroll
         for (int r = 0; r < EPT; ++r) {
-            int i = (int)lane * EPT + r;
-            if (i < P) ws.lag_key[i] = keys_exact ? key[r] : ((uint64_t)b.lag[off + pay[r]] ^ LAG_KEY_MASK);
+            const int i = (int)lane * EPT + r;
+            if (i < P) ws.lag_key[i] = keys_exact ? key[r] : ((uint64_t)lagp[pay[r]] ^ LAG_KEY_MASK);
         }
     }
-    __syncwarp();
+    int32_t* __restrict__ outp = b.out_part + off;
+    int32_t* __restrict__ outc = b.out_cons + off;
+    // 16-byte stores straight from the registers when the topic's slices are aligned (always,
+    // when partition counts are multiples of 4); otherwise staged through shared memory so
+    // that the 4-byte stores are coalesced.
+    const bool vec = EPT >= 4 && aligned16(outp) && aligned16(outc) && aligned16(cset);
+    if (EPT == 1) {
+        if ((int)lane < P) __stcs(outp + lane, (int32_t)v[0]);
+    } else if (vec) {
 #pragma unroll
-    for (int r = 0; r < EPT; ++r) {
-        int m = r * 32 + (int)lane;
-        if (m < P) __stcs(b.out_part + off + m, (int32_t)ws.out_a[stage_addr<EPT>(m)]);
+        for (int c = 0; c < EPT / 4; ++c) {
+            const int i = (int)lane * EPT + c * 4;
+            if (i + 4 <= P) {
+                __stcs(reinterpret_cast<int4*>(outp + i), make_int4((int)v[c * 4], (int)v[c * 4 + 1], (int)v[c * 4 + 2], (int)v[c * 4 + 3]));
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (i + e < P) __stcs(outp + i + e, (int32_t)v[c * 4 + e]);
+            }
+        }
+    } else {
+        stage_store<EPT>(ws.out_a, lane, v);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            const int m = r * 32 + (int)lane;
+            if (m < P) __stcs(outp + m, (int32_t)ws.out_a[stage_addr<EPT>(m)]);
+        }
     }
 
-    int64_t* tot = b.out_total ? b.out_total + b.tc_off[t] : nullptr;
-    int32_t* cnt = b.out_count ? b.out_count + b.tc_off[t] : nullptr;
+    int64_t* tot = nullptr;
+    int32_t* cnt = nullptr;
+    if constexpr (!PLAIN) {
+        if (b.out_total != nullptr) {
+            tot = b.out_total + b.tc_off[t];
+            cnt = b.out_count + b.tc_off[t];
+        }
+    }
     if (!rounds) {
         // P <= C: one partial round on all-zero totals, so the k-th partition in
         // sorted order goes to the k-th member in id order.
+        if (vec) {
 #pragma unroll
-        for (int r = 0; r < EPT; ++r) {
-            int m = r * 32 + (int)lane;
-            if (m < P) {
-                __stcs(b.out_cons + off + m, cset[m]);
-                if (tot) { tot[m] = (int64_t)(ws.lag_key[m] ^ LAG_KEY_MASK); cnt[m] = 1; }
+            for (int c = 0; c < EPT / 4; ++c) {
+                const int i = (int)lane * EPT + c * 4;
+                if (i + 4 <= P) {
+                    __stcs(reinterpret_cast<int4*>(outc + i), __ldg(reinterpret_cast<const int4*>(cset + i)));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (i + e < P) __stcs(outc + i + e, cset[i + e]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < EPT; ++r) {
+                const int m = r * 32 + (int)lane;
+                if (m < P) __stcs(outc + m, cset[m]);
+            }
+        }
+        if constexpr (!PLAIN) {
+            if (tot != nullptr) {
+                __syncwarp();      // lag_key[] written above in sort order
+#pragma unroll
+                for (int r = 0; r < EPT; ++r) {
+                    const int m = r * 32 + (int)lane;
+                    if (m < P) { tot[m] = (int64_t)(ws.lag_key[m] ^ LAG_KEY_MASK); cnt[m] = 1; }
+                }
             }
         }
         // members beyond P keep total 0 / count 0 (buffers are zero-filled)
     } else {
+        __syncwarp();
         warp_rounds_path(P, (int)C64, cset, ws, tot, cnt);
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < EPT; ++r) {
-            int m = r * 32 + (int)lane;
-            if (m < P) __stcs(b.out_cons + off + m, (int32_t)ws.out_b[m]);
+            const int m = r * 32 + (int)lane;
+            if (m < P) __stcs(outc + m, (int32_t)ws.out_b[m]);
         }
     }
     __syncwarp();
 }
 
-__device__ __noinline__ void warp_rounds_path(int P, int C, const int32_t* __restrict__ cset, WarpScratch& ws,
-                                              int64_t* tot, int32_t* cnt) {
+static __device__ __noinline__ void warp_rounds_path(int P, int C, const int32_t* __restrict__ cset, WarpScratch& ws,
+                                                     int64_t* tot, int32_t* cnt) {
     auto lag_at = [&](int64_t k) { return (int64_t)(ws.lag_key[k] ^ LAG_KEY_MASK); };
     auto put = [&](int64_t k, int32_t rank) { ws.out_b[k] = (uint32_t)rank; };
     warp_round_fill_dispatch(P, C, cset, lag_at, put, tot, cnt);
 }
 
 // One warp per topic of `list` (topics with 1 <= P <= 256 and a non-empty consumer set).
+template <bool PLAIN>
 __global__ void __launch_bounds__(SMALL_WARPS * 32, LAGASSIGN_WARP_MINBLOCKS)
 k_warp_topics(DevBatch b, const int32_t* __restrict__ list, int n_list) {
     __shared__ WarpScratch scratch[SMALL_WARPS];
@@ -293,10 +357,10 @@ k_warp_topics(DevBatch b, const int32_t* __restrict__ list, int n_list) {
     const int t = list[idx];
     const int P = (int)(b.topic_off[t + 1] - b.topic_off[t]);
     WarpScratch& ws = scratch[warp];
-    if (P <= 32) warp_topic<1>(b, t, ws);
-    else if (P <= 64) warp_topic<2>(b, t, ws);
-    else if (P <= 128) warp_topic<4>(b, t, ws);
-    else warp_topic<8>(b, t, ws);
+    if (P <= 32) warp_topic<1, PLAIN>(b, t, ws);
+    else if (P <= 64) warp_topic<2, PLAIN>(b, t, ws);
+    else if (P <= 128) warp_topic<4, PLAIN>(b, t, ws);
+    else warp_topic<8, PLAIN>(b, t, ws);
 }
 
 }  // namespace lagassign

@@ -5,7 +5,8 @@ namespace lagassign {
 
 void launch_warp_topics(const DevBatch& b, const int32_t* list, int n, cudaStream_t st) {
     const int grid = (n + SMALL_WARPS - 1) / SMALL_WARPS;
-    k_warp_topics<<<grid, SMALL_WARPS * 32, 0, st>>>(b, list, n);
+    if (b.part == nullptr && b.out_total == nullptr) k_warp_topics<true><<<grid, SMALL_WARPS * 32, 0, st>>>(b, list, n);
+    else k_warp_topics<false><<<grid, SMALL_WARPS * 32, 0, st>>>(b, list, n);
 }
 
 }  // namespace lagassign
