@@ -28,6 +28,8 @@ ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_OOM", -4: "ERR_STA
 OPT_TOTALS = 1
 OPT_PROFILE = 2
 OPT_GROUP = 3
+OPT_PIPE_CHUNK = 4
+OPT_PLAN_CACHE = 5
 
 
 class LagAssignError(RuntimeError):

@@ -6,8 +6,10 @@
 #include "../../include/lagassign.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -105,6 +107,21 @@ struct lagassign_ctx {
     std::vector<int32_t> h_list_warp, h_list_cta[N_CTA_CLASSES], h_list_none;
     cudaStream_t stream_in = nullptr, stream_out = nullptr;
     std::vector<cudaEvent_t> pipe_events;
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};   // execute(): size bins on concurrent streams
+    int64_t pipe_chunk_elems = 0;   // 0 = default (LAGASSIGN_OPT_PIPE_CHUNK)
+    // Plan cache: a consumer group is rebalanced again and again over the same topics and
+    // subscriptions with fresh lags, so the batch SHAPE (everything but lag / partition ids /
+    // offsets) usually repeats. When it does, the plan and the metadata already on the device
+    // are reused and only the per-partition data is uploaded.
+    bool plan_cache = true;         // LAGASSIGN_OPT_PLAN_CACHE
+    struct PlanKey {
+        bool valid = false;
+        bool has_part = false, has_offsets = false, want_totals = false, want_group = false, sort_only = false;
+        std::vector<int64_t> topic_off, cset_off;
+        std::vector<int32_t> topic_cset, cset_rank;
+        lagassign_stats stats{};
+    } plan_key;
+    bool trace = false;             // LAGASSIGN_TRACE=1: host-side phase times of assign_batch on stderr
 
     // grouping of the result by member (LAGASSIGN_OPT_GROUP): an internal child context runs the
     // radix sort of the flat result by member rank (sort_only = the child's mode)
@@ -310,6 +327,23 @@ BigTopics make_big(lagassign_ctx* ctx) {
     return bt;
 }
 
+// Same shape as the batch the current plan was made for (see lagassign_ctx::PlanKey)?
+bool plan_matches(const lagassign_ctx* ctx, const lagassign_batch* in, bool has_offsets) {
+    const auto& k = ctx->plan_key;
+    if (!ctx->plan_cache || !k.valid || !in || !in->topic_off || !in->cset_off) return false;
+    if (k.has_part != (in->partition != nullptr) || k.has_offsets != has_offsets || k.want_totals != ctx->want_totals ||
+        k.want_group != ctx->want_group || k.sort_only != ctx->sort_only)
+        return false;
+    if (in->n_topics < 0 || (size_t)in->n_topics + 1 != k.topic_off.size()) return false;
+    if (in->n_csets < 0 || (size_t)in->n_csets + 1 != k.cset_off.size()) return false;
+    if (!k.topic_cset.empty() && !in->topic_cset) return false;
+    if (!k.cset_rank.empty() && !in->cset_rank) return false;
+    if (memcmp(in->cset_off, k.cset_off.data(), k.cset_off.size() * sizeof(int64_t)) != 0) return false;   // R follows
+    return memcmp(in->topic_off, k.topic_off.data(), k.topic_off.size() * sizeof(int64_t)) == 0 &&
+           (k.topic_cset.empty() || memcmp(in->topic_cset, k.topic_cset.data(), k.topic_cset.size() * sizeof(int32_t)) == 0) &&
+           (k.cset_rank.empty() || memcmp(in->cset_rank, k.cset_rank.data(), k.cset_rank.size() * sizeof(int32_t)) == 0);
+}
+
 int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_offsets* offs, bool defer_data = false) {
     if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
     ctx->uploaded = ctx->executed = false;
@@ -328,6 +362,27 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
         tmp.lag = &dummy;   // not dereferenced by the planner
         in = &tmp;
     }
+    if (plan_matches(ctx, in, offs != nullptr)) {
+        const size_t N = (size_t)ctx->N;
+        if (N > 0 && !in->lag) return fail(ctx, LAGASSIGN_ERR_ARG, "lag is NULL");
+        ctx->stats = ctx->plan_key.stats;
+        ctx->stats.h2d_bytes = 0;        // only what this call copies
+        if (offs) {
+            ctx->reset_latest = offs->reset_latest ? 1 : 0;
+            TRY(upload_vec(ctx, ctx->d_begin, offs->begin_offset, N));
+            TRY(upload_vec(ctx, ctx->d_end, offs->end_offset, N));
+            TRY(upload_vec(ctx, ctx->d_committed, offs->committed, N));
+            TRY(upload_vec(ctx, ctx->d_hascommitted, offs->has_committed, N));
+        } else if (!defer_data) {
+            TRY(upload_vec(ctx, ctx->d_lag, in->lag, N));
+        }
+        if (ctx->has_part && !defer_data) TRY(upload_vec(ctx, ctx->d_part, in->partition, N));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->grp) ctx->grp->uploaded = true;
+        ctx->uploaded = !defer_data;
+        return LAGASSIGN_OK;
+    }
+    ctx->plan_key.valid = false;
     TRY(validate_and_plan(ctx, in, l_warp, l_cta, l_none, bt_topic, bt_off, bt_P, bt_boff, bt_tile0, tile_bt, l_fill, tc_off, bt_seg0, seg_bt, tile_desc));
     const int64_t T = ctx->T, N = ctx->N;
     ctx->has_part = in->partition != nullptr;
@@ -432,6 +487,17 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
     for (int c = 0; c < N_CTA_CLASSES; ++c) ctx->h_list_cta[c].swap(l_cta[c]);
     ctx->h_list_none.swap(l_none);
     ctx->uploaded = !defer_data;
+    {
+        auto& k = ctx->plan_key;
+        k.has_part = ctx->has_part; k.has_offsets = ctx->has_offsets;
+        k.want_totals = ctx->want_totals; k.want_group = ctx->want_group; k.sort_only = ctx->sort_only;
+        k.topic_off.assign(in->topic_off, in->topic_off + T + 1);
+        k.cset_off.assign(in->cset_off, in->cset_off + ctx->S + 1);
+        k.topic_cset.assign(in->topic_cset, in->topic_cset + T);
+        k.cset_rank.assign(in->cset_rank, in->cset_rank + ctx->R);
+        k.stats = ctx->stats;
+        k.valid = true;
+    }
     return LAGASSIGN_OK;
 }
 
@@ -464,11 +530,40 @@ int assign_batch_pipelined(lagassign_ctx* ctx, const lagassign_batch* in, const 
         CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking));
     }
     const int64_t N = ctx->N, T = ctx->T;
-    const int K = (int)std::min<int64_t>(64, std::max<int64_t>(2, (N + PIPE_CHUNK_ELEMS - 1) / PIPE_CHUNK_ELEMS));
+    // Chunk sizes: a short ramp at both ends (chunk/8, /4, /2) so that the first kernels and
+    // the first D2H start early and the last D2H is short; full chunks in between.
+    const int64_t chunk = ctx->pipe_chunk_elems > 0 ? ctx->pipe_chunk_elems : PIPE_CHUNK_ELEMS;
+    std::vector<int64_t> cuts;      // cumulative partition counts at which chunks end (last = N)
+    {
+        const int64_t ramp[3] = {std::max<int64_t>(chunk / 8, 1), std::max<int64_t>(chunk / 4, 1), std::max<int64_t>(chunk / 2, 1)};
+        const int64_t ramp_sum = ramp[0] + ramp[1] + ramp[2];
+        if (N >= 2 * ramp_sum + chunk) {
+            int64_t pos = 0;
+            for (int i = 0; i < 3; ++i) { pos += ramp[i]; cuts.push_back(pos); }
+            const int64_t body = N - 2 * ramp_sum;
+            const int64_t nb = std::min<int64_t>(56, (body + chunk - 1) / chunk);
+            for (int64_t i = 1; i <= nb; ++i) cuts.push_back(ramp_sum + body / nb * i);
+            cuts.back() = ramp_sum + body;
+            pos = ramp_sum + body;
+            for (int i = 2; i >= 0; --i) { pos += ramp[i]; cuts.push_back(pos); }
+        } else {
+            const int64_t k = std::min<int64_t>(62, std::max<int64_t>(1, (N + chunk - 1) / chunk));
+            for (int64_t i = 1; i <= k; ++i) cuts.push_back(N / k * i);
+        }
+        cuts.back() = N;
+    }
+    const int K = (int)cuts.size();
     while ((int)ctx->pipe_events.size() < 2 * K) {
         cudaEvent_t e = nullptr;
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->pipe_events.push_back(e);
+    }
+    // LAGASSIGN_TRACE: timing events at the end of every leg of every chunk
+    std::vector<cudaEvent_t> tev;
+    if (ctx->trace) {
+        tev.resize(1 + 3 * (size_t)K);
+        for (auto& e : tev) CUDA_TRY(ctx, cudaEventCreate(&e));
+        CUDA_TRY(ctx, cudaEventRecord(tev[0], ctx->stream_in));
     }
     DevBatch b = make_dev_batch(ctx);
     const int32_t* src_part = b.out_part;
@@ -479,7 +574,7 @@ int assign_batch_pipelined(lagassign_ctx* ctx, const lagassign_batch* in, const 
     for (int c = 0; c < K; ++c) {
         int64_t t_hi = T;
         if (c + 1 < K) {
-            const int64_t target = N / K * (c + 1);
+            const int64_t target = cuts[c];
             t_hi = std::lower_bound(in->topic_off, in->topic_off + T + 1, target) - in->topic_off;
             t_hi = std::min<int64_t>(std::max(t_hi, t_lo), T);
         }
@@ -495,6 +590,7 @@ int assign_batch_pipelined(lagassign_ctx* ctx, const lagassign_batch* in, const 
             }
         }
         CUDA_TRY(ctx, cudaEventRecord(ev_in, ctx->stream_in));
+        if (ctx->trace) CUDA_TRY(ctx, cudaEventRecord(tev[1 + 3 * c], ctx->stream_in));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ev_in, 0));
         auto slice = [&](const std::vector<int32_t>& v, int& lo, int& hi) {
             lo = (int)(std::lower_bound(v.begin(), v.end(), (int32_t)t_lo) - v.begin());
@@ -510,6 +606,7 @@ int assign_batch_pipelined(lagassign_ctx* ctx, const lagassign_batch* in, const 
             if (hi > lo) { launch_cta_topics(b, ctx->d_list_cta[c2].as<int32_t>() + lo, hi - lo, c2, ctx->sm_count, ctx->stream); ++launches; }
         }
         CUDA_TRY(ctx, cudaEventRecord(ev_out, ctx->stream));
+        if (ctx->trace) CUDA_TRY(ctx, cudaEventRecord(tev[2 + 3 * c], ctx->stream));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_out, ev_out, 0));
         if (n && out->out_partition) {
             CUDA_TRY(ctx, cudaMemcpyAsync(out->out_partition + e0, src_part + e0, n * 4, cudaMemcpyDeviceToHost, ctx->stream_out));
@@ -519,11 +616,24 @@ int assign_batch_pipelined(lagassign_ctx* ctx, const lagassign_batch* in, const 
             CUDA_TRY(ctx, cudaMemcpyAsync(out->out_consumer_rank + e0, src_cons + e0, n * 4, cudaMemcpyDeviceToHost, ctx->stream_out));
             ctx->stats.d2h_bytes += (int64_t)n * 4;
         }
+        if (ctx->trace) CUDA_TRY(ctx, cudaEventRecord(tev[3 + 3 * c], ctx->stream_out));
         t_lo = t_hi;
     }
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream_out));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->trace) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream_in));
+        fprintf(stderr, "[lagassign] pipeline of %d chunks, ms since the first copy was enqueued: chunk (partitions up to): h2d done / kernels done / d2h done\n", K);
+        for (int c = 0; c < K; ++c) {
+            float a = 0, k = 0, d = 0;
+            cudaEventElapsedTime(&a, tev[0], tev[1 + 3 * c]);
+            cudaEventElapsedTime(&k, tev[0], tev[2 + 3 * c]);
+            cudaEventElapsedTime(&d, tev[0], tev[3 + 3 * c]);
+            fprintf(stderr, "[lagassign]   %2d (%lld): %.3f / %.3f / %.3f\n", c, (long long)cuts[c], a, k, d);
+        }
+        for (auto& e : tev) cudaEventDestroy(e);
+    }
     ctx->stats.kernel_launches = launches;
     ctx->uploaded = true;
     ctx->executed = true;
@@ -557,6 +667,7 @@ int create_common(lagassign_ctx** out, int device, void* stream, bool own) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return fail(nullptr, LAGASSIGN_ERR_CUDA, "cudaGetDeviceProperties failed"); }
     ctx->sm_count = prop.multiProcessorCount;
+    { const char* tr = getenv("LAGASSIGN_TRACE"); ctx->trace = tr && tr[0] && tr[0] != '0'; }
     if (own) {
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return fail(nullptr, LAGASSIGN_ERR_CUDA, "cudaStreamCreate failed"); }
         ctx->own_stream = true;
@@ -608,6 +719,7 @@ void lagassign_destroy(lagassign_ctx* ctx) {
     for (DevBuf* gb : gbufs) gb->release();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->pipe_events) cudaEventDestroy(e);
+    if (ctx->ev_fork) { cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join[0]); cudaEventDestroy(ctx->ev_join[1]); }
     if (ctx->stream_in) cudaStreamDestroy(ctx->stream_in);
     if (ctx->stream_out) cudaStreamDestroy(ctx->stream_out);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -627,6 +739,13 @@ int lagassign_set_option(lagassign_ctx* ctx, int option, int64_t value) {
         case LAGASSIGN_OPT_GROUP:
             ctx->want_group = value != 0;
             ctx->uploaded = false;   // the grouping plan and buffers are set up at upload
+            return LAGASSIGN_OK;
+        case LAGASSIGN_OPT_PLAN_CACHE:
+            ctx->plan_cache = value != 0;
+            return LAGASSIGN_OK;
+        case LAGASSIGN_OPT_PIPE_CHUNK:
+            if (value < 0) return fail(ctx, LAGASSIGN_ERR_ARG, "pipeline chunk size must be >= 0");
+            ctx->pipe_chunk_elems = value;
             return LAGASSIGN_OK;
         case LAGASSIGN_OPT_TOTALS:
             ctx->want_totals = value != 0;
@@ -668,22 +787,55 @@ int lagassign_execute(lagassign_ctx* ctx) {
         CUDA_TRY(ctx, cudaMemsetAsync(b.out_total, 0, (size_t)ctx->total_tc * sizeof(int64_t), st));
         CUDA_TRY(ctx, cudaMemsetAsync(b.out_count, 0, (size_t)ctx->total_tc * sizeof(int32_t), st));
     }
+    // The size bins write disjoint slices of the outputs, so they may run side by side: when
+    // more than one bin has work (and per-kernel profiling is off), the warp bin and the CTA
+    // bin go to two side streams forked from / joined back into the context's stream, next to
+    // the radix chain. Small launches then fill the SMs a tail would leave idle.
+    int n_cta_all = 0;
+    for (int c = 0; c < N_CTA_CLASSES; ++c) n_cta_all += ctx->n_cta[c];
+    const int groups = (ctx->n_warp + ctx->n_none > 0) + (n_cta_all > 0) + (ctx->n_big > 0);
+    const bool fork = !ctx->profile && groups > 1;
+    cudaStream_t st_warp = st, st_cta = st;
+    if (fork) {
+        if (!ctx->stream_in) {
+            CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking));
+            CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking));
+        }
+        if (!ctx->ev_fork) {
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join[0], cudaEventDisableTiming));
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join[1], cudaEventDisableTiming));
+        }
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
+        if (ctx->n_big > 0) {          // the radix chain keeps the context's stream
+            st_warp = ctx->stream_in;
+            st_cta = ctx->stream_out;
+        } else {
+            st_cta = ctx->stream_out;  // warp bin on the context's stream, CTA bin beside it
+        }
+        if (st_warp != st) CUDA_TRY(ctx, cudaStreamWaitEvent(st_warp, ctx->ev_fork, 0));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(st_cta, ctx->ev_fork, 0));
+    }
     if (ctx->n_none > 0) {
         ProfScope ps(ctx, K_UNASSIGNED);
-        launch_unassigned_topics(b, ctx->d_list_none.as<int32_t>(), ctx->n_none, st);
+        launch_unassigned_topics(b, ctx->d_list_none.as<int32_t>(), ctx->n_none, st_warp);
         ++launches;
     }
     if (ctx->n_warp > 0) {
         ProfScope ps(ctx, K_WARP);
-        launch_warp_topics(b, ctx->d_list_warp.as<int32_t>(), ctx->n_warp, st);
+        launch_warp_topics(b, ctx->d_list_warp.as<int32_t>(), ctx->n_warp, st_warp);
         ++launches;
     }
     for (int c = 0; c < N_CTA_CLASSES; ++c) {
         if (ctx->n_cta[c] > 0) {
             ProfScope ps(ctx, K_CTA);
-            launch_cta_topics(b, ctx->d_list_cta[c].as<int32_t>(), ctx->n_cta[c], c, sms, st);
+            launch_cta_topics(b, ctx->d_list_cta[c].as<int32_t>(), ctx->n_cta[c], c, sms, st_cta);
             ++launches;
         }
+    }
+    if (fork) {
+        if (st_warp != st) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join[0], st_warp));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join[1], st_cta));
     }
     if (ctx->n_big > 0) {
         BigTopics bt = make_big(ctx);
@@ -739,6 +891,10 @@ int lagassign_execute(lagassign_ctx* ctx) {
             launch_big_fill(bt, ctx->d_list_fill.as<int32_t>(), ctx->n_fill, b, sms, st);
             ++launches;
         }
+    }
+    if (fork) {
+        if (st_warp != st) CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join[0], 0));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join[1], 0));
     }
     if (ctx->want_group && ctx->N > 0 && ctx->grp) {
         // stable partition of the flat result by member rank, see radix.cuh section 7
@@ -811,9 +967,18 @@ int lagassign_download(lagassign_ctx* ctx, const lagassign_result* out) {
 int lagassign_assign_batch(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_result* out) {
     if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
     if (!out) return fail(ctx, LAGASSIGN_ERR_ARG, "result is NULL");
+    const auto t0 = std::chrono::steady_clock::now();
     TRY(do_upload(ctx, in, nullptr, /*defer_data=*/true));     // plan + metadata; the large arrays follow
-    if (ctx->n_big == 0 && !ctx->want_totals && !ctx->want_group && ctx->N >= PIPE_MIN_ELEMS && !out->out_total && !out->out_count)
-        return assign_batch_pipelined(ctx, in, out);
+    if (ctx->n_big == 0 && !ctx->want_totals && !ctx->want_group && ctx->N >= PIPE_MIN_ELEMS && !out->out_total && !out->out_count) {
+        const auto t1 = std::chrono::steady_clock::now();
+        const int rc = assign_batch_pipelined(ctx, in, out);
+        if (ctx->trace) {
+            const auto t2 = std::chrono::steady_clock::now();
+            fprintf(stderr, "[lagassign] assign_batch: plan+metadata %.3f ms, pipelined copies+kernels %.3f ms\n",
+                    std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
+        }
+        return rc;
+    }
     TRY(upload_data_now(ctx, in));
     TRY(lagassign_execute(ctx));
     return lagassign_download(ctx, out);

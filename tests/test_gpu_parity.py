@@ -217,6 +217,68 @@ def test_chunked_pipeline_path(pkg):
         assert np.array_equal(again["out_partition"], exp2["out_partition"])
 
 
+def test_plan_cache_same_shape_new_lags(pkg):
+    """A batch with the shape of the previous one (same topics / consumer sets, fresh lags)
+    reuses the plan and the metadata on the device; results follow the NEW data, and any change
+    of shape or of an option that sizes outputs makes a new plan."""
+    rng = np.random.default_rng(1234)
+    b1 = random_flat(rng, T=300, pmin=0, pmax=4000, C=37, lag_kind="small", explicit_ids="shuffled", n_sets=3)
+    b1["topic_off"] = np.concatenate([b1["topic_off"], [b1["topic_off"][-1] + 20000]]).astype(np.int64)   # + a radix-path topic
+    b1["topic_cset"] = np.concatenate([b1["topic_cset"], [0]]).astype(np.int32)
+    n = int(b1["topic_off"][-1])
+    b1["lag"] = rng.integers(0, 50, size=n, dtype=np.int64)
+    b1["partition"] = None
+    with pkg.FlatAssignor(0, want_totals=True) as f:
+        for step in range(3):
+            b = dict(b1, lag=rng.integers(-5, 1 << (10 * step + 3), size=n, dtype=np.int64))
+            got = f.assign_batch(*args_of(b))
+            exp = oracle.assign_batch(*args_of(b), want_totals=True, threads=8)
+            for k in KEYS:
+                assert np.array_equal(got[k], exp[k]), (step, k)
+            assert f.stats()["n_partitions"] == n and f.stats()["topics_device"] == 1
+            if step > 0:
+                assert f.stats()["h2d_bytes"] == n * 8        # nothing but the lags went up again
+        # upload()/execute()/download() on the cached plan, with explicit ids this time (a new plan: ids are part of the shape flags)
+        ids = np.concatenate([rng.permutation(int(hi - lo)) for lo, hi in zip(b1["topic_off"][:-1], b1["topic_off"][1:])]).astype(np.int32)
+        b = dict(b1, lag=rng.integers(0, 3, size=n, dtype=np.int64), partition=ids)
+        got = f.assign_batch(*args_of(b))
+        exp = oracle.assign_batch(*args_of(b), want_totals=True, threads=8)
+        for k in KEYS:
+            assert np.array_equal(got[k], exp[k]), k
+        # same shape, one consumer set changed in place: must not hit the cache
+        b = dict(b, cset_rank=b["cset_rank"].copy())
+        b["cset_rank"][-1] += 1
+        got = f.assign_batch(*args_of(b))
+        exp = oracle.assign_batch(*args_of(b), want_totals=True, threads=8)
+        for k in KEYS:
+            assert np.array_equal(got[k], exp[k]), k
+        # fewer topics
+        T2 = 100
+        b = dict(b, topic_off=b["topic_off"][:T2 + 1], topic_cset=b["topic_cset"][:T2])
+        m = int(b["topic_off"][-1])
+        b["lag"], b["partition"] = b["lag"][:m], b["partition"][:m]
+        got = f.assign_batch(*args_of(b))
+        exp = oracle.assign_batch(*args_of(b), want_totals=True, threads=8)
+        for k in KEYS:
+            assert np.array_equal(got[k], exp[k]), k
+
+
+def test_pipeline_chunk_option(pkg):
+    """LAGASSIGN_OPT_PIPE_CHUNK only changes how assign_batch() overlaps its copies."""
+    rng = np.random.default_rng(78)
+    b = random_flat(rng, T=20000, pmin=1, pmax=500, C=64, lag_kind="small", explicit_ids=None, n_sets=2)
+    assert len(b["lag"]) > (1 << 21)
+    exp = oracle.assign_batch(*args_of(b), threads=8)
+    with pkg.FlatAssignor(0) as f:
+        for chunk in (0, 1 << 18, 1 << 20, 1 << 30):
+            f.set_option(pkg.OPT_PIPE_CHUNK, chunk)
+            got = f.assign_batch(*args_of(b))
+            assert np.array_equal(got["out_partition"], exp["out_partition"]), chunk
+            assert np.array_equal(got["out_consumer_rank"], exp["out_consumer_rank"]), chunk
+        with pytest.raises(pkg.LagAssignError):
+            f.set_option(pkg.OPT_PIPE_CHUNK, -1)
+
+
 def test_single_consumer_and_single_partition(flat):
     rng = np.random.default_rng(9)
     for P, C in ((1, 1), (1, 5000), (257, 1), (5000, 1), (70000, 1), (70000, 2)):
