@@ -129,11 +129,11 @@ typedef struct lagassign_stats {
 #define LAGASSIGN_OPT_TOTALS  1  /* produce out_total / out_count (default 0) */
 #define LAGASSIGN_OPT_PROFILE 2  /* bracket every kernel launch with CUDA events (default 0) */
 #define LAGASSIGN_OPT_GROUP   3  /* also group the result by member on the device (default 0) */
+#define LAGASSIGN_OPT_PIPE_CHUNK 4 /* partitions per chunk of the copy/compute pipeline of
+                                    * lagassign_assign_batch (0 = library default) */
 #define LAGASSIGN_OPT_PLAN_CACHE 5 /* reuse the plan and the device-resident metadata when a batch has the
                                     * shape (topic_off, topic_cset, consumer sets, flags) of the previous
                                     * one and only lags / ids / offsets differ (default 1) */
-#define LAGASSIGN_OPT_PIPE_CHUNK 4 /* partitions per chunk of the copy/compute pipeline of
-                                    * lagassign_assign_batch (0 = library default) */
 
 int  lagassign_abi_version(void);
 

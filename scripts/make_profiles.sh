@@ -3,7 +3,7 @@
 # usage: bash scripts/make_profiles.sh r01
 R=${1:-r01}
 cd "$(dirname "$0")/.."
-for n in warp_c4 scatter_c6 tilehist_c6 fill_c2; do ncu -i gpurun_out/prof_$n.ncu-rep --page raw --csv 2>/dev/null > gpurun_out/raw_$n.csv; done
+for n in warp_c4 scatter_c6 tilehist_c6 fill_c2 cta8_c5; do ncu -i gpurun_out/prof_$n.ncu-rep --page raw --csv 2>/dev/null > gpurun_out/raw_$n.csv; done
 filt() { grep -v "pcsamp\|per_second\|peak_sustained_elapsed"; }
 hdr() { echo "# $1"; echo "# ncu --set full --clock-control none --import-source on -k regex:$2 -c 1 python bench.py --config $3 --steps 1 --warmup 3 --no-cpu-baseline   (gpurun, 1 x B200, scripts/measure_round.sh)"; }
 (hdr "k_warp_topics, config 4 (100000 topics x 256 partitions)" k_warp_topics 4; python scripts/ncu_summary.py gpurun_out/raw_warp_c4.csv | filt) > profiles/${R}_ncu_k_warp_topics_config4.txt
@@ -11,6 +11,12 @@ hdr() { echo "# $1"; echo "# ncu --set full --clock-control none --import-source
  echo; echo "# per-tile cycle counters of the same kernel (build with -DLAGASSIGN_RT_TIMING; thread 0 of CTA 0 / 200; tile = 4096 elements, 2 CTAs/SM):"; tail -4 gpurun_out/scatter_phase_cycles.txt) > profiles/${R}_ncu_k_big_scatter_config6.txt
 (hdr "k_big_tile_hist, config 6" k_big_tile_hist 6; python scripts/ncu_summary.py gpurun_out/raw_tilehist_c6.csv | filt) > profiles/${R}_ncu_k_big_tile_hist_config6.txt
 (hdr "k_big_fill, config 2 (1 topic x 2^20 partitions, 1024 consumers: 1024 dependent rounds on one SM)" k_big_fill 2; python scripts/ncu_summary.py gpurun_out/raw_fill_c2.csv | filt) > profiles/${R}_ncu_k_big_fill_config2.txt
+(hdr "k_cta_topics<8> (1025..2048 partitions per topic), config 5" k_cta_topics 5; python scripts/ncu_summary.py gpurun_out/raw_cta8_c5.csv | filt) > profiles/${R}_ncu_k_cta_topics_config5.txt
+[ -s gpurun_out/bench_reference_c4.json ] && cp gpurun_out/bench_reference_c4.json profiles/${R}_bench_reference_config4.json
+if [ -s gpurun_out/memcheck_full.log ]; then
+  (echo "# compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py (whole GPU suite), scripts/measure_round.sh"; grep -c . gpurun_out/memcheck_full.log | sed 's/^/# log lines: /'; tail -2 gpurun_out/memcheck_full.log) > profiles/${R}_sanitizer.txt
+  [ -s gpurun_out/racecheck.log ] && (echo "# compute-sanitizer --tool racecheck, tests test_mixed_bins_and_edge_topics + test_wraparound_totals (scripts/sanitize.sh)"; tail -1 gpurun_out/racecheck.log) >> profiles/${R}_sanitizer.txt
+fi
 for c in 2 4 6; do python - <<PY
 import csv,collections
 rows=list(csv.reader(open("gpurun_out/launches_c$c.csv")))
@@ -24,8 +30,9 @@ for r in rows[hi+1:]:
 tot=sum(v[1] for v in agg.values())
 with open("profiles/${R}_launches_config$c.txt","w") as f:
     f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py --config $c --steps 2 --warmup 3 --no-cpu-baseline\n")
-    f.write("# all launches of the process: 5 execute() steps (3 warm-up + 2 timed) plus the e2e calls of bench.py, which\n")
-    f.write("# launch the on-chip kernels once per pipeline chunk. Cold-cache serialised times: compare SHARES, not absolutes.\n")
+    f.write("# all launches of the process: execute() steps (3 warm-up + 2 timed + 2 unprofiled), the e2e calls of bench.py (on-chip\n")
+    f.write("# kernels once per pipeline chunk) and its next-rows section (grouping: k_group_* + k_big_* of the member sort; device lag:\n")
+    f.write("# k_compute_lag). Cold-cache serialised times: compare SHARES, not absolutes.\n")
     f.write("%-60s %8s %14s %7s\n"%("kernel","launches","total ns","share"))
     for k,(n,t) in agg.items(): f.write("%-60s %8d %14.0f %6.1f%%\n"%(k[:60],n,t,100*t/tot))
 PY
