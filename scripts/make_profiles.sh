@@ -29,10 +29,9 @@ for r in rows[hi+1:]:
     a=agg.setdefault(k,[0,0.0]); a[0]+=1; a[1]+=float(r[ix["Metric Value"]])
 tot=sum(v[1] for v in agg.values())
 with open("profiles/${R}_launches_config$c.txt","w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py --config $c --steps 2 --warmup 3 --no-cpu-baseline\n")
-    f.write("# all launches of the process: execute() steps (3 warm-up + 2 timed + 2 unprofiled), the e2e calls of bench.py (on-chip\n")
-    f.write("# kernels once per pipeline chunk) and its next-rows section (grouping: k_group_* + k_big_* of the member sort; device lag:\n")
-    f.write("# k_compute_lag). Cold-cache serialised times: compare SHARES, not absolutes.\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py --config $c --steps 2 --warmup 3 --no-cpu-baseline --hot-path-only\n")
+    f.write("# --hot-path-only: the process launches nothing but the execute() steps (3 warm-up + 2 timed + 2 without per-kernel events);\n")
+    f.write("# no e2e calls, no next-rows section. Cold-cache serialised times: compare SHARES with bench.py's share_of_step, not absolutes.\n")
     f.write("%-60s %8s %14s %7s\n"%("kernel","launches","total ns","share"))
     for k,(n,t) in agg.items(): f.write("%-60s %8d %14.0f %6.1f%%\n"%(k[:60],n,t,100*t/tot))
 PY

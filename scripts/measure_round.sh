@@ -17,11 +17,11 @@ done
 timeout -s KILL 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference_c4.json 2> gpurun_out/bench_reference_c4.err
 for c in 4 6 2; do
   timeout -s KILL 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-    --log-file gpurun_out/launches_c$c.csv python bench.py --config $c --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+    --log-file gpurun_out/launches_c$c.csv python bench.py --config $c --steps 2 --warmup 3 --no-cpu-baseline --hot-path-only > /dev/null 2>&1
 done
 cap() {  # kernel regex, config, skip, output name
   timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:$1 -s $3 -c 1 \
-    -o gpurun_out/$4 python bench.py --config $2 --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+    -o gpurun_out/$4 python bench.py --config $2 --steps 1 --warmup 3 --no-cpu-baseline --hot-path-only > /dev/null 2>&1
 }
 cap k_warp_topics 4 3 prof_warp_c4
 cap k_big_scatter 6 10 prof_scatter_c6
