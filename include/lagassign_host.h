@@ -26,6 +26,8 @@
 
 #include <stdint.h>
 
+#include "lagassign.h"   /* lagassign_batch, error codes */
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -62,6 +64,24 @@ int  lagassign_group_add_topic_lags(lagassign_group *g, const char *topic,
 
 /* assign(partitionLagPerTopic, subscriptions) (Main:166-188) on the GPU. */
 int  lagassign_group_assign(lagassign_group *g);
+
+/* The two host-side halves of lagassign_group_assign, for a caller that runs the device step
+ * itself (its own context / stream, or several groups in one lagassign_assign_batch) and for
+ * the CPU tests of the host logic:
+ *   flatten:   ranks members (String.compareTo, Main:258-259), builds consumersPerTopic and its
+ *              HashMap iteration order (Main:410-426, :177), de-duplicates consumer sets and lays
+ *              lags / ids out flat. *batch_out points into storage owned by the group, valid until
+ *              the next flatten / clear / destroy; batch_out->partition is NULL when every topic
+ *              lists ids 0..P-1 in order. Needs no GPU.
+ *   unflatten: takes the device step's two output arrays (N entries each, as lagassign_result)
+ *              for the batch of the last flatten and fills the group's results exactly as
+ *              lagassign_group_assign does (Main:264 append order). */
+int  lagassign_group_flatten(lagassign_group *g, lagassign_batch *batch_out);
+int  lagassign_group_unflatten(lagassign_group *g, const int32_t *out_partition,
+                               const int32_t *out_consumer_rank);
+/* Members in String.compareTo order: the meaning of the ranks in cset_rank / out_consumer_rank. */
+int64_t lagassign_group_member_count(const lagassign_group *g);
+const char *lagassign_group_member_at_rank(const lagassign_group *g, int64_t rank);
 
 /* Results: Map<member, List<TopicPartition>>. */
 int64_t lagassign_group_result_size(const lagassign_group *g, const char *member_id); /* -1: unknown member */

@@ -78,7 +78,8 @@ def build_host(force: bool = False) -> str:
     if not os.path.isdir(hdir):
         return ""
     srcs = _sources("host", (".cpp",))
-    deps = srcs + _sources("host", (".hpp", ".h")) + [os.path.join(ROOT, "include", "lagassign.h")]
+    deps = srcs + _sources("host", (".hpp", ".h")) + [os.path.join(ROOT, "include", "lagassign.h"),
+                                                       os.path.join(ROOT, "include", "lagassign_host.h")]
     if not srcs:
         return ""
     if not force and os.path.exists(HOST_LIB) and os.path.getmtime(HOST_LIB) >= max(_newest(deps), os.path.getmtime(LIB)):

@@ -49,6 +49,12 @@ def _load_host():
     H.lagassign_group_add_subscription.argtypes = [vp, cp, ctypes.POINTER(cp), i32]
     H.lagassign_group_add_topic_lags.argtypes = [vp, cp, vp, vp, i64]
     H.lagassign_group_assign.argtypes = [vp]
+    H.lagassign_group_flatten.argtypes = [vp, vp]
+    H.lagassign_group_unflatten.argtypes = [vp, vp, vp]
+    H.lagassign_group_member_count.argtypes = [vp]
+    H.lagassign_group_member_count.restype = i64
+    H.lagassign_group_member_at_rank.argtypes = [vp, i64]
+    H.lagassign_group_member_at_rank.restype = cp
     H.lagassign_group_result_size.argtypes = [vp, cp]
     H.lagassign_group_result_size.restype = i64
     H.lagassign_group_result_get.argtypes = [vp, cp, i64, ctypes.POINTER(cp), ctypes.POINTER(ctypes.c_int32)]
@@ -123,9 +129,7 @@ class LagBasedPartitionAssignor:
     def name(self) -> str:
         return self._H.lagassign_group_name(self._g).decode()
 
-    # static assign(Map, Map), Main:166-188
-    def assign(self, partition_lag_per_topic: Mapping[str, Sequence[TopicPartitionLag]],
-               subscriptions: Mapping[str, Sequence[str]]) -> Dict[str, List[TopicPartition]]:
+    def _load_maps(self, partition_lag_per_topic, subscriptions) -> List[str]:
         H = self._H
         self._check(H.lagassign_group_clear(self._g))
         members = list(subscriptions.keys())            # iteration order of the caller's map
@@ -139,7 +143,58 @@ class LagBasedPartitionAssignor:
             self._check(H.lagassign_group_add_topic_lags(
                 self._g, _enc(topic), parts.ctypes.data if len(parts) else None,
                 lags.ctypes.data if len(lags) else None, len(lags)))
+        return members
+
+    # static assign(Map, Map), Main:166-188
+    def assign(self, partition_lag_per_topic: Mapping[str, Sequence[TopicPartitionLag]],
+               subscriptions: Mapping[str, Sequence[str]]) -> Dict[str, List[TopicPartition]]:
+        H = self._H
+        members = self._load_maps(partition_lag_per_topic, subscriptions)
         self._check(H.lagassign_group_assign(self._g))
+        return self._collect(members)
+
+    # The host-side halves of assign() (lagassign_group_flatten / _unflatten): what happens before
+    # and after the device call. No GPU needed; the CPU tests drive them with the oracle in between.
+    def flatten(self, partition_lag_per_topic, subscriptions):
+        """Returns (flat dict of numpy arrays as in include/lagassign.h, topics in assignment
+        order, members by String.compareTo rank). Arrays are copies."""
+        from . import _Batch
+        H = self._H
+        self._flat_members = self._load_maps(partition_lag_per_topic, subscriptions)
+        b = _Batch()
+        self._check(H.lagassign_group_flatten(self._g, ctypes.byref(b)))
+        T, S = int(b.n_topics), int(b.n_csets)
+
+        def arr(ptr, n, dtype):
+            if not ptr or n == 0:
+                return np.zeros(0, dtype)
+            ct = ctypes.c_int64 if dtype == np.int64 else ctypes.c_int32
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ct)), shape=(n,)).astype(dtype, copy=True)
+        topic_off = arr(b.topic_off, T + 1, np.int64)
+        N = int(topic_off[-1]) if T >= 0 and len(topic_off) else 0
+        cset_off = arr(b.cset_off, S + 1, np.int64)
+        R = int(cset_off[-1]) if len(cset_off) else 0
+        flat = dict(topic_off=topic_off, lag=arr(b.lag, N, np.int64),
+                    partition=arr(b.partition, N, np.int32) if b.partition else None,
+                    topic_cset=arr(b.topic_cset, T, np.int32), cset_off=cset_off,
+                    cset_rank=arr(b.cset_rank, R, np.int32))
+        topics = [H.lagassign_group_topic_at(self._g, i).decode("utf-8", "surrogatepass")
+                  for i in range(H.lagassign_group_topic_count(self._g))]
+        by_rank = [H.lagassign_group_member_at_rank(self._g, r).decode("utf-8", "surrogatepass")
+                   for r in range(H.lagassign_group_member_count(self._g))]
+        self.topic_order = topics
+        return flat, topics, by_rank
+
+    def unflatten(self, out_partition, out_consumer_rank) -> Dict[str, List[TopicPartition]]:
+        """Per-member lists from the device step's outputs for the batch of the last flatten()."""
+        op = np.ascontiguousarray(out_partition, dtype=np.int32)
+        oc = np.ascontiguousarray(out_consumer_rank, dtype=np.int32)
+        self._check(self._H.lagassign_group_unflatten(self._g, op.ctypes.data if len(op) else None,
+                                                       oc.ctypes.data if len(oc) else None))
+        return self._collect(self._flat_members)
+
+    def _collect(self, members) -> Dict[str, List[TopicPartition]]:
+        H = self._H
         out: Dict[str, List[TopicPartition]] = {}
         t = ctypes.c_char_p()
         p = ctypes.c_int32()

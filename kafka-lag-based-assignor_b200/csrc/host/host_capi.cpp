@@ -17,6 +17,8 @@ struct lagassign_group {
     Subscriptions subscriptions;
     PartitionLagPerTopic lags;
     Assignment result;
+    FlatBatch flat;
+    bool flat_valid = false;
     std::map<std::string, size_t> result_index;
     std::vector<std::string> topic_order;
     std::string err, client_id, name;
@@ -71,6 +73,7 @@ const char* lagassign_group_name(const lagassign_group* g) { return g ? g->name.
 int lagassign_group_clear(lagassign_group* g) {
     if (!g) return fail(nullptr, LAGASSIGN_ERR_ARG, "group is NULL");
     g->subscriptions.clear(); g->lags.clear(); g->result.clear(); g->result_index.clear(); g->topic_order.clear();
+    g->flat = FlatBatch(); g->flat_valid = false;
     return LAGASSIGN_OK;
 }
 
@@ -102,6 +105,50 @@ int lagassign_group_assign(lagassign_group* g) {
     g->result_index.clear();
     for (size_t i = 0; i < g->result.size(); ++i) g->result_index[g->result[i].first] = i;
     return LAGASSIGN_OK;
+}
+
+int lagassign_group_flatten(lagassign_group* g, lagassign_batch* batch_out) {
+    if (!g || !batch_out) return fail(g, LAGASSIGN_ERR_ARG, "group or batch_out is NULL");
+    g->flat_valid = false;
+    try {
+        g->flat = LagBasedPartitionAssignor::flatten(g->lags, g->subscriptions);
+    } catch (const std::exception& e) {
+        return fail(g, LAGASSIGN_ERR_UNSUPPORTED, e.what());
+    }
+    g->flat_valid = true;
+    g->topic_order = g->flat.topics;
+    const FlatBatch& fb = g->flat;
+    std::memset(batch_out, 0, sizeof *batch_out);
+    batch_out->n_topics = (int64_t)fb.topics.size();
+    batch_out->topic_off = fb.topic_off.data();
+    batch_out->lag = fb.lag.data();
+    batch_out->partition = fb.implicit_ids ? nullptr : fb.partition.data();
+    batch_out->topic_cset = fb.topic_cset.data();
+    batch_out->n_csets = (int64_t)fb.cset_off.size() - 1;
+    batch_out->cset_off = fb.cset_off.data();
+    batch_out->cset_rank = fb.cset_rank.data();
+    return LAGASSIGN_OK;
+}
+
+int lagassign_group_unflatten(lagassign_group* g, const int32_t* out_partition, const int32_t* out_consumer_rank) {
+    if (!g) return fail(nullptr, LAGASSIGN_ERR_ARG, "group is NULL");
+    if (!g->flat_valid) return fail(g, LAGASSIGN_ERR_STATE, "unflatten() before flatten()");
+    const int64_t N = g->flat.topic_off.empty() ? 0 : g->flat.topic_off.back();
+    if (N > 0 && (!out_partition || !out_consumer_rank)) return fail(g, LAGASSIGN_ERR_ARG, "output arrays are NULL");
+    const int32_t M = (int32_t)g->flat.members.size();
+    for (int64_t i = 0; i < N; ++i)
+        if (out_consumer_rank[i] >= M) return fail(g, LAGASSIGN_ERR_ARG, "out_consumer_rank holds a rank beyond the member count");
+    g->result = LagBasedPartitionAssignor::unflatten(g->flat, out_partition, out_consumer_rank);
+    g->result_index.clear();
+    for (size_t i = 0; i < g->result.size(); ++i) g->result_index[g->result[i].first] = i;
+    return LAGASSIGN_OK;
+}
+
+int64_t lagassign_group_member_count(const lagassign_group* g) { return (g && g->flat_valid) ? (int64_t)g->flat.members.size() : 0; }
+
+const char* lagassign_group_member_at_rank(const lagassign_group* g, int64_t rank) {
+    if (!g || !g->flat_valid || rank < 0 || rank >= (int64_t)g->flat.by_rank.size()) return nullptr;
+    return g->flat.members[(size_t)g->flat.by_rank[(size_t)rank]].c_str();
 }
 
 int64_t lagassign_group_result_size(const lagassign_group* g, const char* member_id) {

@@ -35,6 +35,21 @@ using PartitionLagPerTopic = std::unordered_map<std::string, std::vector<TopicPa
 // order of `subscriptions`.
 using Assignment = std::vector<std::pair<std::string, std::vector<TopicPartition>>>;
 
+// The arguments of lagassign_assign_batch() for one assign() call, plus what is needed to
+// turn the flat result back into per-member lists. Built by flatten(), consumed by unflatten().
+struct FlatBatch {
+    std::vector<std::string> members;     // result order = order of `subscriptions` (first occurrence)
+    std::vector<int32_t> by_rank;         // String.compareTo rank -> index into members
+    std::vector<std::string> topics;      // assignment order = HashMap iteration order (Main:177)
+    std::vector<int64_t> topic_off;       // [T+1]
+    std::vector<int64_t> lag;             // [N]
+    std::vector<int32_t> partition;       // [N]
+    bool implicit_ids = true;             // every topic lists partitions 0..P-1 in order
+    std::vector<int32_t> topic_cset;      // [T]
+    std::vector<int64_t> cset_off;        // [S+1]
+    std::vector<int32_t> cset_rank;       // member ranks, ascending inside a set
+};
+
 class LagBasedPartitionAssignor {
  public:
     explicit LagBasedPartitionAssignor(int device = 0);
@@ -55,6 +70,14 @@ class LagBasedPartitionAssignor {
     // topics in the order they were assigned.
     Assignment assign(const PartitionLagPerTopic& partitionLagPerTopic, const Subscriptions& subscriptions,
                       std::vector<std::string>* topicOrderOut = nullptr);
+
+    // The two host-side halves of assign(): everything before and after the device call.
+    // flatten: member ranks (Main:258-259), consumersPerTopic and its iteration order
+    // (Main:410-426, :177), consumer sets de-duplicated, lags/ids laid out flat.
+    // unflatten: Main:264's appends, topics in assignment order, inside a topic in
+    // assignment order; out_consumer_rank < 0 = not assigned.
+    static FlatBatch flatten(const PartitionLagPerTopic& partitionLagPerTopic, const Subscriptions& subscriptions);
+    static Assignment unflatten(const FlatBatch& flat, const int32_t* out_partition, const int32_t* out_consumer_rank);
 
     // static computePartitionLag (Main:376-404); committed == nullptr means no
     // committed offset (partitionMetadata == null).

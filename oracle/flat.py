@@ -31,7 +31,9 @@ def flatten(partition_lag_per_topic: Dict[str, List[Tuple[str, int, int]]],
             part.append(p)
             lag.append(l)
         topic_off.append(len(lag))
-        key = tuple(sorted(rank[m] for m in cpt[t]))
+        # a member that lists the topic twice appears twice in cpt[t] but is ONE key of the
+        # per-topic maps (Main:216-219): a consumer set is a set
+        key = tuple(sorted({rank[m] for m in cpt[t]}))
         topic_cset.append(csets.setdefault(key, len(csets)))
     cset_off = [0]
     cset_rank: List[int] = []
