@@ -1,8 +1,7 @@
-// kernels_cta.cuh — topics whose partitions fit on chip: the whole of
-// assignTopic (LagBasedPartitionAssignor.java:204-277) for one topic in one warp
-// (P <= 256, registers) or one CTA (P <= 4096, shared memory). Lags are read from
-// HBM once and the two result arrays written once: 16 B per partition (20 B with
-// explicit partition ids).
+// kernels_cta.cuh — topics of 257..4096 partitions: the whole of assignTopic
+// (LagBasedPartitionAssignor.java:204-277) for one topic in ONE CTA, partitions in the
+// registers of its 256 threads. Same I/O as the warp kernel (kernels_warp.cuh): lags read
+// once, the two result arrays written once.
 #pragma once
 #include "common.cuh"
 #include "types.cuh"
@@ -18,6 +17,7 @@ namespace lagassign {
 // occupancy match the class). Same ideas as the warp kernel: branch-free register sort
 // (shuffles inside a warp, shared-memory exchanges only for the three index bits that cross
 // warps), adaptive element width with the optimistic one-word sort, staged coalesced stores.
+// (Not yet ported from the warp kernel: neutral padding and 16-byte stores from registers.)
 
 constexpr int CTA_THREADS = 256;
 

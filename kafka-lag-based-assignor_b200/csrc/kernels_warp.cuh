@@ -1,8 +1,8 @@
-// kernels_warp.cuh — topics whose partitions fit on chip: the whole of
-// assignTopic (LagBasedPartitionAssignor.java:204-277) for one topic in one warp
-// (P <= 256, registers) or one CTA (P <= 4096, shared memory). Lags are read from
-// HBM once and the two result arrays written once: 16 B per partition (20 B with
-// explicit partition ids).
+// kernels_warp.cuh — topics of up to 256 partitions: the whole of assignTopic
+// (LagBasedPartitionAssignor.java:204-277) for one topic in ONE WARP, partitions in
+// registers. Lags are read from HBM once and the two result arrays written once: 16 B per
+// partition (20 B with explicit partition ids). Larger topics: kernels_cta.cuh (one CTA,
+// up to 4096 partitions), radix.cuh (device-wide).
 #pragma once
 #include "common.cuh"
 #include "types.cuh"

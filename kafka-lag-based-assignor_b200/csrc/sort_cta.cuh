@@ -1,7 +1,9 @@
-// sort_cta.cuh — bitonic sort of n = 2^m (key, pay) elements in shared memory by
-// one CTA. Strides below 64 are done by each warp on a private 64-element window
-// between two __syncwarp()s (no CTA barrier); larger strides take one
-// __syncthreads() per stage.
+// sort_cta.cuh — CTA-wide bitonic sorts of (key, pay) elements.
+//  * cta_bitonic_sort(): n = 2^m elements in SHARED MEMORY (used by the round fill when a
+//    topic has more than 4096 consumers). Strides below 64 are done by each warp on a private
+//    64-element window between two __syncwarp()s (no CTA barrier); larger strides take one
+//    __syncthreads() per stage.
+//  * cta_bitonic_sort_regs(): elements in REGISTERS (k_cta_topics, k_big_fill), see below.
 #pragma once
 #include "common.cuh"
 #include "sort_warp.cuh"
@@ -47,7 +49,7 @@ __device__ __forceinline__ void cta_bitonic_sort(uint64_t* key, uint32_t* pay, i
 }
 
 // ---- register-resident variant -----------------------------------------------------------
-// n = NT*EPT elements of W words (see sort_warp.cuh; W = 1 or 3 here) held in registers by a
+// n = NT*EPT elements of W words (see sort_warp.cuh; W = 1, 2 or 3) held in registers by a
 // CTA of NT threads, logical index i = tid*EPT + r. Strides below EPT are in-register, below
 // 32*EPT warp shuffles, and only the log2(NT/32) highest index bits cross warps: those
 // stages exchange through shared memory (one __syncthreads() each, two alternating
