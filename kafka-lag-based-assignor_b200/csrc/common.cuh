@@ -13,7 +13,11 @@
 //    pay = index in the topic's consumer list, which is member-id order (:259).
 #pragma once
 #include <cstdint>
+#ifdef LAGASSIGN_HOST_EMULATION
+#include "cuda_emu.hpp"   // tests/emu/: the same device templates compiled with g++ (test infrastructure only)
+#else
 #include <cuda_runtime.h>
+#endif
 
 namespace lagassign {
 

@@ -132,7 +132,11 @@ __device__ __forceinline__ bool cta_sort_adaptive(uint64_t (&key)[EPT], uint32_t
 template <int EPT>
 __global__ void __launch_bounds__(CTA_THREADS, (EPT >= 16) ? 1 : 2)
 k_cta_topics(DevBatch b, const int32_t* __restrict__ list, int n_list) {
+#ifdef LAGASSIGN_HOST_EMULATION
+    unsigned char* smem_raw = emu::cta().dyn_smem;
+#else
     extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
     using L = CtaRegSmem<EPT>;
     constexpr int NT = CTA_THREADS, N = L::N;
     uint32_t* xbuf = reinterpret_cast<uint32_t*>(smem_raw + L::xbuf_off);

@@ -21,6 +21,9 @@ namespace lagassign {
 
 // a < b for W-word unsigned integers (scalars passed most significant first).
 __device__ __forceinline__ bool lt3(uint32_t a2, uint32_t a1, uint32_t a0, uint32_t b2, uint32_t b1, uint32_t b0) {
+#ifdef LAGASSIGN_HOST_EMULATION
+    return a2 != b2 ? a2 < b2 : (a1 != b1 ? a1 < b1 : a0 < b0);
+#else
     uint32_t borrow;
     asm("{\n\t.reg .u32 t;\n\t"
         "sub.cc.u32 t, %1, %4;\n\t"
@@ -29,6 +32,7 @@ __device__ __forceinline__ bool lt3(uint32_t a2, uint32_t a1, uint32_t a0, uint3
         "subc.u32 %0, 0, 0;\n\t}"
         : "=r"(borrow) : "r"(a0), "r"(a1), "r"(a2), "r"(b0), "r"(b1), "r"(b2));
     return borrow != 0;
+#endif
 }
 __device__ __forceinline__ bool lt2(uint32_t a1, uint32_t a0, uint32_t b1, uint32_t b0) {
     return (((uint64_t)a1 << 32) | a0) < (((uint64_t)b1 << 32) | b0);

@@ -2,7 +2,6 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
-#include <cuda_runtime.h>
 
 #include "common.cuh"
 
