@@ -9,6 +9,8 @@
 #include <pthread.h>
 
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -149,10 +151,19 @@ inline int __all_sync(unsigned, int p) {
 }
 
 // ---- memory and arithmetic intrinsics ------------------------------------------------------------
-template <class T> inline T __ldg(const T* p) { return *p; }
-template <class T> inline T __ldcs(const T* p) { return *p; }
-template <class T, class V> inline void __stcs(T* p, V v) { *p = (T)v; }
-inline void __stcs(int4* p, int4 v) { *p = v; }
+namespace emu {
+// the hardware faults on a misaligned vector access; x86 would not: check it here
+inline void check_aligned(const void* p, size_t n) {
+    if (reinterpret_cast<uintptr_t>(p) % n != 0) {
+        std::fprintf(stderr, "cuda_emu: %zu-byte access at misaligned address %p\n", n, p);
+        std::abort();
+    }
+}
+}  // namespace emu
+template <class T> inline T __ldg(const T* p) { emu::check_aligned(p, sizeof(T)); return *p; }
+template <class T> inline T __ldcs(const T* p) { emu::check_aligned(p, sizeof(T)); return *p; }
+template <class T, class V> inline void __stcs(T* p, V v) { emu::check_aligned(p, sizeof(T)); *p = (T)v; }
+inline void __stcs(int4* p, int4 v) { emu::check_aligned(p, 16); *p = v; }
 inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 inline int __clz(unsigned x) { return x == 0 ? 32 : __builtin_clz(x); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
