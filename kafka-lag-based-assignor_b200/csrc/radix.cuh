@@ -162,6 +162,13 @@ k_big_scan(BigTopics bt, int first_pass) {
 constexpr int RT_STAGES = LAGASSIGN_RT_STAGES;
 static_assert(RT_THREADS == 256, "the pass kernels map one thread to one digit value");
 
+#ifdef LAGASSIGN_HOST_EMULATION   // tests/emu: the copy happens at issue, groups are no-ops
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) { std::memcpy(smem_dst, gsrc, 8); }
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) { std::memcpy(smem_dst, gsrc, 4); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {}
+#else
 __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -171,6 +178,7 @@ __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
 
 // 4a ------------------------------------------------------------------------------------------
 template <bool HAS_PART>
@@ -291,7 +299,11 @@ struct PassSmem {
 template <bool HAS_PART>
 __global__ void __launch_bounds__(RT_THREADS, LAGASSIGN_RT_MINBLOCKS)
 k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int32_t* __restrict__ part) {
+#ifdef LAGASSIGN_HOST_EMULATION
+    unsigned char* smem_raw = emu::cta().dyn_smem;
+#else
     extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
     PassSmem& sm = *reinterpret_cast<PassSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (bt.pass_any[pass] == 0) return;   // every topic's digit is constant: nothing to move
@@ -540,7 +552,11 @@ k_big_fill(BigTopics bt, const int32_t* __restrict__ fill_list, int n_fill,
            const int32_t* __restrict__ topic_cset, const int64_t* __restrict__ cset_off,
            const int32_t* __restrict__ cset_rank, const int64_t* __restrict__ tc_off,
            int32_t* __restrict__ out_cons, int64_t* __restrict__ out_total, int32_t* __restrict__ out_count) {
+#ifdef LAGASSIGN_HOST_EMULATION
+    unsigned char* smem_raw = emu::cta().dyn_smem;
+#else
     extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
     uint64_t* ckey = reinterpret_cast<uint64_t*>(smem_raw);
     uint32_t* cidx = reinterpret_cast<uint32_t*>(smem_raw + sizeof(uint64_t) * FILL_CTA_MAX_C);
     for (int li = blockIdx.x; li < n_fill; li += gridDim.x) {

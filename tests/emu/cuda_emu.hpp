@@ -131,6 +131,13 @@ template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned delta) {
 template <class T> inline T __shfl_sync(unsigned, T v, int src) {
     return emu::warp_exchange(v, [&](auto at) { return at(src); });
 }
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned delta) {
+    const int me = emu::tid() & 31;
+    return emu::warp_exchange(v, [&](auto at) { return (me - (int)delta >= 0) ? at(me - (int)delta) : at(me); });
+}
+inline unsigned __match_any_sync(unsigned, unsigned v) {
+    return emu::warp_exchange(v, [&](auto at) { unsigned m = 0; for (int l = 0; l < 32; ++l) m |= (unsigned)(at(l) == v) << l; return m; });
+}
 inline unsigned __reduce_or_sync(unsigned, unsigned v) {
     return emu::warp_exchange(v, [&](auto at) { unsigned r = 0; for (int l = 0; l < 32; ++l) r |= at(l); return r; });
 }
@@ -164,6 +171,15 @@ template <class T> inline T __ldg(const T* p) { emu::check_aligned(p, sizeof(T))
 template <class T> inline T __ldcs(const T* p) { emu::check_aligned(p, sizeof(T)); return *p; }
 template <class T, class V> inline void __stcs(T* p, V v) { emu::check_aligned(p, sizeof(T)); *p = (T)v; }
 inline void __stcs(int4* p, int4 v) { emu::check_aligned(p, 16); *p = v; }
+// atomics: the CUDA threads are concurrent host threads, so these must be real atomics
+template <class T> inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+template <class T> inline T atomicOr(T* p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+template <class T> inline T atomicMax(T* p, T v) {
+    T old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 inline int __clz(unsigned x) { return x == 0 ? 32 : __builtin_clz(x); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }

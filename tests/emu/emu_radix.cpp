@@ -1,0 +1,115 @@
+// emu_radix.cpp — TEST INFRASTRUCTURE: the device-wide path of the product (radix.cuh: k_big_order_check,
+// k_big_hist, k_big_scan, k_big_tile_hist, k_big_seg_scan, k_big_topic_scan, k_big_scatter, k_big_finalize,
+// k_big_fill) compiled for the HOST with the stand-in of cuda_emu.hpp and run one CTA at a time, in the
+// launch order of lagassign_execute(). The planning below restates the big-topic part of validate_and_plan()
+// (lagassign_api.cu) and is test code: it may disagree with the product, which is the point of checking.
+// Built and driven by tests/test_kernels_emulated_cpu.py; never part of the library.
+#define LAGASSIGN_HOST_EMULATION 1
+#include "cuda_emu.hpp"
+
+#include "radix.cuh"
+
+#include <algorithm>
+#include <vector>
+
+using namespace lagassign;
+
+namespace {
+template <class K> void launch(int grid, int block, K k) { if (grid > 0) emu::launch(grid, block, k); }
+}
+
+// Every topic with more than `min_big_p` partitions and a non-empty consumer set goes through the radix
+// path (the product uses it above 4096; smaller thresholds exercise short last tiles and one-tile topics).
+// `sms` scales the grids like the SM count does in the product (small values force grid-stride loops).
+// Returns the number of topics processed, -1 for an unsupported shape.
+extern "C" int emu_assign_big(int64_t n_topics, const int64_t* topic_off, const int64_t* lag, const int32_t* partition,
+                              const int32_t* topic_cset, const int64_t* cset_off, const int32_t* cset_rank,
+                              const int64_t* tc_off, int32_t* out_partition, int32_t* out_consumer_rank,
+                              int64_t* out_total, int32_t* out_count, int64_t min_big_p, int sms, int* passes_run_out) {
+    std::vector<int32_t> bt_topic, bt_tile0, tile_bt, l_fill, bt_seg0, seg_bt;
+    std::vector<int64_t> bt_off, bt_P, bt_boff;
+    std::vector<TileDesc> tile_desc;
+    int64_t boff = 0, tiles = 0;
+    int n_segs = 0;
+    for (int64_t t = 0; t < n_topics; ++t) {
+        const int64_t P = topic_off[t + 1] - topic_off[t];
+        const int32_t s = topic_cset[t];
+        const int64_t C = cset_off[s + 1] - cset_off[s];
+        if (P <= min_big_p || C == 0) continue;
+        if (P > C && C > FILL_CTA_MAX_C) return -1;
+        const int64_t nt = (P + RT_TILE - 1) / RT_TILE;
+        const int32_t b = (int32_t)bt_topic.size();
+        bt_topic.push_back((int32_t)t); bt_off.push_back(topic_off[t]); bt_P.push_back(P); bt_boff.push_back(boff);
+        bt_tile0.push_back((int32_t)tiles); bt_seg0.push_back(n_segs);
+        const int nseg = (int)((nt + RT_SEG - 1) / RT_SEG);
+        for (int k = 0; k < nseg; ++k) seg_bt.push_back(b);
+        for (int64_t k = 0; k < nt; ++k) {
+            tile_bt.push_back(b);
+            TileDesc d;
+            d.b = b; d.tile_in_topic = (int32_t)k; d.n_valid = (int32_t)std::min<int64_t>(RT_TILE, P - k * RT_TILE);
+            d.seg = (int32_t)(n_segs + k / RT_SEG); d.buf_off = boff + k * RT_TILE; d.raw_off = topic_off[t] + k * RT_TILE;
+            tile_desc.push_back(d);
+        }
+        n_segs += nseg;
+        if (P > C) l_fill.push_back(b);
+        boff += P; tiles += nt;
+    }
+    const int B = (int)bt_topic.size();
+    if (B == 0) return 0;
+    static_assert(sizeof(TileDesc) == 32, "tile descriptors are read as two int4");
+
+    std::vector<uint64_t> keyA((size_t)boff), keyB((size_t)boff);
+    std::vector<uint32_t> payA((size_t)boff), payB((size_t)boff);
+    std::vector<uint32_t> ghist((size_t)B * N_PASS * 256, 0), gbase((size_t)B * N_PASS * 256, 0);
+    std::vector<int8_t> sel((size_t)B * (2 * N_PASS + 2), 0);
+    std::vector<int32_t> need_tie((size_t)B, 0);
+    std::vector<uint32_t> tile_hist((size_t)tiles * 256, 0), seg_total((size_t)n_segs * 256, 0), ticket(2 * N_PASS + 1, 0);
+
+    BigTopics bt{};
+    bt.n_big = B; bt.n_tiles = (int)tiles;
+    bt.topic = bt_topic.data(); bt.off = bt_off.data(); bt.P = bt_P.data(); bt.boff = bt_boff.data();
+    bt.tile0 = bt_tile0.data(); bt.tile_bt = tile_bt.data();
+    bt.tile_desc = reinterpret_cast<const int4*>(tile_desc.data());
+    bt.keyA = keyA.data(); bt.keyB = keyB.data(); bt.payA = payA.data(); bt.payB = payB.data();
+    bt.ghist = ghist.data(); bt.gbase = gbase.data();
+    bt.sel_src = sel.data(); bt.sel_dst = sel.data() + (size_t)B * N_PASS;
+    bt.sel_final = sel.data() + (size_t)B * N_PASS * 2; bt.all_equal = sel.data() + (size_t)B * (N_PASS * 2 + 1);
+    bt.need_tie = need_tie.data(); bt.tile_hist = tile_hist.data();
+    bt.seg0 = bt_seg0.data(); bt.seg_bt = seg_bt.data(); bt.n_segs = n_segs; bt.seg_total = seg_total.data();
+    bt.ticket = ticket.data(); bt.passes_run = reinterpret_cast<int32_t*>(ticket.data() + N_PASS);
+    bt.pass_any = ticket.data() + N_PASS + 1;
+
+    DevBatch db{};
+    db.topic_off = topic_off; db.lag = lag; db.part = partition; db.topic_cset = topic_cset;
+    db.cset_off = cset_off; db.cset_rank = cset_rank; db.tc_off = tc_off;
+    db.out_part = out_partition; db.out_cons = out_consumer_rank; db.out_total = out_total; db.out_count = out_count;
+
+    // the launch sequence of lagassign_execute() for the device bin (launch_big.cu for the grid sizes)
+    const bool has_part = partition != nullptr;
+    const int first_pass = has_part ? 0 : N_TIE_PASS;
+    const int n_tiles = (int)tiles;
+    if (has_part) launch(std::min(n_tiles, sms * 8), 256, [&] { k_big_order_check(bt, partition); });
+    if (has_part) launch(std::min(n_tiles, sms * 6), RT_THREADS, [&] { k_big_hist<true>(bt, lag, partition); });
+    else launch(std::min(n_tiles, sms * 6), RT_THREADS, [&] { k_big_hist<false>(bt, lag, nullptr); });
+    launch(B, 256, [&] { k_big_scan(bt, first_pass); });
+    for (int p = first_pass; p < N_PASS; ++p) {
+        if (bt.pass_any[p] == 0) continue;
+        if (has_part) launch(std::min(n_tiles, sms * 8), RT_THREADS, [&] { k_big_tile_hist<true>(bt, p, lag, partition); });
+        else launch(std::min(n_tiles, sms * 8), RT_THREADS, [&] { k_big_tile_hist<false>(bt, p, lag, nullptr); });
+        launch(n_segs, 256, [&] { k_big_seg_scan(bt, p); });
+        launch(B, 256, [&] { k_big_topic_scan(bt, p); });
+        if (has_part) launch(std::min(n_tiles, sms * 2), RT_THREADS, [&] { k_big_scatter<true>(bt, p, lag, partition); });
+        else launch(std::min(n_tiles, sms * 2), RT_THREADS, [&] { k_big_scatter<false>(bt, p, lag, nullptr); });
+    }
+    launch(std::min(n_tiles, sms * 8), 256, [&] {
+        k_big_finalize(bt, lag, partition, topic_cset, cset_off, cset_rank, tc_off, out_partition, out_consumer_rank, out_total, out_count);
+    });
+    if (!l_fill.empty()) {
+        const int n_fill = (int)l_fill.size();
+        launch(std::min(n_fill, sms), BIGFILL_THREADS, [&] {
+            k_big_fill(bt, l_fill.data(), n_fill, lag, topic_cset, cset_off, cset_rank, tc_off, out_consumer_rank, out_total, out_count);
+        });
+    }
+    if (passes_run_out) *passes_run_out = *bt.passes_run;
+    return B;
+}

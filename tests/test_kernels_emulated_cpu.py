@@ -7,7 +7,9 @@ rendezvous for shuffles / reductions / barriers) and this file checks them bit-e
 the oracle. It is a logic check that needs no GPU: it covers the sort networks, the adaptive
 element widths, the optimistic truncated sort and its fallback, explicit-id handling, the round
 fill in all its variants and the store paths. It says nothing about timing, memory-model
-behaviour or the radix path (cp.async, inline PTX), which only the `-m gpu` tests exercise.
+behaviour (cp.async is a plain copy here), which only the `-m gpu` tests exercise. The
+device-wide path (radix.cuh) runs the same way through tests/emu/emu_radix.cpp, which restates the
+big-topic planning and the launch order of lagassign_execute().
 """
 import ctypes
 import os
@@ -52,6 +54,26 @@ def emu():
     return L
 
 
+@pytest.fixture(scope="module")
+def emu_radix():
+    inc = _cuda_include()
+    if inc is None:
+        pytest.skip("CUDA headers (vector_types.h) not found")
+    out = os.path.join(EMU, "_build")
+    os.makedirs(out, exist_ok=True)
+    lib = os.path.join(out, "libemu_radix.so")
+    srcs = [os.path.join(EMU, f) for f in ("emu_radix.cpp", "cuda_emu.hpp")] + \
+           [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(s) for s in srcs):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        r = subprocess.run([cxx, "-O1", "-std=c++17", "-pthread", "-fPIC", "-shared", "-w", "-I", EMU, "-I", CSRC,
+                            "-I", inc, "-o", lib, os.path.join(EMU, "emu_radix.cpp")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+    L = ctypes.CDLL(lib)
+    L.emu_assign_big.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 11 + [ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]
+    return L
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data
 
@@ -71,8 +93,28 @@ def run_emulated(L, b, totals):
     return dict(out_partition=op, out_consumer_rank=oc, out_total=ot, out_count=on)
 
 
-def check(L, b, totals=True):
-    got = run_emulated(L, b, totals)
+def run_emulated_radix(L, b, totals, min_big_p, sms=2):
+    T = len(b["topic_off"]) - 1
+    N = int(b["topic_off"][-1])
+    C = (b["cset_off"][1:] - b["cset_off"][:-1])[b["topic_cset"]] if T else np.zeros(0, np.int64)
+    tc_off = np.concatenate([[0], np.cumsum(C)]).astype(np.int64)
+    op = np.full(N, -7, np.int32)
+    oc = np.full(N, -7, np.int32)
+    ot = np.zeros(int(tc_off[-1]), np.int64) if totals else None
+    on = np.zeros(int(tc_off[-1]), np.int32) if totals else None
+    passes = ctypes.c_int(0)
+    n = L.emu_assign_big(T, _ptr(b["topic_off"]), _ptr(b["lag"]), _ptr(b["partition"]), _ptr(b["topic_cset"]),
+                         _ptr(b["cset_off"]), _ptr(b["cset_rank"]), _ptr(tc_off), _ptr(op), _ptr(oc), _ptr(ot), _ptr(on),
+                         min_big_p, sms, ctypes.byref(passes))
+    assert n >= 0
+    return dict(out_partition=op, out_consumer_rank=oc, out_total=ot, out_count=on), passes.value
+
+
+def check(L, b, totals=True, radix_min_p=None):
+    if radix_min_p is None:
+        got = run_emulated(L, b, totals)
+    else:
+        got, _ = run_emulated_radix(L, b, totals, radix_min_p)
     exp = oracle.assign_batch(*args_of(b), want_totals=True, threads=4)
     off, cs = b["topic_off"], b["topic_cset"]
     for t in range(len(off) - 1):
@@ -155,3 +197,31 @@ def test_cta_kernel_idle_topic_and_equal_rounds(emu):
     check(emu, b, totals=True)
     lag = np.concatenate([np.arange(500, 0, -1), np.zeros(500)]).astype(np.int64)    # busy head, idle tail
     check(emu, uniform_batch(1, 1000, 300, lag), totals=True)
+
+
+@pytest.mark.parametrize("case", [
+    # (T, pmin, pmax, C, lag kind, ids, totals, threshold)
+    (2, 4097, 9000, 1200, "small", None, True, 4096),        # few digit passes, multi-round fill in registers
+    (3, 1, 3000, 50, "u40", None, False, 0),                 # one-tile topics, short last tiles, warp-sized fill
+    (2, 5000, 13000, 5000, "full", "shuffled", True, 4096),  # all 8 lag passes + id tie passes, P > C with C > 4096 (shared-memory fill)
+    (1, 9000, 9000, 300, "dups", "dups", True, 4096),        # duplicate ids and lags
+    (2, 100, 9000, 20000, "small", "sorted", False, 0),      # P <= C: no fill kernel; ids given but already ascending
+])
+def test_radix_path_on_cpu(emu_radix, case):
+    T, pmin, pmax, C, kind, ids, totals, thr = case
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()))
+    b = random_flat(rng, T=T, pmin=pmin, pmax=pmax, C=C, lag_kind=kind, explicit_ids=ids, n_sets=1)
+    check(emu_radix, b, totals, radix_min_p=thr)
+
+
+def test_radix_path_skips_constant_digits(emu_radix):
+    """All-equal lags run zero passes (order = input order, closed-form fill); lags below 2^16 run two."""
+    b = uniform_batch(1, 6000, 64, np.full(6000, 42, np.int64))
+    got, passes = run_emulated_radix(emu_radix, b, True, 4096)
+    assert passes == 0
+    check(emu_radix, b, True, radix_min_p=4096)
+    rng = np.random.default_rng(11)
+    b = uniform_batch(1, 6000, 7000, rng.integers(0, 1 << 16, size=6000, dtype=np.int64))
+    got, passes = run_emulated_radix(emu_radix, b, False, 4096)
+    assert passes == 2
+    check(emu_radix, b, False, radix_min_p=4096)
