@@ -27,6 +27,61 @@ template <> struct Log2E<4> { static constexpr int value = 2; };
 template <> struct Log2E<8> { static constexpr int value = 3; };
 template <> struct Log2E<16> { static constexpr int value = 4; };
 
+#ifdef LAGASSIGN_PACKED_WARP_FILL
+// Sort the C live consumers of a warp by (tkey, cid); padding (KEY_SENTINEL, PAY_SENTINEL) stays behind them.
+template <int EPTC>
+__device__ __forceinline__ void warp_sort_consumers_packed(uint64_t (&tkey)[EPTC], uint32_t (&cid)[EPTC], int C) {
+    constexpr int B = 5 + Log2E<EPTC>::value;          // log2 of the slot count
+    constexpr uint32_t IDMASK = (1u << B) - 1u;
+    const unsigned lane = lane_id();
+    uint64_t lmin = ~0ull, lmax = 0;
+#pragma unroll
+    for (int r = 0; r < EPTC; ++r) {
+        if (cid[r] != PAY_SENTINEL) {
+            lmin = tkey[r] < lmin ? tkey[r] : lmin;
+            lmax = tkey[r] > lmax ? tkey[r] : lmax;
+        }
+    }
+    const uint32_t mnh = __reduce_min_sync(0xffffffffu, (uint32_t)(lmin >> 32));
+    const uint32_t mnl = __reduce_min_sync(0xffffffffu, ((uint32_t)(lmin >> 32) == mnh) ? (uint32_t)lmin : 0xFFFFFFFFu);
+    const uint32_t mxh = __reduce_max_sync(0xffffffffu, (uint32_t)(lmax >> 32));
+    const uint32_t mxl = __reduce_max_sync(0xffffffffu, ((uint32_t)(lmax >> 32) == mxh) ? (uint32_t)lmax : 0u);
+    const uint64_t gmin = ((uint64_t)mnh << 32) | mnl, gmax = ((uint64_t)mxh << 32) | mxl;
+    const uint64_t range = gmax - gmin;
+    if ((range >> (32 - B)) == 0) {
+        uint32_t w[1][EPTC];
+#pragma unroll
+        for (int r = 0; r < EPTC; ++r)
+            w[0][r] = (cid[r] != PAY_SENTINEL) ? (((uint32_t)(tkey[r] - gmin) << B) | cid[r]) : 0xFFFFFFFFu;
+        warp_bitonic_sort_words<1, EPTC>(w);
+#pragma unroll
+        for (int r = 0; r < EPTC; ++r) {
+            const bool live = (int)lane * EPTC + r < C;        // padding sorts last
+            tkey[r] = live ? gmin + (uint64_t)(w[0][r] >> B) : KEY_SENTINEL;
+            cid[r] = live ? (w[0][r] & IDMASK) : PAY_SENTINEL;
+        }
+    } else if ((range >> (64 - B)) == 0) {
+        uint32_t w[2][EPTC];
+#pragma unroll
+        for (int r = 0; r < EPTC; ++r) {
+            const uint64_t v = (cid[r] != PAY_SENTINEL) ? (((tkey[r] - gmin) << B) | cid[r]) : ~0ull;
+            w[0][r] = (uint32_t)v;
+            w[1][r] = (uint32_t)(v >> 32);
+        }
+        warp_bitonic_sort_words<2, EPTC>(w);
+#pragma unroll
+        for (int r = 0; r < EPTC; ++r) {
+            const bool live = (int)lane * EPTC + r < C;
+            const uint64_t v = ((uint64_t)w[1][r] << 32) | w[0][r];
+            tkey[r] = live ? gmin + (v >> B) : KEY_SENTINEL;
+            cid[r] = live ? ((uint32_t)v & IDMASK) : PAY_SENTINEL;
+        }
+    } else {
+        warp_bitonic_sort<EPTC>(tkey, cid);
+    }
+}
+#endif
+
 // One warp, C <= 32*EPTC consumers in registers (position j = lane*EPTC + r).
 //   lag_at(k)        -> int64 lag of the k-th partition in sorted order
 //   put(k, rank)     -> record that sorted partition k goes to global member `rank`
@@ -67,7 +122,14 @@ __device__ __forceinline__ void warp_round_fill(int64_t P, int C, const int32_t*
             const uint64_t nk = __shfl_down_sync(0xffffffffu, tkey[0], 1);
             const uint32_t nc = __shfl_down_sync(0xffffffffu, cid[0], 1);
             if (lane < 31) ok = ok && !elem_less(nk, nc, tkey[EPTC - 1], cid[EPTC - 1]);
+#ifdef LAGASSIGN_PACKED_WARP_FILL
+            // Experimental (compiled out by default; verified under tests/emu, not yet measured on a B200):
+            // totals of one round lie close together, so sort (total - smallest total) << B | index as ONE
+            // 32-bit or 64-bit word when it fits instead of three words (same idea as cta_round_fill_regs).
+            if (!__all_sync(0xffffffffu, ok)) warp_sort_consumers_packed<EPTC>(tkey, cid, C);
+#else
             if (!__all_sync(0xffffffffu, ok)) warp_bitonic_sort<EPTC>(tkey, cid);
+#endif
         }
 #pragma unroll
         for (int r = 0; r < EPTC; ++r) {

@@ -8,7 +8,7 @@ import numpy as np, ctypes
 import oracle
 from helpers import random_flat, args_of
 import test_kernels_emulated_cpu as tk
-L = ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "_build", "libemu_onchip.so"))
+L = ctypes.CDLL(os.environ.get("EMU_LIB") or os.path.join(ROOT, "tests", "emu", "_build", "libemu_onchip.so"))   # EMU_LIB: a variant build
 L.emu_assign_onchip.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 11
 seed0 = int(sys.argv[1]); n = int(sys.argv[2])
 t0 = time.time(); fails = 0
