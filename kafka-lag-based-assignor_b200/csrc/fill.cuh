@@ -313,7 +313,55 @@ __device__ __forceinline__ void cta_round_fill_regs(int64_t P, int C, const int3
                         w[2][r] = live ? (uint32_t)(tk >> 32) : 0xFFFFFFFFu;
                     }
                 } else {
+#ifdef LAGASSIGN_FILL_OPTIMISTIC_W2
+                    // Experimental (compiled out by default; verified under tests/emu, not yet measured on a B200):
+                    // totals too far apart for the exact one-word form (high-entropy 63-bit lags, BASELINE config 2).
+                    // Sort the TOP 64-B bits of (total - smallest total) with the index below them, optimistically:
+                    // if no two neighbours of the result share the truncated total the order is the exact
+                    // (total, index) order. The full totals wait in shared memory, indexed by consumer.
+                    constexpr int N = NT * EPT;
+                    uint64_t* tot_by_id = reinterpret_cast<uint64_t*>(xbuf + 4 * N);     // behind the two 2-word exchange buffers
+                    const int sh = bits_of(gmax - gmin) - (64 - B);                        // >= 1 here
+                    uint32_t w2[2][EPT];
+#pragma unroll
+                    for (int r = 0; r < EPT; ++r) {
+                        const bool live = w[0][r] != PAY_SENTINEL;
+                        const uint64_t tk = ((uint64_t)w[2][r] << 32) | w[1][r];
+                        if (live) tot_by_id[w[0][r]] = tk;
+                        const uint64_t v = live ? ((((tk - gmin) >> sh) << B) | w[0][r]) : ~0ull;
+                        w2[0][r] = (uint32_t)v; w2[1][r] = (uint32_t)(v >> 32);
+                    }
+                    cta_bitonic_sort_regs<2, EPT, NT>(w2, xbuf);
+                    int dup = 0;
+#pragma unroll
+                    for (int r = 0; r + 1 < EPT; ++r) {
+                        const uint64_t a = (((uint64_t)w2[1][r] << 32) | w2[0][r]) >> B, c2 = (((uint64_t)w2[1][r + 1] << 32) | w2[0][r + 1]) >> B;
+                        dup |= (tid * EPT + r + 1 < C) && a == c2;
+                    }
+                    __syncthreads();          // every thread is through the last exchange of the sort: xbuf is free
+                    xbuf[tid] = w2[0][0]; xbuf[NT + tid] = w2[1][0];
+                    __syncthreads();
+                    if (tid + 1 < NT && tid * EPT + EPT < C) {
+                        const uint64_t a = (((uint64_t)w2[1][EPT - 1] << 32) | w2[0][EPT - 1]) >> B;
+                        const uint64_t c2 = (((uint64_t)xbuf[NT + tid + 1] << 32) | xbuf[tid + 1]) >> B;
+                        dup |= a == c2;
+                    }
+                    if (!__syncthreads_or(dup)) {
+#pragma unroll
+                        for (int r = 0; r < EPT; ++r) {
+                            const bool live = tid * EPT + r < C;       // padding sorts last
+                            const uint32_t id = w2[0][r] & ((1u << B) - 1u);
+                            const uint64_t tk = live ? tot_by_id[id] : ~0ull;
+                            w[0][r] = live ? id : PAY_SENTINEL;
+                            w[1][r] = (uint32_t)tk;
+                            w[2][r] = (uint32_t)(tk >> 32);
+                        }
+                    } else {
+                        cta_bitonic_sort_regs<3, EPT, NT>(w, xbuf);    // w[] is untouched: exact sort
+                    }
+#else
                     cta_bitonic_sort_regs<3, EPT, NT>(w, xbuf);
+#endif
                 }
             }
         }

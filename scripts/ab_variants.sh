@@ -1,0 +1,16 @@
+#!/bin/bash
+# A/B of variants/*.so (scripts/build_variants.sh) against the committed library on a B200: the GPU parity tests
+# that touch the changed path, then the configs whose dominant kernel it is. Run through gpurun.
+run() {  # label, pytest -k expression, configs...
+  echo "== $1"; shift
+  timeout -s KILL 400 python -m pytest tests/test_gpu_parity.py -q -x --timeout=380 -k "$1" 2>&1 | tail -1; shift
+  for c in "$@"; do
+    timeout -s KILL 200 python bench.py --config $c --steps 10 --no-cpu-baseline 2>/dev/null | tail -1 | \
+      python -c "import sys,json; d=json.loads(sys.stdin.read()); print('config', d['config']['config'], '%.4e'%d['value'], {k: round(v, 4) for k, v in d['kernel_ms_per_step'].items()})"
+  done
+}
+K1="warp_bin or realistic or random_shape or config3 or wraparound"
+K2="cta_bin or device_bin or config2 or mixed or single_consumer or wraparound or realistic"
+unset LAGASSIGN_LIBRARY; run "committed" "$K1 or $K2" 7 2 3
+export LAGASSIGN_LIBRARY=$PWD/variants/liblagassign_packedfill.so; run "packed warp fill" "$K1" 7 3
+export LAGASSIGN_LIBRARY=$PWD/variants/liblagassign_optw2.so; run "optimistic two-word fill" "$K2" 2
