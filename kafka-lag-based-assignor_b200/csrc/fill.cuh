@@ -20,6 +20,10 @@
 
 namespace lagassign {
 
+template <int NT> struct Log2NT;
+template <> struct Log2NT<256> { static constexpr int value = 8; };
+template <> struct Log2NT<512> { static constexpr int value = 9; };
+template <> struct Log2NT<1024> { static constexpr int value = 10; };
 template <int E> struct Log2E;
 template <> struct Log2E<1> { static constexpr int value = 0; };
 template <> struct Log2E<2> { static constexpr int value = 1; };
@@ -291,8 +295,7 @@ __device__ __forceinline__ void cta_round_fill_regs(int64_t P, int C, const int3
                 // Totals of one round lie close together (that is what the greedy fill is for):
                 // if (total - smallest total) fits above the index bits of one 64-bit word, sort
                 // that word (6 instructions per compare-exchange instead of 10); else three words.
-                constexpr int B = 8 + Log2E<EPT>::value;          // log2(NT*EPT), NT = 256
-                static_assert(NT == 256, "B assumes 256 threads");
+                constexpr int B = Log2NT<NT>::value + Log2E<EPT>::value;          // log2(NT*EPT)
                 if (((gmax - gmin) >> (64 - B)) == 0) {
                     uint32_t w2[2][EPT];
 #pragma unroll

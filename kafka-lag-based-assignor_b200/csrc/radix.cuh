@@ -580,6 +580,7 @@ k_big_fill(BigTopics bt, const int32_t* __restrict__ fill_list, int n_fill,
         uint32_t* xbuf = reinterpret_cast<uint32_t*>(smem_raw);
         if (C <= FILL_WARP_MAX_C) {
             if (threadIdx.x < 32) warp_round_fill_dispatch(P, C, cset, lag_at, put, tot, cnt);
+#if LAGASSIGN_BIGFILL_THREADS == 256
         } else if (C <= 512) {
             cta_round_fill_regs<2, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
         } else if (C <= 1024) {
@@ -588,6 +589,16 @@ k_big_fill(BigTopics bt, const int32_t* __restrict__ fill_list, int n_fill,
             cta_round_fill_regs<8, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
         } else if (C <= BIGFILL_REG_MAX_C) {
             cta_round_fill_regs<16, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
+#else   // experimental thread counts: the smallest register tile that holds the consumers
+        } else if (C <= BIGFILL_THREADS) {
+            cta_round_fill_regs<1, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
+        } else if (C <= 2 * BIGFILL_THREADS) {
+            cta_round_fill_regs<2, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
+        } else if (C <= 4 * BIGFILL_THREADS && 4 * BIGFILL_THREADS <= BIGFILL_REG_MAX_C) {
+            cta_round_fill_regs<4, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
+        } else if (C <= 8 * BIGFILL_THREADS && 8 * BIGFILL_THREADS <= BIGFILL_REG_MAX_C) {
+            cta_round_fill_regs<8, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
+#endif
         } else {
             cta_round_fill<BIGFILL_MAXJ>(P, C, max(64, 1 << (32 - __clz(C - 1))), cset, ckey, cidx,
                                          lag_at, put, tot, cnt);

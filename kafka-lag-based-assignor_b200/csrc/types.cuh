@@ -85,7 +85,10 @@ struct BigTopics {
 };
 
 
-constexpr int BIGFILL_THREADS = 256;
+#ifndef LAGASSIGN_BIGFILL_THREADS
+#define LAGASSIGN_BIGFILL_THREADS 256     // experimental: 512 / 1024 (more warps for the sequential round chain)
+#endif
+constexpr int BIGFILL_THREADS = LAGASSIGN_BIGFILL_THREADS;
 constexpr int BIGFILL_MAXJ = FILL_CTA_MAX_C / BIGFILL_THREADS;
 constexpr int BIGFILL_REG_MAX_C = 4096;                      // consumers kept in registers up to here
 constexpr size_t BIGFILL_SMEM = (size_t)FILL_CTA_MAX_C * 12; // >= 2*3*4096 words of exchange buffers

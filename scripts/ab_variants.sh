@@ -14,3 +14,4 @@ K2="cta_bin or device_bin or config2 or mixed or single_consumer or wraparound o
 unset LAGASSIGN_LIBRARY; run "committed" "$K1 or $K2" 7 2 3
 export LAGASSIGN_LIBRARY=$PWD/variants/liblagassign_packedfill.so; run "packed warp fill" "$K1" 7 3
 export LAGASSIGN_LIBRARY=$PWD/variants/liblagassign_optw2.so; run "optimistic two-word fill" "$K2" 2
+export LAGASSIGN_LIBRARY=$PWD/variants/liblagassign_fill1024.so; run "optimistic two-word fill, 1024-thread k_big_fill" "device_bin or config2 or mixed or single_consumer or wraparound" 2
