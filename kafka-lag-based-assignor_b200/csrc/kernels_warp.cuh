@@ -155,7 +155,20 @@ __device__ __forceinline__ bool warp_sort_adaptive(uint64_t (&key)[EPT], uint32_
             key[r] = hi | (v >> B);
         }
     } else {
+#ifdef LAGASSIGN_WARP_GENERAL_BY_COPY
+        // Experimental (compiled out by default): hand the out-of-line sort COPIES, so that key[] / pay[]
+        // are not address-taken and stay in registers on the common path (today they cost ~22 local-memory
+        // stores per topic at config 4, ncu source view).
+        uint64_t k3[EPT];
+        uint32_t p3[EPT];
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) { k3[r] = key[r]; p3[r] = pay[r]; }
+        warp_sort_general<EPT>(k3, p3);
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) { key[r] = k3[r]; pay[r] = p3[r]; }
+#else
         warp_sort_general<EPT>(key, pay);
+#endif
     }
     return true;
 }
