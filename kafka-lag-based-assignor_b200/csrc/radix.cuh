@@ -76,6 +76,61 @@ k_big_hist(BigTopics bt, const int64_t* __restrict__ lag, const int32_t* __restr
         const int64_t t0 = (int64_t)(g - bt.tile0[b]) * RT_TILE;
         const int64_t* lg = lag + bt.off[b];
         const bool tie = HAS_PART && bt.need_tie[b] != 0;
+#ifdef LAGASSIGN_HIST_TILE_SKIP
+        // Experimental (compiled out by default; verified under tests/emu, not yet measured on a B200): a digit
+        // on which all keys of the tile agree (the high bytes of small lags, every byte of an idle topic) is
+        // counted with ONE atomic for the tile instead of one same-address atomic per element.
+        __shared__ uint32_t red[RT_WARPS][4];
+        uint64_t key[RT_IPT];
+        uint64_t o = 0, a = ~0ull;
+#pragma unroll
+        for (int k = 0; k < RT_IPT; ++k) {
+            const int64_t e = t0 + k * RT_THREADS + threadIdx.x;
+            key[k] = (e < P) ? ((uint64_t)ld_stream(lg + e) ^ LAG_KEY_MASK) : 0ull;
+            if (e < P) { o |= key[k]; a &= key[k]; }
+        }
+        {
+            const uint32_t o_lo = __reduce_or_sync(0xffffffffu, (uint32_t)o), o_hi = __reduce_or_sync(0xffffffffu, (uint32_t)(o >> 32));
+            const uint32_t a_lo = __reduce_and_sync(0xffffffffu, (uint32_t)a), a_hi = __reduce_and_sync(0xffffffffu, (uint32_t)(a >> 32));
+            if ((threadIdx.x & 31) == 0) {
+                uint32_t* row = red[threadIdx.x >> 5];
+                row[0] = o_lo; row[1] = o_hi; row[2] = a_lo; row[3] = a_hi;
+            }
+        }
+        __syncthreads();
+        uint64_t all_or = 0, all_and = ~0ull;
+#pragma unroll
+        for (int w = 0; w < RT_WARPS; ++w) {
+            all_or |= ((uint64_t)red[w][1] << 32) | red[w][0];
+            all_and &= ((uint64_t)red[w][3] << 32) | red[w][2];
+        }
+        const uint64_t diff = all_or ^ all_and;            // bits in which the tile's keys differ
+        const uint32_t n_valid = (uint32_t)min((int64_t)RT_TILE, P - t0);
+#pragma unroll
+        for (int d = 0; d < N_LAG_PASS; ++d) {
+            if (((diff >> (8 * d)) & 0xFFull) == 0) {      // uniform over the CTA
+                if (threadIdx.x == 0) atomicAdd(&h[N_TIE_PASS + d][digit_of(all_and, d)], n_valid);
+            } else {
+#pragma unroll
+                for (int k = 0; k < RT_IPT; ++k) {
+                    const int64_t e = t0 + k * RT_THREADS + threadIdx.x;
+                    if (e < P) atomicAdd(&h[N_TIE_PASS + d][digit_of(key[k], d)], 1u);
+                }
+            }
+        }
+        if (tie) {
+#pragma unroll 4
+            for (int k = 0; k < RT_IPT; ++k) {
+                const int64_t e = t0 + k * RT_THREADS + threadIdx.x;
+                if (e < P) {
+                    const uint32_t pk = (uint32_t)part[bt.off[b] + e] ^ 0x80000000u;
+#pragma unroll
+                    for (int d = 0; d < N_TIE_PASS; ++d) atomicAdd(&h[d][(pk >> (8 * d)) & 0xFFu], 1u);
+                }
+            }
+        }
+        __syncthreads();      // red[] is rewritten by the next tile
+#else
 #pragma unroll 4
         for (int k = 0; k < RT_IPT; ++k) {
             const int64_t e = t0 + k * RT_THREADS + threadIdx.x;
@@ -91,6 +146,7 @@ k_big_hist(BigTopics bt, const int64_t* __restrict__ lag, const int32_t* __restr
                 }
             }
         }
+#endif
     }
     flush(cur_b);
 }

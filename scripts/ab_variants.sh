@@ -11,8 +11,9 @@ run() {  # label, pytest -k expression, configs...
 }
 K1="warp_bin or realistic or random_shape or config3 or wraparound"
 K2="cta_bin or device_bin or config2 or mixed or single_consumer or wraparound or realistic"
-unset LAGASSIGN_LIBRARY; run "committed" "$K1 or $K2" 4 7 2 3
+unset LAGASSIGN_LIBRARY; run "committed" "$K1 or $K2 or config5 or grouping" 4 7 2 3 5 6
 export LAGASSIGN_LIBRARY=$PWD/variants/liblagassign_nostl.so; run "warp kernel without address-taken key/pay arrays" "$K1" 4 7 3
 export LAGASSIGN_LIBRARY=$PWD/variants/liblagassign_packedfill.so; run "packed warp fill" "$K1" 7 3
 export LAGASSIGN_LIBRARY=$PWD/variants/liblagassign_optw2.so; run "optimistic two-word fill" "$K2" 2
 export LAGASSIGN_LIBRARY=$PWD/variants/liblagassign_fill1024.so; run "optimistic two-word fill, 1024-thread k_big_fill" "device_bin or config2 or mixed or single_consumer or wraparound" 2
+export LAGASSIGN_LIBRARY=$PWD/variants/liblagassign_histskip.so; run "k_big_hist with per-tile constant-digit skip" "device_bin or config2 or config5 or mixed or grouping" 5 2 6
