@@ -13,6 +13,7 @@ K1="warp_bin or realistic or random_shape or config3 or wraparound"
 K2="cta_bin or device_bin or config2 or mixed or single_consumer or wraparound or realistic"
 unset LAGASSIGN_LIBRARY; run "committed" "$K1 or $K2 or config5 or grouping" 4 7 2 3 5 6
 export LAGASSIGN_LIBRARY=$PWD/variants/liblagassign_nostl.so; run "warp kernel without address-taken key/pay arrays" "$K1" 4 7 3
+export LAGASSIGN_LIBRARY=$PWD/variants/liblagassign_groups.so; run "four topics per warp (+ by-copy general sort)" "$K1 or config4 or mixed or chunked" 4 7 3
 export LAGASSIGN_LIBRARY=$PWD/variants/liblagassign_packedfill.so; run "packed warp fill" "$K1" 7 3
 export LAGASSIGN_LIBRARY=$PWD/variants/liblagassign_optw2.so; run "optimistic two-word fill" "$K2" 2
 export LAGASSIGN_LIBRARY=$PWD/variants/liblagassign_fill1024.so; run "optimistic two-word fill, 1024-thread k_big_fill" "device_bin or config2 or mixed or single_consumer or wraparound" 2
