@@ -135,7 +135,7 @@ def check(L, b, totals=True, radix_min_p=None):
 def test_warp_kernel_on_cpu(emu, lag_kind, ids):
     rng = np.random.default_rng(zlib.crc32(repr((lag_kind, ids)).encode()))
     for C, totals in ((1, True), (7, False), (40, True), (300, ids is not None)):
-        b = random_flat(rng, T=6, pmin=0, pmax=256, C=C, lag_kind=lag_kind, explicit_ids=ids, n_sets=2)
+        b = random_flat(rng, T=4, pmin=0, pmax=256, C=C, lag_kind=lag_kind, explicit_ids=ids, n_sets=2)
         check(emu, b, totals)
 
 
@@ -201,9 +201,9 @@ def test_cta_kernel_idle_topic_and_equal_rounds(emu):
 
 @pytest.mark.parametrize("case", [
     # (T, pmin, pmax, C, lag kind, ids, totals, threshold)
-    (2, 4097, 9000, 1200, "small", None, True, 4096),        # few digit passes, multi-round fill in registers
+    (1, 4097, 6000, 1200, "small", None, True, 4096),        # few digit passes, multi-round fill in registers
     (3, 1, 3000, 50, "u40", None, False, 0),                 # one-tile topics, short last tiles, warp-sized fill
-    (2, 5000, 13000, 5000, "full", "shuffled", True, 4096),  # all 8 lag passes + id tie passes, P > C with C > 4096 (shared-memory fill)
+    (1, 5100, 9000, 5000, "full", "shuffled", True, 4096),   # all 8 lag passes + id tie passes, P > C with C > 4096 (shared-memory fill)
     (1, 9000, 9000, 300, "dups", "dups", True, 4096),        # duplicate ids and lags
     (2, 100, 9000, 20000, "small", "sorted", False, 0),      # P <= C: no fill kernel; ids given but already ascending
 ])
