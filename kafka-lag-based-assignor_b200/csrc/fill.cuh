@@ -296,6 +296,28 @@ __device__ __forceinline__ void cta_round_fill_regs(int64_t P, int C, const int3
                 // if (total - smallest total) fits above the index bits of one 64-bit word, sort
                 // that word (6 instructions per compare-exchange instead of 10); else three words.
                 constexpr int B = Log2NT<NT>::value + Log2E<EPT>::value;          // log2(NT*EPT)
+#ifdef LAGASSIGN_FILL_W1
+                // Experimental (compiled out by default; verified under tests/emu, not yet measured on a B200):
+                // small lags keep a round's totals within 2^(32-B) of each other; then ONE 32-bit word per
+                // consumer orders them (min/max compare-exchange: 2 instructions instead of 6).
+                if (((gmax - gmin) >> (32 - B)) == 0) {
+                    uint32_t w1[1][EPT];
+#pragma unroll
+                    for (int r = 0; r < EPT; ++r) {
+                        const uint64_t tk = ((uint64_t)w[2][r] << 32) | w[1][r];
+                        w1[0][r] = (w[0][r] != PAY_SENTINEL) ? (((uint32_t)(tk - gmin) << B) | w[0][r]) : 0xFFFFFFFFu;
+                    }
+                    cta_bitonic_sort_regs<1, EPT, NT>(w1, xbuf);
+#pragma unroll
+                    for (int r = 0; r < EPT; ++r) {
+                        const bool live = tid * EPT + r < C;       // padding sorts last
+                        const uint64_t tk = gmin + (uint64_t)(w1[0][r] >> B);
+                        w[0][r] = live ? (w1[0][r] & ((1u << B) - 1u)) : PAY_SENTINEL;
+                        w[1][r] = live ? (uint32_t)tk : 0xFFFFFFFFu;
+                        w[2][r] = live ? (uint32_t)(tk >> 32) : 0xFFFFFFFFu;
+                    }
+                } else
+#endif
                 if (((gmax - gmin) >> (64 - B)) == 0) {
                     uint32_t w2[2][EPT];
 #pragma unroll
