@@ -70,6 +70,7 @@ void launch(int grid, int block, Kernel k) {
     Cta& c = cta();
     c.n_threads = block;
     for (int b = 0; b < grid; ++b) {
+        std::memset(c.dyn_smem, 0xCD, sizeof c.dyn_smem);      // a CTA must not rely on what a previous one left behind
         pthread_barrier_init(&c.cta_bar, nullptr, (unsigned)block);
         for (int w = 0; w < (block + 31) / 32; ++w)
             pthread_barrier_init(&c.warp_bar[w], nullptr, (unsigned)std::min(32, block - 32 * w));
