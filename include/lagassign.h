@@ -135,6 +135,11 @@ typedef struct lagassign_stats {
                                     * shape (topic_off, topic_cset, consumer sets, flags) of the previous
                                     * one and only lags / ids / offsets differ (default 1) */
 
+#define LAGASSIGN_OPT_EXACT_RANK 6 /* device-wide radix path: 1 = rank with the exact ballot form from the start instead
+                                    * of the fast atomic form + certificate (default 0, or 1 when the probe at
+                                    * lagassign_create finds that the device does not serve same-address shared
+                                    * atomics of one instruction in lane order); see csrc/radix.cuh section 4d */
+
 int  lagassign_abi_version(void);
 
 /* Number of CUDA devices visible; 0 devices is not an error here. */
@@ -166,7 +171,8 @@ int  lagassign_assign_batch(lagassign_ctx *ctx, const lagassign_batch *in,
 /* Split form. upload: validate, plan (bin topics by size), copy inputs to HBM.
  * execute: enqueue the kernels (asynchronous, except that batches with topics of
  * more than 4096 partitions wait once for the digit histograms to decide which radix
- * passes to launch). download: wait and copy results to host. execute may be repeated
+ * passes to launch and once, at the end, for the certificate of the sort).
+ * download: wait and copy results to host. execute may be repeated
  * on the same uploaded batch. */
 int  lagassign_upload(lagassign_ctx *ctx, const lagassign_batch *in);
 int  lagassign_upload_offsets(lagassign_ctx *ctx, const lagassign_batch *in,

@@ -30,6 +30,7 @@ OPT_PROFILE = 2
 OPT_GROUP = 3
 OPT_PIPE_CHUNK = 4
 OPT_PLAN_CACHE = 5
+OPT_EXACT_RANK = 6
 
 
 class LagAssignError(RuntimeError):

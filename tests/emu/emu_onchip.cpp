@@ -45,12 +45,6 @@ extern "C" int emu_assign_onchip(int64_t n_topics, const int64_t* topic_off, con
     if (!l_warp.empty()) {
         const int n = (int)l_warp.size();
         const int grid = (n + SMALL_WARPS - 1) / SMALL_WARPS;
-#ifdef LAGASSIGN_WARP_GROUPS
-        if (partition == nullptr && out_total == nullptr) {
-            const int warps = (n + GRP_TOPICS - 1) / GRP_TOPICS;
-            emu::launch((warps + SMALL_WARPS - 1) / SMALL_WARPS, SMALL_WARPS * 32, [&] { k_warp_topics_grouped<true>(b, l_warp.data(), n); });
-        } else
-#endif
         if (partition == nullptr && out_total == nullptr)
             emu::launch(grid, SMALL_WARPS * 32, [&] { k_warp_topics<true>(b, l_warp.data(), n); });
         else
@@ -63,13 +57,4 @@ extern "C" int emu_assign_onchip(int64_t n_topics, const int64_t* topic_off, con
     run_cta_class<16>(b, l_cta[3]);
     for (auto& l : l_cta) ran += (int)l.size();
     return ran;
-}
-
-// how many warps of the experimental grouped kernel took its fast path so far (0 when it is not compiled in)
-extern "C" int emu_grouped_fast_warps_count() {
-#ifdef LAGASSIGN_WARP_GROUPS
-    return emu_grouped_fast_warps;
-#else
-    return 0;
-#endif
 }

@@ -52,18 +52,30 @@ extern "C" int emu_assign_big(int64_t n_topics, const int64_t* topic_off, const 
         }
         n_segs += nseg;
         if (P > C) l_fill.push_back(b);
-        boff += P; tiles += nt;
+        boff += (P + RT_BUF_ALIGN - 1) / RT_BUF_ALIGN * RT_BUF_ALIGN; tiles += nt;
     }
     const int B = (int)bt_topic.size();
     if (B == 0) return 0;
     static_assert(sizeof(TileDesc) == 32, "tile descriptors are read as two int4");
 
-    std::vector<uint64_t> keyA((size_t)boff), keyB((size_t)boff);
-    std::vector<uint32_t> payA((size_t)boff), payB((size_t)boff);
+    // (the product's device buffers carry allocation slack; bulk copies round sizes up to 16 bytes)
+    std::vector<uint64_t> keyA((size_t)boff + 4), keyB((size_t)boff + 4);
+    std::vector<uint32_t> payA((size_t)boff + 4), payB((size_t)boff + 4);
+    std::vector<uint8_t> digbuf((size_t)boff + 16, 0xEE);
+    // the caller's lag array, in a 16-byte aligned copy with slack at both ends like the product's device copy;
+    // `lag_shift` (0 or 1 element) makes the emulated device pointer 16-byte aligned or not
+    const int64_t n_total = topic_off[n_topics];
+    std::vector<int64_t> lag_store((size_t)n_total + 8, 0);
+    const int lag_shift = (int)(n_total & 1);
+    int64_t* lag_base = lag_store.data() + 2;
+    if ((reinterpret_cast<uintptr_t>(lag_base) & 15u) != 0) ++lag_base;          // 16-byte aligned
+    lag_base += lag_shift;                                                       // or deliberately only 8-byte aligned
+    std::copy(lag, lag + n_total, lag_base);
+    lag = lag_base;
     std::vector<uint32_t> ghist((size_t)B * N_PASS * 256, 0), gbase((size_t)B * N_PASS * 256, 0);
-    std::vector<int8_t> sel((size_t)B * (2 * N_PASS + 2), 0);
+    std::vector<int8_t> sel((size_t)B * (3 * N_PASS + 2), 0);
     std::vector<int32_t> need_tie((size_t)B, 0);
-    std::vector<uint32_t> tile_hist((size_t)tiles * 256, 0), seg_total((size_t)n_segs * 256, 0), ticket(2 * N_PASS + 1, 0);
+    std::vector<uint32_t> tile_hist((size_t)tiles * 256, 0), seg_total((size_t)n_segs * 256, 0), ticket(RT_TICKET_WORDS, 0);
 
     BigTopics bt{};
     bt.n_big = B; bt.n_tiles = (int)tiles;
@@ -73,11 +85,14 @@ extern "C" int emu_assign_big(int64_t n_topics, const int64_t* topic_off, const 
     bt.keyA = keyA.data(); bt.keyB = keyB.data(); bt.payA = payA.data(); bt.payB = payB.data();
     bt.ghist = ghist.data(); bt.gbase = gbase.data();
     bt.sel_src = sel.data(); bt.sel_dst = sel.data() + (size_t)B * N_PASS;
-    bt.sel_final = sel.data() + (size_t)B * N_PASS * 2; bt.all_equal = sel.data() + (size_t)B * (N_PASS * 2 + 1);
+    bt.nxt_pass = sel.data() + (size_t)B * N_PASS * 2;
+    bt.sel_final = sel.data() + (size_t)B * N_PASS * 3; bt.all_equal = sel.data() + (size_t)B * (N_PASS * 3 + 1);
+    bt.dig = digbuf.data();
     bt.need_tie = need_tie.data(); bt.tile_hist = tile_hist.data();
     bt.seg0 = bt_seg0.data(); bt.seg_bt = seg_bt.data(); bt.n_segs = n_segs; bt.seg_total = seg_total.data();
     bt.ticket = ticket.data(); bt.passes_run = reinterpret_cast<int32_t*>(ticket.data() + N_PASS);
     bt.pass_any = ticket.data() + N_PASS + 1;
+    bt.verify_fail = ticket.data() + 2 * N_PASS + 1;
 
     DevBatch db{};
     db.topic_off = topic_off; db.lag = lag; db.part = partition; db.topic_cset = topic_cset;
@@ -86,6 +101,10 @@ extern "C" int emu_assign_big(int64_t n_topics, const int64_t* topic_off, const 
 
     // the launch sequence of lagassign_execute() for the device bin (launch_big.cu for the grid sizes)
     const bool has_part = partition != nullptr;
+    // The emulator's "lanes" are free-running host threads, so the fast ranking (one atomic per element, relying on
+    // lane-ordered service) is NOT stable here: the exact form is the default, and EMU_FAST_RANK=1 is used to check
+    // that the certificate (k_big_verify) catches what then goes wrong.
+    const bool exact = getenv("EMU_FAST_RANK") == nullptr;
     const int first_pass = has_part ? 0 : N_TIE_PASS;
     const int n_tiles = (int)tiles;
     if (has_part) launch(std::min(n_tiles, sms * 8), 256, [&] { k_big_order_check(bt, partition); });
@@ -98,9 +117,11 @@ extern "C" int emu_assign_big(int64_t n_topics, const int64_t* topic_off, const 
         else launch(std::min(n_tiles, sms * 8), RT_THREADS, [&] { k_big_tile_hist<false>(bt, p, lag, nullptr); });
         launch(n_segs, 256, [&] { k_big_seg_scan(bt, p); });
         launch(B, 256, [&] { k_big_topic_scan(bt, p); });
-        if (has_part) launch(std::min(n_tiles, sms * 2), RT_THREADS, [&] { k_big_scatter<true>(bt, p, lag, partition); });
-        else launch(std::min(n_tiles, sms * 2), RT_THREADS, [&] { k_big_scatter<false>(bt, p, lag, nullptr); });
+        if (has_part) launch(std::min(n_tiles, sms * 2), SC_THREADS, [&] { (exact ? k_big_scatter<true, true>(bt, p, lag, partition) : k_big_scatter<true, false>(bt, p, lag, partition)); });
+        else launch(std::min(n_tiles, sms * 2), SC_THREADS, [&] { (exact ? k_big_scatter<false, true>(bt, p, lag, nullptr) : k_big_scatter<false, false>(bt, p, lag, nullptr)); });
     }
+    launch(std::min(n_tiles, sms * 8), 256, [&] { k_big_verify(bt, partition); });
+    if (*bt.verify_fail != 0) return -2;      // the certificate of the sort failed
     launch(std::min(n_tiles, sms * 8), 256, [&] {
         k_big_finalize(bt, lag, partition, topic_cset, cset_off, cset_rank, tc_off, out_partition, out_consumer_rank, out_total, out_count);
     });

@@ -411,6 +411,23 @@ def test_config5_full_closed_form(pkg):
     assert st["radix_passes_run"] == 0 and st["topics_device"] > 0
 
 
+def _all_threads():
+    return max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+
+
+@pytest.mark.parametrize("n,totals", [(4, False), (5, True), (6, False)])
+def test_config_full_size_vs_oracle_every_topic(pkg, n, totals):
+    """Full-size BASELINE configs 4 and 5 and the sort-only variant (config 6, 64 x 2^20 keys through all
+    eight radix passes): EVERY topic compared bit-exactly with the oracle (round formulation on all host
+    threads), not a sample. Totals are left out where they would be 100 000 x 4096 entries."""
+    b, _ = baseline_config(n)
+    with pkg.FlatAssignor(0, want_totals=totals) as f:
+        got = f.assign_batch(*args_of(b))
+    exp = oracle.assign_batch(*args_of(b), mode=oracle.ROUNDS, want_totals=totals, threads=_all_threads())
+    for k in KEYS if totals else KEYS[:2]:
+        assert np.array_equal(got[k], exp[k]), k
+
+
 # ---- remaining C-ABI entry points -------------------------------------------------------------------
 
 def test_profile_option_and_stats(pkg):

@@ -225,3 +225,31 @@ def test_radix_path_skips_constant_digits(emu_radix):
     got, passes = run_emulated_radix(emu_radix, b, False, 4096)
     assert passes == 2
     check(emu_radix, b, False, radix_min_p=4096)
+
+
+def test_radix_certificate_catches_unordered_atomics(emu_radix, monkeypatch):
+    """The fast ranking of k_big_scatter (one shared-memory atomic per element) is stable only if the lanes of
+    one instruction are served in lane order. The emulator's lanes are free-running host threads, so with
+    EMU_FAST_RANK=1 that order is arbitrary: k_big_verify (the certificate lagassign_execute() reads before it
+    trusts the sort) must then either report the failure (-2) or the result must be exact anyway."""
+    monkeypatch.setenv("EMU_FAST_RANK", "1")
+    rng = np.random.default_rng(77)
+    caught = 0
+    for _ in range(4):
+        b = random_flat(rng, T=3, pmin=3000, pmax=9000, C=40, lag_kind="dups", n_sets=1, full_sets=True)
+        T = len(b["topic_off"]) - 1
+        N = int(b["topic_off"][-1])
+        C = (b["cset_off"][1:] - b["cset_off"][:-1])[b["topic_cset"]]
+        tc_off = np.concatenate([[0], np.cumsum(C)]).astype(np.int64)
+        # two executed passes are needed for instability to matter: lags 0..3 in the low byte, 0..3 in the next
+        b["lag"] = (b["lag"] + 256 * rng.integers(0, 4, size=N)).astype(np.int64)
+        op = np.full(N, -7, np.int32); oc = np.full(N, -7, np.int32)
+        n = emu_radix.emu_assign_big(T, _ptr(b["topic_off"]), _ptr(b["lag"]), None, _ptr(b["topic_cset"]),
+                                     _ptr(b["cset_off"]), _ptr(b["cset_rank"]), _ptr(tc_off), _ptr(op), _ptr(oc), None, None,
+                                     2000, 2, None)
+        if n == -2:
+            caught += 1
+            continue
+        exp = oracle.assign_batch(*args_of(b), threads=4)
+        assert np.array_equal(op, exp["out_partition"]) and np.array_equal(oc, exp["out_consumer_rank"])
+    assert caught > 0, "host threads never reordered same-address atomics?"
