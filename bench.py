@@ -53,6 +53,24 @@ def algorithmic_bytes(batch) -> int:
     return N * per + T * 12
 
 
+def workload_config(batch, desc, cfg, world):
+    """The `config` object of the JSON line: the same for both arms (a function of the workload and N only)."""
+    from kafka_lag_based_assignor_b200.distributed import shard_batch, shard_bounds
+    bounds = shard_bounds(batch["topic_off"], world)
+    local_bytes = max(algorithmic_bytes(shard_batch(batch, lo, hi)) for lo, hi in bounds)
+    flush_needed = local_bytes < 2 * L2_BYTES
+    return {"workload": desc, "config": cfg,
+            "parallelism": f"topic-sharded x{world}" if world > 1 else "single GPU",
+            "l2": "L2 flushed between timed steps (256 MiB write)" if flush_needed else "inputs larger than L2 (126 MB)",
+            "collective": ("narrow result form (1-4 B partition id, 0-4 B consumer per partition) all-gathered with NCCL and "
+                           "widened, inside the timed step") if world > 1 else "none",
+            "partitions_per_step": int(batch["topic_off"][-1])}, flush_needed
+
+
+# --impl reference: topics per step, fixed per config (the same work on every box)
+REFERENCE_TOPICS_PER_STEP = {2: 1, 3: 10000, 4: 4096, 5: 64, 6: 1, 7: 20000}
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -148,12 +166,8 @@ def run_reference(args, batch, desc):
     threads = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     off = batch["topic_off"]
     T = len(off) - 1
-    # one step = a bounded sample of topics, sized for ~2 s
-    probe = max(1, min(T, 64 * threads))
-    t0 = time.perf_counter()
-    oracle.assign_batch(*args_of(batch), mode=oracle.LITERAL, threads=threads, topic_lo=0, topic_hi=probe)
-    dt = max(time.perf_counter() - t0, 1e-6)
-    per_step = int(min(T, max(probe, probe * 2.0 / dt)))
+    # one step = a FIXED prefix of the workload's topics (the same work on every box)
+    per_step = int(min(T, REFERENCE_TOPICS_PER_STEP[args.config]))
     n = int(off[per_step])
     for _ in range(args.warmup):
         oracle.assign_batch(*args_of(batch), mode=oracle.LITERAL, threads=threads, topic_lo=0, topic_hi=per_step)
@@ -168,10 +182,9 @@ def run_reference(args, batch, desc):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64",
         "data": "synthetic",
-        "config": {"workload": desc, "config": args.config,
-                   "note": "reference algorithm (Main:166-277, O(P log P + P*C)) restated in C (oracle/oracle.c, "
-                           "literal mode), topics spread over all host threads; the JVM original cannot run in "
-                           "this image"},
+        "config": workload_config(batch, desc, args.config, args.gpus)[0],
+        "reference_note": "reference algorithm (Main:166-277, O(P log P + P*C)) restated in C (oracle/oracle.c, literal "
+                          "mode), topics spread over all host threads; the JVM original cannot run in this image",
         "cpu_baseline": {"value": value, "unit": "assignments/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "assignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -228,8 +241,7 @@ def main():
     sh = ShardedAssignor(f, rank, world)
     sh.upload(batch)
     local_alg_bytes = algorithmic_bytes(sh.local)
-    working_set = local_alg_bytes
-    flush_needed = working_set < 2 * L2_BYTES
+    config_obj, flush_needed = workload_config(batch, desc, args.config, world)
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda") if flush_needed else None
 
     def flush():
@@ -408,7 +420,7 @@ def main():
         achieved = (alg / (per_launch_ms * 1e-3) / 1e9) if alg else None
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if world == 1 and os.path.exists(tp):     # measured at N = 1 (ncu is never run on a multi-rank command)
             try:
                 traffic = json.load(open(tp)).get(f"config{args.config}", {}).get(dom_name)
             except Exception:
@@ -417,10 +429,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "assignments/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": desc, "config": args.config, "parallelism": f"topic-sharded x{world}" if world > 1 else "single GPU",
-                       "l2": "L2 flushed between timed steps (256 MiB write)" if flush_needed else "inputs larger than L2 (126 MB)",
-                       "collective": "NCCL all-gather of out_partition+out_consumer_rank inside the timed step" if world > 1 else "none",
-                       "partitions_per_step": N_total},
+            "config": config_obj,
             "clocks": clocks,
             "e2e": {"value": N_total * e2e_steps / (t_e2e_ms * 1e-3), "unit": "assignments/s",
                     "h2d_bytes_per_step": st2["h2d_bytes"], "d2h_bytes_per_step": st2["d2h_bytes"],

@@ -62,7 +62,7 @@
 extern "C" {
 #endif
 
-#define LAGASSIGN_ABI_VERSION 1
+#define LAGASSIGN_ABI_VERSION 2
 
 #define LAGASSIGN_OK               0
 #define LAGASSIGN_ERR_ARG         -1  /* NULL pointer, non-monotone offsets, unsorted set ... */
@@ -156,6 +156,18 @@ int  lagassign_create(lagassign_ctx **ctx, int device);
  * sees the kernels. */
 int  lagassign_create_on_stream(lagassign_ctx **ctx, int device, void *cuda_stream);
 
+/* One context over SEVERAL devices of this process ("topics shard naturally across the 8 GPUs"):
+ * the batch of lagassign_assign_batch / upload is cut into contiguous topic ranges balanced by partition count,
+ * one per device; every device runs the whole path on its range concurrently (its own stream and PCIe link) and
+ * copies its results straight into the caller's host arrays at the range's offset. No collective: the host is
+ * the gather point, which is where the JVM leader that calls Main:149 needs the map. A topic is never split.
+ * Not available on such a context: lagassign_bind_device_outputs, lagassign_download_lags, LAGASSIGN_OPT_GROUP,
+ * per-kernel profiles (lagassign_profile_count reports 0 kinds). A device may be listed more than once (several
+ * streams on one GPU; the tests use it to exercise the split on a one-GPU box). */
+int  lagassign_create_multi(lagassign_ctx **ctx, const int *devices, int n_devices);
+/* Number of devices behind a context (1 for lagassign_create / lagassign_create_on_stream). */
+int  lagassign_shard_count(const lagassign_ctx *ctx, int *n_out);
+
 void lagassign_destroy(lagassign_ctx *ctx);
 
 /* Last error text of this context (or of the calling thread when ctx is NULL). */
@@ -186,6 +198,27 @@ int  lagassign_download(lagassign_ctx *ctx, const lagassign_result *out);
  * buffer). Pass NULLs to go back to the context's own buffers. */
 int  lagassign_bind_device_outputs(lagassign_ctx *ctx, int32_t *d_out_partition,
                                    int32_t *d_out_consumer_rank);
+
+/* Result exchange for the one-process-per-GPU arrangement (topics sharded over ranks, every rank finally holding
+ * the whole map as two int32 arrays: what the reference returns at Main:187). Only the narrow form of a rank's
+ * results crosses NVLink: partition ids in part_width = 1 / 2 / 4 bytes (every id of the batch below 256 / 65536 /
+ * any), consumers in cons_width = 2 / 4 bytes, or cons_width = 0 when every topic of the batch has P <= C or no
+ * subscriber — then the consumer of sorted partition k is the k-th member of the topic's set (SURVEY 0 fact 5;
+ * Main:240-263 on all-zero totals) and every rank writes it from the replicated table.
+ *   pack:   this rank's int32 results (n entries, device pointers) -> its slot (slot_bytes(n, ...) bytes, 16-aligned)
+ *   gather: the caller's collective moves the slots (slots of slot_bytes(max n over ranks) each, rank order)
+ *   unpack: all slots -> out_partition / out_consumer_rank of the WHOLE batch, one warp per topic; needs the whole
+ *           batch's topic_off / topic_cset / consumer sets and the first topic of every rank (world + 1 entries)
+ *           in device memory.
+ * All pointers are DEVICE pointers; work is enqueued on cuda_stream. */
+int64_t lagassign_exchange_slot_bytes(int64_t n, int part_width, int cons_width);
+int  lagassign_exchange_pack(void *cuda_stream, int64_t n, const int32_t *d_part, const int32_t *d_cons,
+                             int part_width, int cons_width, void *d_slot);
+int  lagassign_exchange_unpack(void *cuda_stream, int64_t n_topics, const int64_t *d_topic_off,
+                               const int32_t *d_topic_cset, const int64_t *d_cset_off, const int32_t *d_cset_rank,
+                               const int64_t *d_shard_first_topic, int world, const void *d_slots,
+                               int64_t slot_bytes, int part_width, int cons_width,
+                               int32_t *d_out_partition, int32_t *d_out_consumer_rank);
 
 /* Device copy of the computed lags (valid after execute(); for tests of the
  * fused lag computation). */

@@ -92,6 +92,8 @@ def load_library() -> ctypes.CDLL:
     L.lagassign_device_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
     L.lagassign_create.argtypes = [ctypes.POINTER(vp), i32]
     L.lagassign_create_on_stream.argtypes = [ctypes.POINTER(vp), i32, vp]
+    L.lagassign_create_multi.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int), i32]
+    L.lagassign_shard_count.argtypes = [vp, ctypes.POINTER(ctypes.c_int)]
     L.lagassign_destroy.argtypes = [vp]
     L.lagassign_destroy.restype = None
     L.lagassign_last_error.argtypes = [vp]
@@ -111,14 +113,20 @@ def load_library() -> ctypes.CDLL:
     L.lagassign_profile_count.argtypes = [vp, ctypes.POINTER(ctypes.c_int)]
     L.lagassign_profile_entry.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_char_p),
                                           ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]
+    L.lagassign_exchange_slot_bytes.argtypes = [i64, i32, i32]
+    L.lagassign_exchange_slot_bytes.restype = i64
+    L.lagassign_exchange_pack.argtypes = [vp, i64, vp, vp, i32, i32, vp]
+    L.lagassign_exchange_unpack.argtypes = [vp, i64, vp, vp, vp, vp, vp, i32, vp, i64, i32, i32, vp, vp]
     L.lagassign_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
     L.lagassign_host_free.argtypes = [vp]
-    for name in ("lagassign_device_count", "lagassign_create", "lagassign_create_on_stream",
+    for name in ("lagassign_device_count", "lagassign_create", "lagassign_create_on_stream", "lagassign_create_multi",
+                 "lagassign_shard_count",
                  "lagassign_set_option", "lagassign_assign_batch", "lagassign_upload",
                  "lagassign_upload_offsets", "lagassign_execute", "lagassign_sync", "lagassign_download",
                  "lagassign_bind_device_outputs", "lagassign_download_lags", "lagassign_get_stats",
                  "lagassign_profile_count", "lagassign_profile_entry",
                  "lagassign_group_sizes", "lagassign_download_grouping",
+                 "lagassign_exchange_pack", "lagassign_exchange_unpack",
                  "lagassign_host_alloc", "lagassign_host_free"):
         getattr(L, name).restype = i32
     _lib = L
@@ -138,43 +146,45 @@ def _arr(a, dtype, name):
     return out
 
 
-class _PinnedOwner:
-    def __init__(self, ptr):
-        self.ptr = ptr
-
-    def __del__(self):
-        try:
-            load_library().lagassign_host_free(self.ptr)
-        except Exception:
-            pass
+def _free_pinned(ptr):
+    try:
+        load_library().lagassign_host_free(ctypes.c_void_p(ptr))
+    except Exception:
+        pass
 
 
 def pinned_empty(n: int, dtype) -> np.ndarray:
-    """numpy array over pinned host memory from lagassign_host_alloc()."""
+    """numpy array over pinned host memory from lagassign_host_alloc(); freed with the array."""
+    import weakref
     dtype = np.dtype(dtype)
     L = load_library()
     p = ctypes.c_void_p()
-    rc = L.lagassign_host_alloc(ctypes.byref(p), max(1, n) * dtype.itemsize)
+    nbytes = max(1, n) * dtype.itemsize
+    rc = L.lagassign_host_alloc(ctypes.byref(p), nbytes)
     if rc != 0:
         raise LagAssignError(rc, L.lagassign_last_error(None).decode())
-    buf = (ctypes.c_char * (max(1, n) * dtype.itemsize)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=n)
-    owner = _PinnedOwner(p.value)
-    _PINNED[arr.ctypes.data] = owner
-    return arr
+    buf = (ctypes.c_char * nbytes).from_address(p.value)
+    weakref.finalize(buf, _free_pinned, p.value)      # numpy arrays over `buf` hold a reference to it (their base)
+    return np.frombuffer(buf, dtype=dtype, count=n)
 
 
-_PINNED = {}
 
 
 class FlatAssignor:
     """One lagassign context (one GPU, one stream). Flat-array interface, see
     include/lagassign.h for the layout."""
 
-    def __init__(self, device: int = 0, stream: Optional[int] = None, want_totals: bool = False):
+    def __init__(self, device=0, stream: Optional[int] = None, want_totals: bool = False):
+        """device: one device index, or a list of distinct indices for a multi-device context
+        (lagassign_create_multi: topics are split over the devices, results land in the caller's arrays)."""
         self._L = load_library()
         self._ctx = ctypes.c_void_p()
-        if stream is None:
+        if isinstance(device, (list, tuple)):
+            if stream is not None:
+                raise ValueError("a multi-device context owns its streams")
+            devs = (ctypes.c_int * len(device))(*[int(d) for d in device])
+            rc = self._L.lagassign_create_multi(ctypes.byref(self._ctx), devs, len(device))
+        elif stream is None:
             rc = self._L.lagassign_create(ctypes.byref(self._ctx), device)
         else:
             rc = self._L.lagassign_create_on_stream(ctypes.byref(self._ctx), device, ctypes.c_void_p(stream))

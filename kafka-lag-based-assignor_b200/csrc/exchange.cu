@@ -1,0 +1,135 @@
+// exchange.cu — compact form of a rank's results for the multi-GPU gather (include/lagassign.h, "result exchange").
+//
+// With topics sharded over ranks (one process per GPU) every rank finally holds the whole assignment map as two
+// int32 arrays. What has to cross NVLink is much less than those 8 bytes per partition:
+//   * partition ids fit 1 or 2 bytes whenever every topic has at most 256 / 65536 partitions;
+//   * the consumer of a topic with P <= C is not information at all: the single partial round on all-zero totals
+//     gives sorted partition k to the k-th member of the topic's set (Main:240-263), which every
+//     rank can write from the replicated consumer-set table.
+// k_exchange_pack narrows a rank's own results into its slot of the gather buffer; after the all-gather
+// k_exchange_unpack widens every slot into the final arrays, one warp per topic, deriving the consumers where it can.
+#include "../../include/lagassign.h"
+
+#include <algorithm>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace {
+
+template <int W> struct Narrow;
+template <> struct Narrow<1> { using type = uint8_t; };
+template <> struct Narrow<2> { using type = uint16_t; };
+template <> struct Narrow<4> { using type = uint32_t; };
+
+template <int PW, int CW>
+__global__ void __launch_bounds__(256)
+k_exchange_pack(int64_t n, const int32_t* __restrict__ part, const int32_t* __restrict__ cons, uint8_t* __restrict__ dst) {
+    using PT = typename Narrow<PW>::type;
+    PT* dp = reinterpret_cast<PT*>(dst);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        dp[e] = (PT)(uint32_t)part[e];
+        if constexpr (CW != 0) {
+            using CT = typename Narrow<CW>::type;
+            CT* dc = reinterpret_cast<CT*>(dst + ((n * PW + 15) & ~(int64_t)15));
+            dc[e] = (CT)(uint32_t)cons[e];        // -1 (no subscriber) becomes all ones
+        }
+    }
+}
+
+struct UnpackArgs {
+    int64_t n_topics;
+    const int64_t* topic_off;    // [T+1] of the WHOLE batch
+    const int32_t* topic_cset;   // [T]
+    const int64_t* cset_off;     // [S+1]
+    const int32_t* cset_rank;
+    const int64_t* shard_first_topic;   // [world+1] topic ranges of the ranks
+    int world;
+    int64_t slot_bytes;          // distance between the ranks' slots in `src`
+    const uint8_t* src;          // gathered slots
+    int32_t* out_part;           // [N]
+    int32_t* out_cons;           // [N]
+};
+
+template <int PW, int CW>
+__global__ void __launch_bounds__(256)
+k_exchange_unpack(UnpackArgs a) {
+    using PT = typename Narrow<PW>::type;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t t = warp0; t < a.n_topics; t += n_warps) {
+        // rank that computed topic t (world <= 8..64: a linear scan of a register-resident table is enough)
+        int r = 0;
+        while (r + 1 < a.world && t >= a.shard_first_topic[r + 1]) ++r;
+        const int64_t off = a.topic_off[t], P = a.topic_off[t + 1] - off;
+        const int64_t start = a.topic_off[a.shard_first_topic[r]];                 // first partition of that rank
+        const int64_t n_r = a.topic_off[a.shard_first_topic[r + 1]] - start;
+        const uint8_t* slot = a.src + (int64_t)r * a.slot_bytes;
+        const PT* sp = reinterpret_cast<const PT*>(slot) + (off - start);
+        const int s = a.topic_cset[t];
+        const int64_t coff = a.cset_off[s], C = a.cset_off[s + 1] - coff;
+        if constexpr (CW == 0) {
+            // every topic of the batch has P <= C (or no subscriber): consumers from the table
+            for (int64_t k = lane; k < P; k += 32) {
+                a.out_part[off + k] = (int32_t)(uint32_t)sp[k];
+                a.out_cons[off + k] = C > 0 ? a.cset_rank[coff + k] : -1;
+            }
+        } else {
+            using CT = typename Narrow<CW>::type;
+            const CT* sc = reinterpret_cast<const CT*>(slot + ((n_r * PW + 15) & ~(int64_t)15)) + (off - start);
+            for (int64_t k = lane; k < P; k += 32) {
+                a.out_part[off + k] = (int32_t)(uint32_t)sp[k];
+                const CT c = sc[k];
+                a.out_cons[off + k] = (c == (CT)~(CT)0) ? -1 : (int32_t)(uint32_t)c;
+            }
+        }
+    }
+}
+
+thread_local const char* g_exch_err = "";
+
+int exch_fail(const char* m) { g_exch_err = m; return LAGASSIGN_ERR_ARG; }
+
+}  // namespace
+
+extern "C" {
+
+int64_t lagassign_exchange_slot_bytes(int64_t n, int part_width, int cons_width) {
+    if (n < 0) return -1;
+    return ((n * part_width + 15) & ~(int64_t)15) + ((n * cons_width + 15) & ~(int64_t)15);
+}
+
+int lagassign_exchange_pack(void* cuda_stream, int64_t n, const int32_t* d_part, const int32_t* d_cons,
+                            int part_width, int cons_width, void* d_slot) {
+    if (n < 0 || !d_slot || (n > 0 && (!d_part || (cons_width != 0 && !d_cons)))) return exch_fail("NULL argument");
+    if (n == 0) return LAGASSIGN_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    uint8_t* dst = static_cast<uint8_t*>(d_slot);
+#define PACK_CASE(PW, CW) if (part_width == PW && cons_width == CW) { k_exchange_pack<PW, CW><<<grid, 256, 0, st>>>(n, d_part, d_cons, dst); } else
+    PACK_CASE(1, 0) PACK_CASE(2, 0) PACK_CASE(4, 0) PACK_CASE(1, 2) PACK_CASE(2, 2) PACK_CASE(4, 2)
+    PACK_CASE(1, 4) PACK_CASE(2, 4) PACK_CASE(4, 4) { return exch_fail("unsupported widths"); }
+#undef PACK_CASE
+    return cudaGetLastError() == cudaSuccess ? LAGASSIGN_OK : LAGASSIGN_ERR_CUDA;
+}
+
+int lagassign_exchange_unpack(void* cuda_stream, int64_t n_topics, const int64_t* d_topic_off, const int32_t* d_topic_cset,
+                              const int64_t* d_cset_off, const int32_t* d_cset_rank, const int64_t* d_shard_first_topic,
+                              int world, const void* d_slots, int64_t slot_bytes, int part_width, int cons_width,
+                              int32_t* d_out_partition, int32_t* d_out_consumer_rank) {
+    if (n_topics < 0 || world < 1 || !d_topic_off || !d_cset_off || !d_shard_first_topic || !d_slots ||
+        !d_out_partition || !d_out_consumer_rank || (n_topics > 0 && !d_topic_cset))
+        return exch_fail("NULL argument");
+    if (n_topics == 0) return LAGASSIGN_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    UnpackArgs a{n_topics, d_topic_off, d_topic_cset, d_cset_off, d_cset_rank, d_shard_first_topic, world, slot_bytes,
+                 static_cast<const uint8_t*>(d_slots), d_out_partition, d_out_consumer_rank};
+    const int grid = (int)std::min<int64_t>((n_topics + 7) / 8, 148 * 16);
+#define UNPACK_CASE(PW, CW) if (part_width == PW && cons_width == CW) { k_exchange_unpack<PW, CW><<<grid, 256, 0, st>>>(a); } else
+    UNPACK_CASE(1, 0) UNPACK_CASE(2, 0) UNPACK_CASE(4, 0) UNPACK_CASE(1, 2) UNPACK_CASE(2, 2) UNPACK_CASE(4, 2)
+    UNPACK_CASE(1, 4) UNPACK_CASE(2, 4) UNPACK_CASE(4, 4) { return exch_fail("unsupported widths"); }
+#undef UNPACK_CASE
+    return cudaGetLastError() == cudaSuccess ? LAGASSIGN_OK : LAGASSIGN_ERR_CUDA;
+}
+
+}  // extern "C"

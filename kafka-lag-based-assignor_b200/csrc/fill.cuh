@@ -214,6 +214,38 @@ __device__ __forceinline__ void cta_round_fill(int64_t P, int C, int nc, const i
     }
 }
 
+// One CTA, ANY number of consumers: ckey/cidx (nc = pow2 >= C slots) live wherever the caller puts them — the
+// device-wide path hands in a global-memory workspace when a topic has more consumers than fit in shared memory
+// (C > FILL_CTA_MAX_C). Same rounds as above with run-time loops; correct for every shape, not tuned: such
+// topics (tens of thousands of consumers AND even more partitions) are rare.
+template <class LagAt, class PutCons>
+__device__ __forceinline__ void cta_round_fill_any(int64_t P, int64_t C, int64_t nc, const int32_t* __restrict__ cset,
+                                                   uint64_t* ckey, uint32_t* cidx, LagAt lag_at, PutCons put,
+                                                   int64_t* out_total, int32_t* out_count) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int64_t j = tid; j < nc; j += nt) {
+        const bool live = j < C;
+        ckey[j] = live ? TOTAL_KEY_MASK : KEY_SENTINEL;
+        cidx[j] = live ? (uint32_t)j : PAY_SENTINEL;
+    }
+    __syncthreads();
+    for (int64_t base = 0; base < P; base += C) {
+        if (base > 0) cta_bitonic_sort(ckey, cidx, (int)nc);       // starts and ends with a __syncthreads()
+        for (int64_t j = tid; j < C && base + j < P; j += nt) {
+            put(base + j, cset[cidx[j]]);                                                            // Main:264
+            ckey[j] = ((ckey[j] ^ TOTAL_KEY_MASK) + (uint64_t)lag_at(base + j)) ^ TOTAL_KEY_MASK;    // Main:265, wraps
+        }
+    }
+    __syncthreads();
+    if (out_total != nullptr) {
+        const int64_t full = P / C, rem = P % C;
+        for (int64_t j = tid; j < C; j += nt) {
+            out_total[cidx[j]] = (int64_t)(ckey[j] ^ TOTAL_KEY_MASK);
+            out_count[cidx[j]] = (int32_t)(full + (j < rem ? 1 : 0));                                // Main:266
+        }
+    }
+}
+
 // One CTA of NT threads, consumers in REGISTERS (position j = tid*EPT + r, n =
 // NT*EPT >= C): per round one cta_bitonic_sort_regs() and a wrapping add, nothing
 // else touches shared memory. Used for 256 < C <= 4096.

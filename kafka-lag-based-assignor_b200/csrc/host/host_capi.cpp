@@ -55,14 +55,20 @@ const char* lagassign_group_last_error(const lagassign_group* g) { return g ? g-
 
 int lagassign_group_configure(lagassign_group* g, const char* const* keys, const char* const* values, int n) {
     if (!g) return fail(nullptr, LAGASSIGN_ERR_ARG, "group is NULL");
-    std::map<std::string, std::string> cfg;
-    for (int i = 0; i < n; ++i) cfg[keys[i]] = values[i] ? values[i] : "";
+    if (n < 0 || (n > 0 && (!keys || !values))) return fail(g, LAGASSIGN_ERR_ARG, "keys / values is NULL");
     try {
+        std::map<std::string, std::string> cfg;
+        for (int i = 0; i < n; ++i) {
+            if (!keys[i]) return fail(g, LAGASSIGN_ERR_ARG, "config key is NULL");
+            if (values[i]) cfg[keys[i]] = values[i];      // a NULL value is a missing key (Main:107-113 rejects a null group.id)
+        }
         g->assignor->configure(cfg);
+        g->client_id = g->assignor->metadataConsumerProps().at("client.id");
     } catch (const std::invalid_argument& e) {
         return fail(g, LAGASSIGN_ERR_ARG, e.what());
+    } catch (const std::exception& e) {                   // nothing may cross the extern "C" boundary
+        return fail(g, LAGASSIGN_ERR_ARG, e.what());
     }
-    g->client_id = g->assignor->metadataConsumerProps().at("client.id");
     return LAGASSIGN_OK;
 }
 

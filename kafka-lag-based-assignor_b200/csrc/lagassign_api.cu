@@ -13,6 +13,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -99,7 +100,9 @@ struct lagassign_ctx {
     DevBuf d_list_warp, d_list_cta[N_CTA_CLASSES], d_list_none, d_list_fill;
     DevBuf d_bt_topic, d_bt_off, d_bt_P, d_bt_boff, d_bt_tile0, d_bt_seg0, d_tile_bt, d_seg_bt, d_seg_total, d_tile_desc;
     int n_segs = 0;
+    int64_t fill_ws_elems = 0;
     // radix workspaces
+    DevBuf d_fill_ws_off, d_fill_ws_key, d_fill_ws_idx;
     DevBuf d_keyA, d_keyB, d_payA, d_payB, d_dig, d_ghist, d_gbase, d_sel, d_need_tie, d_status, d_ticket;
     // outputs
     DevBuf d_out_part, d_out_cons, d_out_total, d_out_count;
@@ -134,6 +137,12 @@ struct lagassign_ctx {
     DevBuf d_grp_topic, d_grp_part, d_member_start, d_member_off;
 
     lagassign_stats stats{};
+
+    // lagassign_create_multi(): a parent context owns one child context per device and no device state of its own;
+    // topics are split into contiguous ranges, one per child (see the "multi-device" section at the end of this file)
+    std::vector<lagassign_ctx*> shards;
+    struct ShardRange { int64_t t0 = 0, t1 = 0, e0 = 0, e1 = 0, tc0 = 0; std::vector<int64_t> topic_off; };
+    std::vector<ShardRange> shard_ranges;
 };
 
 namespace {
@@ -198,7 +207,7 @@ int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
                       std::vector<int32_t>& bt_topic, std::vector<int64_t>& bt_off, std::vector<int64_t>& bt_P,
                       std::vector<int64_t>& bt_boff, std::vector<int32_t>& bt_tile0, std::vector<int32_t>& tile_bt,
                       std::vector<int32_t>& l_fill, std::vector<int64_t>& tc_off, std::vector<int32_t>& bt_seg0,
-                      std::vector<int32_t>& seg_bt, std::vector<TileDesc>& tile_desc) {
+                      std::vector<int32_t>& seg_bt, std::vector<TileDesc>& tile_desc, std::vector<int64_t>& fill_ws_off) {
     if (!in) return fail(ctx, LAGASSIGN_ERR_ARG, "batch is NULL");
     const int64_t T = in->n_topics, S = in->n_csets;
     if (T < 0 || S < 0) return fail(ctx, LAGASSIGN_ERR_ARG, "negative n_topics / n_csets");
@@ -228,6 +237,7 @@ int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
 
     tc_off.assign((size_t)T + 1, 0);
     ctx->n_segs = 0;
+    ctx->fill_ws_elems = 0;
     int64_t boff = 0, tiles = 0, assigned = 0;
     for (int64_t t = 0; t < T; ++t) {
         const int32_t s = in->topic_cset[t];
@@ -238,10 +248,6 @@ int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
         if (P == 0) continue;
         if (C == 0 && !ctx->sort_only) { l_none.push_back((int32_t)t); continue; }
         assigned += P;
-        if (P > C && C > FILL_CTA_MAX_C)
-            return fail(ctx, LAGASSIGN_ERR_UNSUPPORTED,
-                        "topic %lld: %lld partitions over %lld consumers needs multi-round fill with more than %d consumers",
-                        (long long)t, (long long)P, (long long)C, FILL_CTA_MAX_C);
         if (P <= WARP_MAX_P && !ctx->sort_only) l_warp.push_back((int32_t)t);
         else if (P <= CTA_MAX_P && !ctx->sort_only) l_cta[cta_class_of(P)].push_back((int32_t)t);
         else {
@@ -270,6 +276,15 @@ int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
                 tile_desc.push_back(d);
             }
             if (P > C) l_fill.push_back(b);
+            // more consumers than the on-chip fills hold (and still more partitions): a global workspace of pow2 >= C slots
+            int64_t ws = -1;
+            if (P > C && C > FILL_CTA_MAX_C) {
+                int64_t nc = 1;
+                while (nc < C) nc <<= 1;
+                ws = ctx->fill_ws_elems;
+                ctx->fill_ws_elems += nc;
+            }
+            fill_ws_off.push_back(ws);
             boff += (P + RT_BUF_ALIGN - 1) / RT_BUF_ALIGN * RT_BUF_ALIGN;
             tiles += nt;
         }
@@ -320,6 +335,9 @@ BigTopics make_big(lagassign_ctx* ctx) {
     bt.sel_final = sel + (size_t)ctx->n_big * N_PASS * 3;
     bt.all_equal = sel + (size_t)ctx->n_big * (N_PASS * 3 + 1);
     bt.dig = ctx->d_dig.as<uint8_t>();
+    bt.fill_ws_off = ctx->d_fill_ws_off.as<int64_t>();
+    bt.fill_ws_key = ctx->d_fill_ws_key.as<uint64_t>();
+    bt.fill_ws_idx = ctx->d_fill_ws_idx.as<uint32_t>();
     bt.need_tie = ctx->d_need_tie.as<int32_t>();
     bt.tile_hist = ctx->d_status.as<uint32_t>();
     bt.seg0 = ctx->d_bt_seg0.as<int32_t>();
@@ -352,12 +370,13 @@ bool plan_matches(const lagassign_ctx* ctx, const lagassign_batch* in, bool has_
 
 int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_offsets* offs, bool defer_data = false) {
     if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
+    if (!in) return fail(ctx, LAGASSIGN_ERR_ARG, "batch is NULL");
     ctx->uploaded = ctx->executed = false;
     ctx->stats = lagassign_stats{};
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     std::vector<int32_t> l_warp, l_cta[N_CTA_CLASSES], l_none, bt_topic, bt_tile0, tile_bt, l_fill, bt_seg0, seg_bt;
     std::vector<TileDesc> tile_desc;
-    std::vector<int64_t> bt_off, bt_P, bt_boff, tc_off;
+    std::vector<int64_t> bt_off, bt_P, bt_boff, tc_off, fill_ws_off;
     lagassign_batch tmp;
     if (offs) {
         // lags are produced on the device; planning only needs the shapes
@@ -389,7 +408,7 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
         return LAGASSIGN_OK;
     }
     ctx->plan_key.valid = false;
-    TRY(validate_and_plan(ctx, in, l_warp, l_cta, l_none, bt_topic, bt_off, bt_P, bt_boff, bt_tile0, tile_bt, l_fill, tc_off, bt_seg0, seg_bt, tile_desc));
+    TRY(validate_and_plan(ctx, in, l_warp, l_cta, l_none, bt_topic, bt_off, bt_P, bt_boff, bt_tile0, tile_bt, l_fill, tc_off, bt_seg0, seg_bt, tile_desc, fill_ws_off));
     const int64_t T = ctx->T, N = ctx->N;
     ctx->has_part = in->partition != nullptr;
     ctx->has_offsets = offs != nullptr;
@@ -429,6 +448,7 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
     TRY(upload_vec(ctx, ctx->d_seg_bt, seg_bt.data(), seg_bt.size()));
     TRY(upload_vec(ctx, ctx->d_tile_desc, tile_desc.data(), tile_desc.size()));
     TRY(upload_vec(ctx, ctx->d_tile_bt, tile_bt.data(), tile_bt.size()));
+    TRY(upload_vec(ctx, ctx->d_fill_ws_off, fill_ws_off.data(), fill_ws_off.size()));
 
     // outputs and workspaces
     if (!ctx->sort_only) {
@@ -475,6 +495,8 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
         CUDA_TRY(ctx, ctx->d_gbase.ensure(hb));
         CUDA_TRY(ctx, ctx->d_sel.ensure((size_t)ctx->n_big * (3 * N_PASS + 2)));
         CUDA_TRY(ctx, ctx->d_dig.ensure(nb));
+        CUDA_TRY(ctx, ctx->d_fill_ws_key.ensure(std::max<size_t>((size_t)ctx->fill_ws_elems, 1) * sizeof(uint64_t)));
+        CUDA_TRY(ctx, ctx->d_fill_ws_idx.ensure(std::max<size_t>((size_t)ctx->fill_ws_elems, 1) * sizeof(uint32_t)));
         CUDA_TRY(ctx, ctx->d_need_tie.ensure((size_t)ctx->n_big * sizeof(int32_t)));
         CUDA_TRY(ctx, ctx->d_status.ensure((size_t)ctx->n_tiles * 256 * sizeof(uint32_t)));       // tile_hist
         CUDA_TRY(ctx, ctx->d_seg_total.ensure((size_t)ctx->n_segs * 256 * sizeof(uint32_t)));
@@ -531,7 +553,7 @@ constexpr int64_t PIPE_CHUNK_ELEMS = 3 << 20;    // ~24 MB of lags per chunk
 // into contiguous topic ranges and the three legs (H2D of the lags, kernels, D2H of
 // the results) of successive chunks overlap on three streams. PCIe is full duplex,
 // so the call approaches max(H2D, D2H) instead of their sum.
-int assign_batch_pipelined(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_result* out) {
+int assign_batch_pipelined_impl(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_result* out, std::vector<cudaEvent_t>& tev) {
     if (!ctx->stream_in) {
         CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking));
         CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking));
@@ -565,10 +587,9 @@ int assign_batch_pipelined(lagassign_ctx* ctx, const lagassign_batch* in, const 
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->pipe_events.push_back(e);
     }
-    // LAGASSIGN_TRACE: timing events at the end of every leg of every chunk
-    std::vector<cudaEvent_t> tev;
+    // LAGASSIGN_TRACE: timing events at the end of every leg of every chunk (destroyed by the caller)
     if (ctx->trace) {
-        tev.resize(1 + 3 * (size_t)K);
+        tev.assign(1 + 3 * (size_t)K, nullptr);
         for (auto& e : tev) CUDA_TRY(ctx, cudaEventCreate(&e));
         CUDA_TRY(ctx, cudaEventRecord(tev[0], ctx->stream_in));
     }
@@ -639,7 +660,6 @@ int assign_batch_pipelined(lagassign_ctx* ctx, const lagassign_batch* in, const 
             cudaEventElapsedTime(&d, tev[0], tev[3 + 3 * c]);
             fprintf(stderr, "[lagassign]   %2d (%lld): %.3f / %.3f / %.3f\n", c, (long long)cuts[c], a, k, d);
         }
-        for (auto& e : tev) cudaEventDestroy(e);
     }
     ctx->stats.kernel_launches = launches;
     ctx->uploaded = true;
@@ -647,6 +667,22 @@ int assign_batch_pipelined(lagassign_ctx* ctx, const lagassign_batch* in, const 
     ctx->prof.clear();
     ctx->prof_resolved = true;
     return LAGASSIGN_OK;
+}
+
+int assign_batch_pipelined(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_result* out) {
+    std::vector<cudaEvent_t> tev;
+    const int rc = assign_batch_pipelined_impl(ctx, in, out, tev);
+    if (rc != LAGASSIGN_OK) {
+        // Copies into and out of the CALLER's buffers may still be in flight on the three streams: they must have
+        // ended before the error is returned and the caller is free to release those buffers.
+        if (ctx->stream_in) cudaStreamSynchronize(ctx->stream_in);
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        if (ctx->stream_out) cudaStreamSynchronize(ctx->stream_out);
+        cudaGetLastError();
+    }
+    for (cudaEvent_t e : tev)
+        if (e) cudaEventDestroy(e);
+    return rc;
 }
 
 int configure_kernels(lagassign_ctx* ctx) {
@@ -701,6 +737,13 @@ int create_common(lagassign_ctx** out, int device, void* stream, bool own) {
     return LAGASSIGN_OK;
 }
 
+int multi_set_option(lagassign_ctx* ctx, int option, int64_t value);
+int multi_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_offsets* offs);
+int multi_execute(lagassign_ctx* ctx);
+int multi_sync(lagassign_ctx* ctx);
+int multi_download(lagassign_ctx* ctx, const lagassign_result* out);
+int multi_assign_batch(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_result* out);
+
 }  // namespace
 
 extern "C" {
@@ -724,6 +767,11 @@ int lagassign_create_on_stream(lagassign_ctx** ctx, int device, void* cuda_strea
 
 void lagassign_destroy(lagassign_ctx* ctx) {
     if (!ctx) return;
+    if (!ctx->shards.empty()) {
+        for (lagassign_ctx* c : ctx->shards) lagassign_destroy(c);
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_topic_off, &ctx->d_lag, &ctx->d_part, &ctx->d_topic_cset, &ctx->d_cset_off,
@@ -731,7 +779,7 @@ void lagassign_destroy(lagassign_ctx* ctx) {
                       &ctx->d_hascommitted, &ctx->d_list_warp, &ctx->d_list_cta[0], &ctx->d_list_cta[1], &ctx->d_list_cta[2], &ctx->d_list_cta[3], &ctx->d_list_none,
                       &ctx->d_list_fill, &ctx->d_bt_topic, &ctx->d_bt_off, &ctx->d_bt_P, &ctx->d_bt_boff,
                       &ctx->d_bt_tile0, &ctx->d_tile_bt, &ctx->d_keyA, &ctx->d_keyB, &ctx->d_payA,
-                      &ctx->d_payB, &ctx->d_dig, &ctx->d_ghist, &ctx->d_gbase, &ctx->d_sel, &ctx->d_need_tie,
+                      &ctx->d_payB, &ctx->d_dig, &ctx->d_fill_ws_off, &ctx->d_fill_ws_key, &ctx->d_fill_ws_idx, &ctx->d_ghist, &ctx->d_gbase, &ctx->d_sel, &ctx->d_need_tie,
                       &ctx->d_status, &ctx->d_seg_total, &ctx->d_bt_seg0, &ctx->d_seg_bt, &ctx->d_tile_desc, &ctx->d_ticket, &ctx->d_out_part, &ctx->d_out_cons,
                       &ctx->d_out_total, &ctx->d_out_count};
     for (DevBuf* b : bufs) b->release();
@@ -752,6 +800,7 @@ const char* lagassign_last_error(const lagassign_ctx* ctx) {
 }
 
 int lagassign_set_option(lagassign_ctx* ctx, int option, int64_t value) {
+    if (ctx && !ctx->shards.empty()) return multi_set_option(ctx, option, value);
     if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
     switch (option) {
         case LAGASSIGN_OPT_PROFILE:
@@ -780,14 +829,17 @@ int lagassign_set_option(lagassign_ctx* ctx, int option, int64_t value) {
     }
 }
 
-int lagassign_upload(lagassign_ctx* ctx, const lagassign_batch* in) { return do_upload(ctx, in, nullptr); }
+int lagassign_upload(lagassign_ctx* ctx, const lagassign_batch* in) {
+    if (ctx && !ctx->shards.empty()) return multi_upload(ctx, in, nullptr); return do_upload(ctx, in, nullptr); }
 
 int lagassign_upload_offsets(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_offsets* offs) {
     if (!offs) return fail(ctx, LAGASSIGN_ERR_ARG, "offsets is NULL");
+    if (ctx && !ctx->shards.empty()) return multi_upload(ctx, in, offs);
     return do_upload(ctx, in, offs);
 }
 
 int lagassign_execute(lagassign_ctx* ctx) {
+    if (ctx && !ctx->shards.empty()) return multi_execute(ctx);
     if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
     if (!ctx->uploaded) return fail(ctx, LAGASSIGN_ERR_STATE, "execute() before a successful upload()");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -970,6 +1022,7 @@ int lagassign_execute(lagassign_ctx* ctx) {
 }
 
 int lagassign_sync(lagassign_ctx* ctx) {
+    if (ctx && !ctx->shards.empty()) return multi_sync(ctx);
     if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -977,6 +1030,7 @@ int lagassign_sync(lagassign_ctx* ctx) {
 }
 
 int lagassign_download(lagassign_ctx* ctx, const lagassign_result* out) {
+    if (ctx && !ctx->shards.empty()) return multi_download(ctx, out);
     if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
     if (!out) return fail(ctx, LAGASSIGN_ERR_ARG, "result is NULL");
     if (!ctx->executed) return fail(ctx, LAGASSIGN_ERR_STATE, "download() before execute()");
@@ -1014,6 +1068,7 @@ int lagassign_download(lagassign_ctx* ctx, const lagassign_result* out) {
 }
 
 int lagassign_assign_batch(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_result* out) {
+    if (ctx && !ctx->shards.empty()) return multi_assign_batch(ctx, in, out);
     if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
     if (!out) return fail(ctx, LAGASSIGN_ERR_ARG, "result is NULL");
     const auto t0 = std::chrono::steady_clock::now();
@@ -1034,6 +1089,7 @@ int lagassign_assign_batch(lagassign_ctx* ctx, const lagassign_batch* in, const 
 }
 
 int lagassign_bind_device_outputs(lagassign_ctx* ctx, int32_t* d_out_partition, int32_t* d_out_consumer_rank) {
+    if (ctx && !ctx->shards.empty()) return fail(ctx, LAGASSIGN_ERR_UNSUPPORTED, "not available on a multi-device context");
     if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
     if ((d_out_partition == nullptr) != (d_out_consumer_rank == nullptr))
         return fail(ctx, LAGASSIGN_ERR_ARG, "bind both device outputs or neither");
@@ -1043,6 +1099,7 @@ int lagassign_bind_device_outputs(lagassign_ctx* ctx, int32_t* d_out_partition, 
 }
 
 int lagassign_download_lags(lagassign_ctx* ctx, int64_t* lag_out) {
+    if (ctx && !ctx->shards.empty()) return fail(ctx, LAGASSIGN_ERR_UNSUPPORTED, "not available on a multi-device context");
     if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
     if (!lag_out) return fail(ctx, LAGASSIGN_ERR_ARG, "lag_out is NULL");
     if (!ctx->executed) return fail(ctx, LAGASSIGN_ERR_STATE, "download_lags() before execute()");
@@ -1060,6 +1117,7 @@ int lagassign_group_sizes(const lagassign_ctx* ctx, int64_t* n_members, int64_t*
 }
 
 int lagassign_download_grouping(lagassign_ctx* ctx, const lagassign_grouping* out) {
+    if (ctx && !ctx->shards.empty()) return fail(ctx, LAGASSIGN_ERR_UNSUPPORTED, "not available on a multi-device context");
     if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
     if (!out || !out->member_off) return fail(ctx, LAGASSIGN_ERR_ARG, "grouping output is NULL");
     if (!ctx->want_group) return fail(ctx, LAGASSIGN_ERR_STATE, "LAGASSIGN_OPT_GROUP was not enabled before upload()");
@@ -1100,6 +1158,7 @@ static int resolve_profile(lagassign_ctx* ctx) {
 
 int lagassign_profile_count(lagassign_ctx* ctx, int* n_out) {
     if (!ctx || !n_out) return fail(ctx, LAGASSIGN_ERR_ARG, "ctx or n_out is NULL");
+    if (!ctx->shards.empty()) { *n_out = 0; return LAGASSIGN_OK; }      // per-kernel times belong to one device
     TRY(resolve_profile(ctx));
     *n_out = K_KINDS;
     return LAGASSIGN_OK;
@@ -1130,3 +1189,189 @@ int lagassign_host_free(void* ptr) {
 }
 
 }  // extern "C"
+
+// ---- multi-device contexts (lagassign_create_multi) -------------------------------------------------------
+// One process, several GPUs, no collective: topics are independent (Main:215-225), so a batch is cut into
+// contiguous topic ranges balanced by partition count, one per device; every device runs the whole path on its
+// range — own stream, own PCIe link — and copies its results into the caller's host arrays at the range's
+// offset. The host is the gather point, which is where the reference's caller (Main:149, :152-156) needs the
+// map anyway. A topic is never split (its fill is one sequential chain).
+namespace {
+
+int multi_fail_from(lagassign_ctx* ctx, const std::vector<int>& rcs) {
+    for (size_t i = 0; i < rcs.size(); ++i)
+        if (rcs[i] != LAGASSIGN_OK)
+            return fail(ctx, rcs[i], "device %d: %s", ctx->shards[i]->device, ctx->shards[i]->err.c_str());
+    return LAGASSIGN_OK;
+}
+
+template <class F>
+int multi_for_each(lagassign_ctx* ctx, F f) {
+    const size_t n = ctx->shards.size();
+    std::vector<int> rcs(n, LAGASSIGN_OK);
+    std::vector<std::thread> th;
+    for (size_t i = 1; i < n; ++i) th.emplace_back([&, i] { rcs[i] = f(i); });
+    rcs[0] = f(0);
+    for (auto& t : th) t.join();
+    return multi_fail_from(ctx, rcs);
+}
+
+int multi_split(lagassign_ctx* ctx, const lagassign_batch* in) {
+    if (!in || !in->topic_off || in->n_topics < 0) return fail(ctx, LAGASSIGN_ERR_ARG, "batch / topic_off is NULL");
+    const int64_t T = in->n_topics;
+    for (int64_t t = 0; t < T; ++t)
+        if (in->topic_off[t + 1] < in->topic_off[t]) return fail(ctx, LAGASSIGN_ERR_ARG, "topic_off not monotone at %lld", (long long)t);
+    if (T > 0 && (!in->topic_cset || !in->cset_off)) return fail(ctx, LAGASSIGN_ERR_ARG, "topic_cset / cset_off is NULL");
+    const int64_t N = in->topic_off[T];
+    const size_t n = ctx->shards.size();
+    ctx->shard_ranges.assign(n, lagassign_ctx::ShardRange{});
+    int64_t t_lo = 0, tc = 0;
+    for (size_t i = 0; i < n; ++i) {
+        auto& r = ctx->shard_ranges[i];
+        int64_t t_hi = T;
+        if (i + 1 < n) {
+            const int64_t target = (int64_t)((__int128)N * (int64_t)(i + 1) / (int64_t)n);
+            t_hi = std::lower_bound(in->topic_off, in->topic_off + T + 1, target) - in->topic_off;
+            t_hi = std::min<int64_t>(std::max(t_hi, t_lo), T);
+        }
+        r.t0 = t_lo; r.t1 = t_hi; r.e0 = in->topic_off[t_lo]; r.e1 = in->topic_off[t_hi]; r.tc0 = tc;
+        r.topic_off.resize((size_t)(t_hi - t_lo) + 1);
+        for (int64_t t = t_lo; t <= t_hi; ++t) r.topic_off[(size_t)(t - t_lo)] = in->topic_off[t] - r.e0;
+        for (int64_t t = t_lo; t < t_hi; ++t) {
+            const int32_t s = in->topic_cset[t];
+            if (s < 0 || s >= in->n_csets) return fail(ctx, LAGASSIGN_ERR_ARG, "topic_cset[%lld] out of range", (long long)t);
+            tc += in->cset_off[s + 1] - in->cset_off[s];
+        }
+        t_lo = t_hi;
+    }
+    ctx->T = T; ctx->N = N; ctx->total_tc = tc;
+    return LAGASSIGN_OK;
+}
+
+lagassign_batch shard_batch(const lagassign_ctx* ctx, const lagassign_batch* in, size_t i) {
+    const auto& r = ctx->shard_ranges[i];
+    lagassign_batch b = *in;
+    b.n_topics = r.t1 - r.t0;
+    b.topic_off = r.topic_off.data();
+    b.lag = in->lag ? in->lag + r.e0 : nullptr;
+    b.partition = in->partition ? in->partition + r.e0 : nullptr;
+    b.topic_cset = in->topic_cset ? in->topic_cset + r.t0 : nullptr;
+    return b;
+}
+
+lagassign_result shard_result(const lagassign_ctx* ctx, const lagassign_result* out, size_t i) {
+    const auto& r = ctx->shard_ranges[i];
+    lagassign_result o{};
+    o.out_partition = out->out_partition ? out->out_partition + r.e0 : nullptr;
+    o.out_consumer_rank = out->out_consumer_rank ? out->out_consumer_rank + r.e0 : nullptr;
+    o.out_total = out->out_total ? out->out_total + r.tc0 : nullptr;
+    o.out_count = out->out_count ? out->out_count + r.tc0 : nullptr;
+    return o;
+}
+
+void multi_collect_stats(lagassign_ctx* ctx) {
+    lagassign_stats a{};
+    for (lagassign_ctx* c : ctx->shards) {
+        const lagassign_stats& s = c->stats;
+        a.n_partitions += s.n_partitions; a.n_assigned += s.n_assigned; a.topics_warp += s.topics_warp;
+        a.topics_cta += s.topics_cta; a.topics_device += s.topics_device; a.topics_unassigned += s.topics_unassigned;
+        a.device_sort_elems += s.device_sort_elems; a.radix_passes_run = std::max(a.radix_passes_run, s.radix_passes_run);
+        a.kernel_launches += s.kernel_launches; a.h2d_bytes += s.h2d_bytes; a.d2h_bytes += s.d2h_bytes;
+    }
+    ctx->stats = a;
+}
+
+int multi_set_option(lagassign_ctx* ctx, int option, int64_t value) {
+    if (option == LAGASSIGN_OPT_GROUP && value != 0)
+        return fail(ctx, LAGASSIGN_ERR_UNSUPPORTED, "grouping by member is not available on a multi-device context");
+    for (lagassign_ctx* c : ctx->shards) {
+        const int rc = lagassign_set_option(c, option, value);
+        if (rc != LAGASSIGN_OK) return fail(ctx, rc, "device %d: %s", c->device, c->err.c_str());
+    }
+    if (option == LAGASSIGN_OPT_TOTALS) ctx->want_totals = value != 0;
+    return LAGASSIGN_OK;
+}
+
+int multi_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_offsets* offs) {
+    ctx->uploaded = ctx->executed = false;
+    TRY(multi_split(ctx, in));
+    const int rc = multi_for_each(ctx, [&](size_t i) {
+        const lagassign_batch b = shard_batch(ctx, in, i);
+        if (!offs) return lagassign_upload(ctx->shards[i], &b);
+        const int64_t e0 = ctx->shard_ranges[i].e0;
+        lagassign_offsets o = *offs;
+        if (!o.begin_offset || !o.end_offset || !o.committed || !o.has_committed) return lagassign_upload_offsets(ctx->shards[i], &b, &o);
+        o.begin_offset += e0; o.end_offset += e0; o.committed += e0; o.has_committed += e0;
+        return lagassign_upload_offsets(ctx->shards[i], &b, &o);
+    });
+    multi_collect_stats(ctx);
+    ctx->uploaded = rc == LAGASSIGN_OK;
+    return rc;
+}
+
+int multi_execute(lagassign_ctx* ctx) {
+    if (!ctx->uploaded) return fail(ctx, LAGASSIGN_ERR_STATE, "execute() before a successful upload()");
+    const int rc = multi_for_each(ctx, [&](size_t i) { return lagassign_execute(ctx->shards[i]); });
+    multi_collect_stats(ctx);
+    ctx->executed = rc == LAGASSIGN_OK;
+    return rc;
+}
+
+int multi_sync(lagassign_ctx* ctx) {
+    return multi_for_each(ctx, [&](size_t i) { return lagassign_sync(ctx->shards[i]); });
+}
+
+int multi_download(lagassign_ctx* ctx, const lagassign_result* out) {
+    if (!out) return fail(ctx, LAGASSIGN_ERR_ARG, "result is NULL");
+    if (!ctx->executed) return fail(ctx, LAGASSIGN_ERR_STATE, "download() before execute()");
+    const int rc = multi_for_each(ctx, [&](size_t i) {
+        const lagassign_result o = shard_result(ctx, out, i);
+        return lagassign_download(ctx->shards[i], &o);
+    });
+    multi_collect_stats(ctx);
+    return rc;
+}
+
+int multi_assign_batch(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_result* out) {
+    if (!out) return fail(ctx, LAGASSIGN_ERR_ARG, "result is NULL");
+    ctx->uploaded = ctx->executed = false;
+    TRY(multi_split(ctx, in));
+    const int rc = multi_for_each(ctx, [&](size_t i) {
+        const lagassign_batch b = shard_batch(ctx, in, i);
+        const lagassign_result o = shard_result(ctx, out, i);
+        return lagassign_assign_batch(ctx->shards[i], &b, &o);
+    });
+    multi_collect_stats(ctx);
+    ctx->uploaded = ctx->executed = rc == LAGASSIGN_OK;
+    return rc;
+}
+
+}  // namespace
+
+extern "C" int lagassign_create_multi(lagassign_ctx** ctx, const int* devices, int n_devices) {
+    if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx out-pointer is NULL");
+    *ctx = nullptr;
+    if (!devices || n_devices < 1) return fail(nullptr, LAGASSIGN_ERR_ARG, "devices is NULL or n_devices < 1");
+    lagassign_ctx* parent = new (std::nothrow) lagassign_ctx();
+    if (!parent) return fail(nullptr, LAGASSIGN_ERR_OOM, "out of host memory");
+    parent->device = devices[0];
+    for (int i = 0; i < n_devices; ++i) {
+        lagassign_ctx* c = nullptr;
+        const int rc = lagassign_create(&c, devices[i]);
+        if (rc != LAGASSIGN_OK) {
+            const std::string m = g_thread_error;
+            for (lagassign_ctx* d : parent->shards) lagassign_destroy(d);
+            delete parent;
+            return fail(nullptr, rc, "device %d: %s", devices[i], m.c_str());
+        }
+        parent->shards.push_back(c);
+    }
+    *ctx = parent;
+    return LAGASSIGN_OK;
+}
+
+extern "C" int lagassign_shard_count(const lagassign_ctx* ctx, int* n_out) {
+    if (!ctx || !n_out) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx or n_out is NULL");
+    *n_out = ctx->shards.empty() ? 1 : (int)ctx->shards.size();
+    return LAGASSIGN_OK;
+}

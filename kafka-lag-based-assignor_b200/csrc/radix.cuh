@@ -76,18 +76,21 @@ k_big_hist(BigTopics bt, const int64_t* __restrict__ lag, const int32_t* __restr
         const int64_t t0 = (int64_t)(g - bt.tile0[b]) * RT_TILE;
         const int64_t* lg = lag + bt.off[b];
         const bool tie = HAS_PART && bt.need_tie[b] != 0;
-#ifdef LAGASSIGN_HIST_TILE_SKIP
-        // Experimental (compiled out by default; verified under tests/emu, not yet measured on a B200): a digit
-        // on which all keys of the tile agree (the high bytes of small lags, every byte of an idle topic) is
-        // counted with ONE atomic for the tile instead of one same-address atomic per element.
+        // A digit on which all keys of the tile agree (the high bytes of small lags, every byte of an idle
+        // topic) is counted with ONE atomic for the tile instead of one same-address atomic per element
+        // (B200: config 5, all-zero lags, 0.218 -> 0.126 ms; uniform 63-bit keys pay 14 % for the test).
         __shared__ uint32_t red[RT_WARPS][4];
         uint64_t key[RT_IPT];
         uint64_t o = 0, a = ~0ull;
 #pragma unroll
+        uint8_t* dg = bt.dig + bt.boff[b];
         for (int k = 0; k < RT_IPT; ++k) {
             const int64_t e = t0 + k * RT_THREADS + threadIdx.x;
             key[k] = (e < P) ? ((uint64_t)ld_stream(lg + e) ^ LAG_KEY_MASK) : 0ull;
-            if (e < P) { o |= key[k]; a &= key[k]; }
+            if (e < P) {
+                o |= key[k]; a &= key[k];
+                dg[e] = (uint8_t)key[k];      // digit of the first lag pass, for its counting kernel (4a) when it is the topic's first pass
+            }
         }
         {
             const uint32_t o_lo = __reduce_or_sync(0xffffffffu, (uint32_t)o), o_hi = __reduce_or_sync(0xffffffffu, (uint32_t)(o >> 32));
@@ -130,23 +133,6 @@ k_big_hist(BigTopics bt, const int64_t* __restrict__ lag, const int32_t* __restr
             }
         }
         __syncthreads();      // red[] is rewritten by the next tile
-#else
-#pragma unroll 4
-        for (int k = 0; k < RT_IPT; ++k) {
-            const int64_t e = t0 + k * RT_THREADS + threadIdx.x;
-            const bool live = e < P;
-            if (live) {
-                const uint64_t key = (uint64_t)ld_stream(lg + e) ^ LAG_KEY_MASK;
-#pragma unroll
-                for (int d = 0; d < N_LAG_PASS; ++d) atomicAdd(&h[N_TIE_PASS + d][digit_of(key, d)], 1u);
-                if (tie) {
-                    const uint32_t pk = (uint32_t)part[bt.off[b] + e] ^ 0x80000000u;
-#pragma unroll
-                    for (int d = 0; d < N_TIE_PASS; ++d) atomicAdd(&h[d][(pk >> (8 * d)) & 0xFFu], 1u);
-                }
-            }
-        }
-#endif
     }
     flush(cur_b);
 }
@@ -221,7 +207,11 @@ k_big_scan(BigTopics bt, int first_pass) {
 // every dependency between CTAs; so that it does not have to read the 8-byte keys again,
 // the scatter of pass p also writes, next to every key, the ONE byte the counting kernel
 // of the topic's next executed pass needs (BigTopics::dig).
-constexpr int RT_STAGES = 2;
+#ifndef LAGASSIGN_RT_STAGES
+#define LAGASSIGN_RT_STAGES 2
+#endif
+constexpr int RT_STAGES = LAGASSIGN_RT_STAGES;   // tiles in flight per CTA (the one being processed included)
+static_assert(RT_STAGES >= 2 && RT_STAGES <= 4, "ring depth");
 static_assert(RT_THREADS == 256, "the pass kernels map one thread to one digit value");
 
 // digit of an element in `pass`: passes below N_TIE_PASS sort by partition id (pv = the id),
@@ -231,17 +221,24 @@ __device__ __forceinline__ uint32_t pass_digit(int pass, uint64_t key, uint32_t 
 }
 
 // ---- bulk asynchronous copies (TMA, cp.async.bulk: SASS UBLKCP) completing on an mbarrier ----------
-#ifdef LAGASSIGN_HOST_EMULATION   // tests/emu: the copy happens at issue, the barrier is a no-op
+#ifdef LAGASSIGN_HOST_EMULATION   // tests/emu: the copy happens at issue; the barrier word = {completed phases, pending bytes}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
 __device__ __forceinline__ void fence_mbar_init() {}
 __device__ __forceinline__ void fence_proxy_async() {}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t*, uint32_t) {}
-__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t*) {
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    __atomic_store_n(reinterpret_cast<uint32_t*>(bar) + 1, bytes, __ATOMIC_RELAXED);
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     emu::check_aligned(smem_dst, 16); emu::check_aligned(gsrc, 16);
     if (bytes % 16 != 0) { std::fprintf(stderr, "cuda_emu: bulk copy of %u bytes\n", bytes); std::abort(); }
     std::memcpy(smem_dst, gsrc, bytes);
+    uint32_t* w = reinterpret_cast<uint32_t*>(bar);
+    if (__atomic_sub_fetch(w + 1, bytes, __ATOMIC_RELAXED) == 0) __atomic_add_fetch(w, 1u, __ATOMIC_RELEASE);   // phase complete
 }
-__device__ __forceinline__ void mbar_wait(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(bar);
+    while ((__atomic_load_n(w, __ATOMIC_ACQUIRE) & 1u) == parity) std::this_thread::yield();
+}
 #else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -268,53 +265,70 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif
 
 // 4a ------------------------------------------------------------------------------------------
+// One CTA per tile, grid-stride. What bounds this kernel is the chain of dependent loads per tile
+// (descriptor -> buffer choice -> data), so the next tile's descriptor and digit bytes are fetched
+// while the current tile is counted (warp-private counters, shared-memory atomics).
 template <bool HAS_PART>
 __global__ void __launch_bounds__(RT_THREADS)
 k_big_tile_hist(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int32_t* __restrict__ part) {
     __shared__ uint32_t whist[RT_WARPS][256];
     const int tid = threadIdx.x, warp = tid >> 5;
     if (bt.pass_any[pass] == 0) return;
-    for (int g = blockIdx.x; g < bt.n_tiles; g += gridDim.x) {
-        const int b = bt.tile_bt[g];
-        const int src = bt.sel_src[b * N_PASS + pass];
-        if (src == SEL_SKIP) continue;
-        const int64_t t0 = (int64_t)(g - bt.tile0[b]) * RT_TILE;
-        const int n_valid = (int)min((int64_t)RT_TILE, bt.P[b] - t0);
+    static_assert(RT_IPT == 16, "one uint4 of digit bytes per thread");
+    struct T { int src, n_valid; int64_t buf_off, raw_off; uint4 v; };
+    auto fetch = [&](int g) {
+        T t;
+        t.src = SEL_SKIP; t.n_valid = 0; t.buf_off = 0; t.raw_off = 0; t.v = make_uint4(0, 0, 0, 0);
+        if (g < bt.n_tiles) {
+            const int4 a = __ldg(bt.tile_desc + 2 * (size_t)g), c = __ldg(bt.tile_desc + 2 * (size_t)g + 1);
+            t.n_valid = a.z;
+            t.buf_off = ((int64_t)(uint32_t)c.y << 32) | (uint32_t)c.x;
+            t.raw_off = ((int64_t)(uint32_t)c.w << 32) | (uint32_t)c.z;
+            t.src = bt.sel_src[a.x * N_PASS + pass];
+            // the digit bytes are only meaningful when src is a sort buffer; reading them anyway keeps the load
+            // independent of the buffer choice (the buffer is allocated and padded for every tile)
+            if (tid * 16 < t.n_valid) t.v = *reinterpret_cast<const uint4*>(bt.dig + t.buf_off + tid * 16);
+        }
+        return t;
+    };
 #pragma unroll
-        for (int w = 0; w < RT_WARPS; ++w) whist[w][tid] = 0;
-        __syncthreads();
-        if (src != SEL_RAW) {
-            // the scatter of the topic's previous pass left this pass's digit of every element in bt.dig:
-            // 16 consecutive elements per thread, one 16-byte load
-            static_assert(RT_IPT == 16, "one uint4 of digit bytes per thread");
-            const int i0 = tid * 16;
-            if (i0 < n_valid) {
-                const uint4 v = *reinterpret_cast<const uint4*>(bt.dig + bt.boff[b] + t0 + i0);
-                const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+    for (int w = 0; w < RT_WARPS; ++w) whist[w][tid] = 0;
+    T cur = fetch((int)blockIdx.x);
+    __syncthreads();
+    for (int g = blockIdx.x; g < bt.n_tiles; g += gridDim.x) {
+        const T nxt = fetch(g + (int)gridDim.x);
+        if (cur.src != SEL_SKIP) {                 // uniform over the CTA
+            const int n_valid = cur.n_valid;
+            if (cur.src != SEL_RAW || pass == N_TIE_PASS) {
+                // the scatter of the topic's previous pass left this pass's digit of every element in bt.dig
+                // (for a topic whose first pass is the first lag pass, k_big_hist did)
+                const int i0 = tid * 16;
+                const uint32_t wds[4] = {cur.v.x, cur.v.y, cur.v.z, cur.v.w};
 #pragma unroll
                 for (int q = 0; q < 16; ++q)
                     if (i0 + q < n_valid) atomicAdd(&whist[warp][(wds[q >> 2] >> (8 * (q & 3))) & 0xFFu], 1u);
-            }
-        } else {
-            // the topic's first executed pass: digits from the caller's arrays
-            const int64_t* lg = lag + bt.off[b] + t0;
-            const int32_t* pt = HAS_PART ? part + bt.off[b] + t0 : nullptr;
-#pragma unroll 4
-            for (int k = 0; k < RT_IPT; ++k) {
-                const int i = k * RT_THREADS + tid;
-                if (i < n_valid) {
-                    const uint32_t pv = (HAS_PART && pass < N_TIE_PASS) ? (uint32_t)pt[i] : 0u;
-                    const uint64_t key = (!HAS_PART || pass >= N_TIE_PASS) ? ((uint64_t)ld_stream(lg + i) ^ LAG_KEY_MASK) : 0ull;
-                    atomicAdd(&whist[warp][pass_digit(pass, key, pv)], 1u);
+            } else {
+                // the topic's first executed pass: digits from the caller's arrays
+                const int64_t* lg = lag + cur.raw_off;
+                const int32_t* pt = HAS_PART ? part + cur.raw_off : nullptr;
+#pragma unroll
+                for (int k = 0; k < RT_IPT; ++k) {
+                    const int i = k * RT_THREADS + tid;
+                    if (i < n_valid) {
+                        const uint32_t pv = (HAS_PART && pass < N_TIE_PASS) ? (uint32_t)pt[i] : 0u;
+                        const uint64_t key = (!HAS_PART || pass >= N_TIE_PASS) ? ((uint64_t)ld_stream(lg + i) ^ LAG_KEY_MASK) : 0ull;
+                        atomicAdd(&whist[warp][pass_digit(pass, key, pv)], 1u);
+                    }
                 }
             }
-        }
-        __syncthreads();
-        uint32_t c = 0;
+            __syncthreads();
+            uint32_t c = 0;
 #pragma unroll
-        for (int w = 0; w < RT_WARPS; ++w) c += whist[w][tid];
-        bt.tile_hist[(size_t)g * 256 + tid] = c;
-        __syncthreads();
+            for (int w = 0; w < RT_WARPS; ++w) { c += whist[w][tid]; whist[w][tid] = 0; }   // read and clear for the next tile
+            bt.tile_hist[(size_t)g * 256 + tid] = c;
+            __syncthreads();
+        }
+        cur = nxt;
     }
 }
 
@@ -368,9 +382,10 @@ k_big_topic_scan(BigTopics bt, int pass) {
 // 4d ------------------------------------------------------------------------------------------
 // CTAs of SC_THREADS threads walk the tiles with a grid stride. One elected thread fetches a tile
 // with two bulk asynchronous copies (TMA; keys and payloads) into a ring of RT_STAGES shared-memory
-// stages, one tile ahead, completion on an mbarrier per stage: HBM loads stay in flight while the
-// current tile is ranked and scattered and no thread spends issue slots on the copy. The stage
-// being processed doubles as the staging buffer of the tile-local scatter.
+// stages, completion on an mbarrier per stage: HBM loads stay in flight while the current tile is
+// ranked and scattered and no thread spends issue slots on the copy. The stage being processed
+// doubles as the staging buffer of the tile-local scatter and is refilled as soon as the sorted
+// tile has been read back out of it.
 //
 // Ranking (stable: elements with equal digit keep memory order). A warp owns a contiguous run of
 // the tile, item k of lane l being element warp*32*IPT + k*32 + l, and keeps running digit counts
@@ -389,17 +404,19 @@ k_big_topic_scan(BigTopics bt, int pass) {
 //    group's base. Atomics of one warp on one address complete in program order, so items need no
 //    barrier between them.
 #ifndef LAGASSIGN_SC_THREADS
-#define LAGASSIGN_SC_THREADS 512
+#define LAGASSIGN_SC_THREADS 256
 #endif
 constexpr int SC_THREADS = LAGASSIGN_SC_THREADS;
 constexpr int SC_WARPS = SC_THREADS / 32;
 constexpr int SC_IPT = RT_TILE / SC_THREADS;
 static_assert(SC_THREADS >= 256 && SC_THREADS * SC_IPT == RT_TILE, "a tile is SC_THREADS x SC_IPT elements; threads 0..255 also own one digit value each");
+static_assert(RT_TILE < 65536 && SC_WARPS % 2 == 0, "tile-local offsets are packed two per word");
 
 struct PassSmem {
     alignas(16) uint64_t key[RT_STAGES][RT_TILE + 2];   // + 2: a raw source may start 8 bytes after a 16-byte boundary
     alignas(16) uint32_t pay[RT_STAGES][RT_TILE + 4];
-    uint32_t whist[SC_WARPS][256];   // per-warp running digit counts, then tile-local offsets per (warp, digit)
+    uint32_t whist[SC_WARPS / 2][256];   // per-warp running digit counts, then tile-local offsets per (warp, digit):
+                                         // 16 bits each (<= RT_TILE), warps 2j and 2j+1 in the low / high half of word j
     int32_t dst_base[256];           // index in the topic of the tile's first element of each digit, minus its tile-local offset
     uint32_t wsum[8];
     alignas(8) uint64_t full_bar[RT_STAGES];
@@ -442,10 +459,12 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
 
     // A tile's geometry is one 32-byte record; the record also remembers which buffer the
     // topic reads in this pass (-1: pass skipped for the topic, or no such tile).
-    struct Tile { TileDesc d; int src; };
+    struct Tile { TileDesc d; int src, dst, nxt_pass; };
     auto load_tile = [&](int g) {
         Tile t;
         t.src = SEL_SKIP;
+        t.dst = SEL_SKIP;
+        t.nxt_pass = -1;
         t.d.b = -1;
         if (g < n_tiles) {
             const int4 a = __ldg(bt.tile_desc + 2 * (size_t)g), c = __ldg(bt.tile_desc + 2 * (size_t)g + 1);
@@ -453,6 +472,8 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
             t.d.buf_off = ((int64_t)(uint32_t)c.y << 32) | (uint32_t)c.x;
             t.d.raw_off = ((int64_t)(uint32_t)c.w << 32) | (uint32_t)c.z;
             t.src = bt.sel_src[t.d.b * N_PASS + pass];
+            t.dst = bt.sel_dst[t.d.b * N_PASS + pass];
+            t.nxt_pass = bt.nxt_pass[t.d.b * N_PASS + pass];   // the topic's next executed pass (-1: none)
         }
         return t;
     };
@@ -479,39 +500,55 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
         }
     };
 
-    static_assert(RT_STAGES == 2, "the descriptor pipeline below is written for a two-stage ring");
     if (tid == 0) {
-        mbar_init(&sm.full_bar[0], 1);
-        mbar_init(&sm.full_bar[1], 1);
+#pragma unroll
+        for (int j = 0; j < RT_STAGES; ++j) mbar_init(&sm.full_bar[j], 1);
         fence_mbar_init();
     }
 #pragma unroll
-    for (int w = 0; w < SC_WARPS; ++w)
+    for (int w = 0; w < SC_WARPS / 2; ++w)
         if (tid < 256) sm.whist[w][tid] = 0;
     __syncthreads();
     const int G = (int)gridDim.x;
+    uint32_t* const my_cnt = sm.whist[warp >> 1];      // this warp's counters: the (warp & 1) half of these words
+    const int my_sh = (warp & 1) * 16;
     const int g0 = (int)blockIdx.x;
-    Tile cur = load_tile(g0);              // tile being processed
-    if (tid == 0) issue_loads(0, cur);
-    Tile pre = load_tile(g0 + G);          // next tile: its loads are issued at the top of the iteration
-    uint32_t phase[2] = {0u, 0u};          // parity of the next completion of each stage's barrier
+    // q[j] = the tile of iteration it + j, already being fetched into ring stage (it + j) % RT_STAGES; `far` is the
+    // tile after those: it is fetched into the stage of the current tile as soon as every thread has read the
+    // tile-local scatter back out of it, BEFORE the global stores are issued — so a warp that is held up by the
+    // store queue does not hold up the refill, and warps flow from their stores straight into the next tile
+    // (whose first barrier comes after its ranking).
+    Tile q[RT_STAGES];
+#pragma unroll
+    for (int j = 0; j < RT_STAGES; ++j) q[j] = load_tile(g0 + j * G);
+    if (tid == 0) {
+#pragma unroll
+        for (int j = 0; j < RT_STAGES; ++j) issue_loads(j, q[j]);
+    }
+    Tile far = load_tile(g0 + RT_STAGES * G);
+    uint32_t phase = 0u;                   // bit j: parity of the next completion of stage j's barrier
+    int s = 0;                             // ring stage of the tile being processed
 
     for (int it = 0;; ++it) {
-        const int s = it & 1;
         const int g = g0 + it * G;
-        fence_proxy_async();   // this thread's reads/writes of stage s^1 (previous tile) before the bulk copy into it
-        __syncthreads();       // previous tile fully stored, counters zeroed: its stage may be refilled
-        const Tile nxt = pre;
-        if (tid == 0) issue_loads(s ^ 1, nxt);
-        pre = load_tile(g + 2 * G);        // consumed by the next iteration
-        RT_TICK(0);
         if (g >= n_tiles) break;
-        if (cur.src == SEL_SKIP) { cur = nxt; continue; }   // this topic's digit is constant in this pass
+        const Tile cur = q[0];
+#pragma unroll
+        for (int j = 0; j + 1 < RT_STAGES; ++j) q[j] = q[j + 1];
+        q[RT_STAGES - 1] = far;                                    // tile it + RT_STAGES: next occupant of this stage
+        far = load_tile(g + (RT_STAGES + 1) * G);
+        const Tile refill = q[RT_STAGES - 1];
+        RT_TICK(0);
+        const int s_cur = s;
+        s = (s + 1 == RT_STAGES) ? 0 : s + 1;
+        if (cur.src == SEL_SKIP) {           // this topic's digit is constant in this pass: nothing was fetched,
+            if (tid == 0) issue_loads(s_cur, refill);   // the stage is free (its last reader passed a barrier long ago)
+            continue;
+        }
 
-        const int b = cur.d.b;
         const int src = cur.src;
-        const int dst = bt.sel_dst[b * N_PASS + pass];
-        const int nxt_pass = bt.nxt_pass[b * N_PASS + pass];   // the topic's next executed pass (-1: none)
+        const int dst = cur.dst;
+        const int nxt_pass = cur.nxt_pass;
         const int64_t t0 = (int64_t)cur.d.tile_in_topic * RT_TILE;
         const int n_valid = cur.d.n_valid;
         const int64_t boff = cur.d.buf_off - t0;
@@ -523,12 +560,11 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
         // where this tile's elements of digit `tid` start in the topic (4b + 4c); used after the ranking
         uint32_t base_d = 0;
         if (tid < 256) base_d = bt.tile_hist[(size_t)g * 256 + tid] + bt.seg_total[(size_t)cur.d.seg * 256 + tid];
-        cur = nxt;
         RT_TICK(1);
 
         // this thread's elements: item k of lane l in warp w is tile element w*32*IPT + k*32 + l
-        mbar_wait(&sm.full_bar[s], phase[s]);
-        phase[s] ^= 1u;
+        mbar_wait(&sm.full_bar[s_cur], (phase >> s_cur) & 1u);
+        phase ^= 1u << s_cur;
         uint64_t key[SC_IPT];
         uint32_t pay[SC_IPT];
         uint32_t dig[SC_IPT];
@@ -536,8 +572,8 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
         for (int k = 0; k < SC_IPT; ++k) {
             const int i = warp * (32 * SC_IPT) + k * 32 + lane;
             if (i < n_valid) {
-                if (src == SEL_RAW) { key[k] = sm.key[s][i + sh] ^ LAG_KEY_MASK; pay[k] = (uint32_t)(t0 + i); }
-                else { key[k] = sm.key[s][i]; pay[k] = sm.pay[s][i]; }
+                if (src == SEL_RAW) { key[k] = sm.key[s_cur][i + sh] ^ LAG_KEY_MASK; pay[k] = (uint32_t)(t0 + i); }
+                else { key[k] = sm.key[s_cur][i]; pay[k] = sm.pay[s_cur][i]; }
                 dig[k] = pass_digit(pass, key[k], (HAS_PART && pass < N_TIE_PASS) ? (uint32_t)pt[pay[k]] : 0u);
             } else {
                 key[k] = KEY_SENTINEL; pay[k] = PAY_SENTINEL; dig[k] = 255u;  // padding: neither counted nor moved
@@ -554,12 +590,12 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
             const bool valid = warp * (32 * SC_IPT) + k * 32 + lane < n_valid;
             if constexpr (!EXACT) {
                 rank[k] = 0;
-                if (valid) rank[k] = atomicAdd(&sm.whist[warp][dig[k]], 1u);
+                if (valid) rank[k] = (atomicAdd(&my_cnt[dig[k]], 1u << my_sh) >> my_sh) & 0xFFFFu;
             } else {
                 const uint32_t peers = peers_of_digit(dig[k]) & __ballot_sync(0xffffffffu, valid);
                 const uint32_t below = peers & ((1u << lane) - 1u);
                 uint32_t pre_cnt = 0;
-                if (valid && below == 0) pre_cnt = atomicAdd(&sm.whist[warp][dig[k]], (uint32_t)__popc(peers));
+                if (valid && below == 0) pre_cnt = (atomicAdd(&my_cnt[dig[k]], (uint32_t)__popc(peers) << my_sh) >> my_sh) & 0xFFFFu;
                 pre_cnt = __shfl_sync(0xffffffffu, pre_cnt, (__ffs(peers) - 1) & 31);
                 rank[k] = pre_cnt + __popc(below);
             }
@@ -572,10 +608,11 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
             uint32_t cnt = 0, x = 0;
             if (tid < 256) {
 #pragma unroll
-                for (int w = 0; w < SC_WARPS; ++w) {
-                    const uint32_t v = sm.whist[w][tid];
-                    sm.whist[w][tid] = cnt;
-                    cnt += v;
+                for (int w = 0; w < SC_WARPS / 2; ++w) {
+                    const uint32_t v = sm.whist[w][tid];          // counts of warps 2w (low half) and 2w+1 (high half)
+                    const uint32_t lo = v & 0xFFFFu, hi = v >> 16;
+                    sm.whist[w][tid] = cnt | ((cnt + lo) << 16);   // their exclusive offsets inside the digit
+                    cnt += lo + hi;
                 }
                 x = cnt;
 #pragma unroll
@@ -591,7 +628,7 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
                 for (int w = 0; w < warp; ++w) add += sm.wsum[w];
                 const uint32_t excl = x - cnt + add;
 #pragma unroll
-                for (int w = 0; w < SC_WARPS; ++w) sm.whist[w][tid] += excl;
+                for (int w = 0; w < SC_WARPS / 2; ++w) sm.whist[w][tid] += excl * 0x10001u;   // both halves stay below RT_TILE
                 sm.dst_base[tid] = (int32_t)(base_d - excl);
             }
         }
@@ -602,15 +639,16 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
 #pragma unroll
         for (int k = 0; k < SC_IPT; ++k) {
             if (warp * (32 * SC_IPT) + k * 32 + lane < n_valid) {
-                const uint32_t pos = sm.whist[warp][dig[k]] + rank[k];
-                sm.key[s][pos] = key[k];
-                sm.pay[s][pos] = pay[k];
+                const uint32_t pos = ((my_cnt[dig[k]] >> my_sh) & 0xFFFFu) + rank[k];
+                sm.key[s_cur][pos] = key[k];
+                sm.pay[s_cur][pos] = pay[k];
             }
         }
         __syncthreads();
-        // (the counters are free again: zero them for the next tile; the barrier at the top of the loop orders it)
+        RT_TICK(5);
+        // (the counters are free again: zero them for the next tile; the barrier below orders it)
 #pragma unroll
-        for (int w = 0; w < SC_WARPS; ++w)
+        for (int w = 0; w < SC_WARPS / 2; ++w)
             if (tid < 256) sm.whist[w][tid] = 0;
         // ... then out in digit runs (coalesced), with the digit byte of the topic's next pass beside the key
         {
@@ -621,9 +659,13 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
 #pragma unroll
             for (int k = 0; k < SC_IPT; ++k) {       // all shared-memory reads first, then the stores
                 const int i = k * SC_THREADS + tid;
-                kk[k] = sm.key[s][i];
-                pp[k] = sm.pay[s][i];
+                kk[k] = sm.key[s_cur][i];
+                pp[k] = sm.pay[s_cur][i];
             }
+            fence_proxy_async();   // this thread's reads/writes of the stage before the bulk copy into it
+            __syncthreads();       // everyone holds its part of the sorted tile in registers, counters are zeroed
+            if (tid == 0) issue_loads(s_cur, refill);
+            RT_TICK(6);
 #pragma unroll
             for (int k = 0; k < SC_IPT; ++k) {
                 const int i = k * SC_THREADS + tid;
@@ -636,22 +678,27 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
             for (int k = 0; k < SC_IPT; ++k) {
                 const int i = k * SC_THREADS + tid;
                 if (i < n_valid) {
+#if defined(LAGASSIGN_SC_STCS) && !defined(LAGASSIGN_HOST_EMULATION)
+                    __stcs(reinterpret_cast<unsigned long long*>(dkey + oo[k]), (unsigned long long)kk[k]);
+                    __stcs(dpay + oo[k], pp[k]);
+#else
                     dkey[oo[k]] = kk[k];
                     dpay[oo[k]] = pp[k];
+#endif
                     if (nxt_pass >= 0) ddig[oo[k]] = (uint8_t)pass_digit(nxt_pass, kk[k], pv[k]);
                 }
             }
         }
-        RT_TICK(5);
+        RT_TICK(7);
 #ifdef LAGASSIGN_RT_TIMING
         ++t_tiles;
 #endif
     }
 #ifdef LAGASSIGN_RT_TIMING
     if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 200) && t_tiles > 0)
-        printf("pass %d cta %d tiles %d | cycles per tile: top+issue %lld meta %lld wait+lds %lld rank+bar %lld scan+bar %lld scatter+store %lld\n",
+        printf("pass %d cta %d tiles %d | cycles per tile: top %lld meta %lld wait+lds %lld rank+bar %lld scan+bar %lld local-scatter+bar %lld readback+bar %lld stores %lld\n",
                pass, (int)blockIdx.x, t_tiles, t_acc[0] / t_tiles, t_acc[1] / t_tiles, t_acc[2] / t_tiles, t_acc[3] / t_tiles,
-               t_acc[4] / t_tiles, t_acc[5] / t_tiles);
+               t_acc[4] / t_tiles, t_acc[5] / t_tiles, t_acc[6] / t_tiles, t_acc[7] / t_tiles);
 #endif
 }
 
@@ -780,9 +827,14 @@ k_big_fill(BigTopics bt, const int32_t* __restrict__ fill_list, int n_fill,
             cta_round_fill_regs<8, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
         } else if (C <= BIGFILL_REG_MAX_C) {
             cta_round_fill_regs<16, BIGFILL_THREADS>(P, C, cset, xbuf, lag_at, put, tot, cnt);
-        } else {
+        } else if (C <= FILL_CTA_MAX_C) {
             cta_round_fill<BIGFILL_MAXJ>(P, C, max(64, 1 << (32 - __clz(C - 1))), cset, ckey, cidx,
                                          lag_at, put, tot, cnt);
+        } else {
+            // more consumers than fit on chip (and still more partitions): the same rounds in a global workspace
+            const int64_t ws = bt.fill_ws_off[b];
+            cta_round_fill_any(P, (int64_t)C, (int64_t)1 << (32 - __clz(C - 1)), cset, bt.fill_ws_key + ws, bt.fill_ws_idx + ws,
+                               lag_at, put, tot, cnt);
         }
         __syncthreads();
     }

@@ -88,6 +88,9 @@ struct BigTopics {
     int32_t* passes_run;       // [1] max over topics of executed passes (stat)
     uint32_t* pass_any;        // [N_PASS] does any topic run this pass? (else the launch returns at once)
     uint32_t* verify_fail;     // [1] set by k_big_verify when a sorted sequence is not strictly increasing
+    const int64_t* fill_ws_off; // [B] slot offset of the topic's round-fill workspace (C > FILL_CTA_MAX_C), else -1
+    uint64_t* fill_ws_key;     // consumers of such topics: (total key, index) in global memory,
+    uint32_t* fill_ws_idx;     //   pow2 >= C slots per topic
 };
 
 

@@ -4,9 +4,13 @@ Topics are independent in the reference — totals and counts are created afresh
 for each one (LagBasedPartitionAssignor.java:215-225) and the batch driver loops
 over them sequentially (Main:177-184) — so they shard with no data-path
 exchange. The only collective is the one the path needs at the end: an
-all-gather of (out_partition, out_consumer_rank) so every rank holds the whole
-assignment map (NCCL over NVLink on GPUs; the same code runs on gloo/CPU
-tensors in the tests). The reference has no counterpart (single JVM thread).
+all-gather so every rank holds the whole assignment map (NCCL over NVLink on
+GPUs). What crosses NVLink is the NARROW form of each rank's results
+(exchange_format(): partition ids in 1/2/4 bytes, consumers in 0/2/4 bytes —
+0 when every topic has P <= C, because the consumer of sorted partition k is
+then the k-th member of the topic's set and every rank writes it itself);
+lagassign_exchange_pack / _unpack (include/lagassign.h) narrow and widen on the
+device. The reference has no counterpart (single JVM thread).
 
 Shards are CONTIGUOUS topic ranges balanced by partition count, so the global
 result is simply the concatenation of the ranks' results. A single huge topic
@@ -52,6 +56,32 @@ def partition_counts(topic_off: np.ndarray, bounds: Sequence[Tuple[int, int]]) -
     return [int(off[hi] - off[lo]) for lo, hi in bounds]
 
 
+def exchange_format(batch: dict) -> Tuple[int, int]:
+    """(part_width, cons_width) in bytes of the narrow result form for this batch, see
+    include/lagassign.h "Result exchange". Decided from the WHOLE batch, identically on every rank."""
+    off = np.asarray(batch["topic_off"], dtype=np.int64)
+    P = np.diff(off)
+    part = batch.get("partition")
+    if part is None:
+        max_id = int(P.max()) - 1 if len(P) else 0
+        min_id = 0
+    else:
+        part = np.asarray(part)
+        max_id = int(part.max()) if part.size else 0
+        min_id = int(part.min()) if part.size else 0
+    pw = 4 if min_id < 0 or max_id >= 65536 else (2 if max_id >= 256 else 1)
+    cset_off = np.asarray(batch["cset_off"], dtype=np.int64)
+    csize = np.diff(cset_off)
+    C = csize[np.asarray(batch["topic_cset"], dtype=np.int64)] if len(P) else np.zeros(0, np.int64)
+    if bool(np.all((P <= C) | (C == 0))):
+        cw = 0                                  # consumers are derivable everywhere
+    else:
+        ranks = np.asarray(batch["cset_rank"])
+        n_members = int(ranks.max()) + 1 if ranks.size else 0
+        cw = 2 if n_members < 65535 else 4      # 0xFFFF stands for "no subscriber" (-1)
+    return pw, cw
+
+
 def all_gather_results(local_part, local_cons, counts: Sequence[int], group=None):
     """All-gather the ranks' (out_partition, out_consumer_rank) torch tensors
     (int32, 1-D, on the backend's device) into the full arrays of sum(counts)
@@ -86,8 +116,9 @@ def all_gather_results(local_part, local_cons, counts: Sequence[int], group=None
 
 class ShardedAssignor:
     """One rank's view of a topic-sharded assign(): upload this rank's contiguous
-    shard, run the kernels writing straight into this rank's slice of the gather
-    buffers, all-gather. torch (CUDA + NCCL) is plumbing only."""
+    shard, run the kernels, narrow the results into this rank's slot of the gather
+    buffer, all-gather the slots, widen them into the full int32 arrays.
+    torch (CUDA + NCCL) is plumbing only."""
 
     def __init__(self, flat_assignor, rank: int, world_size: int, group=None):
         self.f = flat_assignor
@@ -97,6 +128,8 @@ class ShardedAssignor:
 
     def upload(self, batch: dict):
         import torch
+        from . import load_library
+        self.L = load_library()
         self.bounds = shard_bounds(batch["topic_off"], self.world)
         self.counts = partition_counts(batch["topic_off"], self.bounds)
         lo, hi = self.bounds[self.rank]
@@ -105,22 +138,27 @@ class ShardedAssignor:
         self.f.upload(b["topic_off"], b["lag"], b["partition"], b["topic_cset"], b["cset_off"], b["cset_rank"])
         total = int(sum(self.counts))
         dev = torch.device("cuda", torch.cuda.current_device())
-        self.equal = len(set(self.counts)) == 1
         self.start = int(sum(self.counts[:self.rank]))
         n = self.counts[self.rank]
-        if self.equal:
-            # One buffer [rank][partition | consumer][n]: the kernels write into this rank's block and
-            # ONE in-place all-gather moves both result arrays (a second collective launch costs more
-            # than the extra bytes).
-            self.buf = torch.empty((self.world, 2, max(n, 1)), dtype=torch.int32, device=dev)
-            self.f.bind_device_outputs(self.buf[self.rank, 0].data_ptr(), self.buf[self.rank, 1].data_ptr())
-            self.full_part = self.full_cons = None
-        else:
-            self.full_part = torch.empty(total, dtype=torch.int32, device=dev)
-            self.full_cons = torch.empty(total, dtype=torch.int32, device=dev)
-            self.loc_part = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-            self.loc_cons = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-            self.f.bind_device_outputs(self.loc_part.data_ptr(), self.loc_cons.data_ptr())
+        self.full_part = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        self.full_cons = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        if self.world == 1:
+            self.f.bind_device_outputs(self.full_part.data_ptr(), self.full_cons.data_ptr())
+            return
+        self.n_topics = len(batch["topic_off"]) - 1
+        self.pw, self.cw = exchange_format(batch)
+        self.slot_bytes = int(self.L.lagassign_exchange_slot_bytes(max(self.counts), self.pw, self.cw))
+        self.slots = torch.empty(self.world * max(self.slot_bytes, 16), dtype=torch.uint8, device=dev)
+        self.loc_part = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        self.loc_cons = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        self.f.bind_device_outputs(self.loc_part.data_ptr(), self.loc_cons.data_ptr())
+        # the whole batch's shape, for the widening kernel (small: 12 B per topic + the consumer sets)
+        t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+        self.d_topic_off = t(batch["topic_off"], np.int64)
+        self.d_topic_cset = t(batch["topic_cset"], np.int32)
+        self.d_cset_off = t(batch["cset_off"], np.int64)
+        self.d_cset_rank = t(batch["cset_rank"], np.int32) if len(batch["cset_rank"]) else torch.zeros(1, dtype=torch.int32, device=dev)
+        self.d_first = t([lo_ for lo_, _ in self.bounds] + [self.n_topics], np.int64)
 
     def execute(self, gather: bool = True):
         self.f.execute()
@@ -128,20 +166,27 @@ class ShardedAssignor:
             self.gather()
 
     def gather(self):
-        """All-gather the ranks' results (no-op on one rank)."""
+        """Narrow, all-gather, widen (no-op on one rank)."""
+        import ctypes
+        import torch
         import torch.distributed as dist
         if self.world == 1:
             return
-        n = self.counts[self.rank]
-        if self.equal:
-            dist.all_gather_into_tensor(self.buf.view(-1), self.buf[self.rank].view(-1), group=self.group)
-        else:
-            self.full_part, self.full_cons = all_gather_results(self.loc_part[:n], self.loc_cons[:n],
-                                                                self.counts, self.group)
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        vp = ctypes.c_void_p
+        my = self.slots[self.rank * self.slot_bytes:(self.rank + 1) * self.slot_bytes]
+        rc = self.L.lagassign_exchange_pack(st, self.counts[self.rank], vp(self.loc_part.data_ptr()), vp(self.loc_cons.data_ptr()),
+                                            self.pw, self.cw, vp(my.data_ptr()))
+        assert rc == 0, rc
+        dist.all_gather_into_tensor(self.slots[:self.world * self.slot_bytes], my, group=self.group)
+        rc = self.L.lagassign_exchange_unpack(st, self.n_topics, vp(self.d_topic_off.data_ptr()), vp(self.d_topic_cset.data_ptr()),
+                                              vp(self.d_cset_off.data_ptr()), vp(self.d_cset_rank.data_ptr()),
+                                              vp(self.d_first.data_ptr()), self.world, vp(self.slots.data_ptr()),
+                                              self.slot_bytes, self.pw, self.cw,
+                                              vp(self.full_part.data_ptr()), vp(self.full_cons.data_ptr()))
+        assert rc == 0, rc
 
     def results(self):
         """(out_partition, out_consumer_rank) of the whole batch as contiguous 1-D tensors."""
-        if self.equal:
-            n = self.counts[self.rank]
-            return self.buf[:, 0, :n].reshape(-1), self.buf[:, 1, :n].reshape(-1)
-        return self.full_part, self.full_cons
+        total = int(sum(self.counts))
+        return self.full_part[:total], self.full_cons[:total]

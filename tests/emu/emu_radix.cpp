@@ -27,7 +27,8 @@ extern "C" int emu_assign_big(int64_t n_topics, const int64_t* topic_off, const 
                               const int64_t* tc_off, int32_t* out_partition, int32_t* out_consumer_rank,
                               int64_t* out_total, int32_t* out_count, int64_t min_big_p, int sms, int* passes_run_out) {
     std::vector<int32_t> bt_topic, bt_tile0, tile_bt, l_fill, bt_seg0, seg_bt;
-    std::vector<int64_t> bt_off, bt_P, bt_boff;
+    std::vector<int64_t> bt_off, bt_P, bt_boff, fill_ws_off;
+    int64_t fill_ws_elems = 0;
     std::vector<TileDesc> tile_desc;
     int64_t boff = 0, tiles = 0;
     int n_segs = 0;
@@ -36,7 +37,6 @@ extern "C" int emu_assign_big(int64_t n_topics, const int64_t* topic_off, const 
         const int32_t s = topic_cset[t];
         const int64_t C = cset_off[s + 1] - cset_off[s];
         if (P <= min_big_p || C == 0) continue;
-        if (P > C && C > FILL_CTA_MAX_C) return -1;
         const int64_t nt = (P + RT_TILE - 1) / RT_TILE;
         const int32_t b = (int32_t)bt_topic.size();
         bt_topic.push_back((int32_t)t); bt_off.push_back(topic_off[t]); bt_P.push_back(P); bt_boff.push_back(boff);
@@ -52,6 +52,9 @@ extern "C" int emu_assign_big(int64_t n_topics, const int64_t* topic_off, const 
         }
         n_segs += nseg;
         if (P > C) l_fill.push_back(b);
+        int64_t ws = -1;
+        if (P > C && C > FILL_CTA_MAX_C) { int64_t nc = 1; while (nc < C) nc <<= 1; ws = fill_ws_elems; fill_ws_elems += nc; }
+        fill_ws_off.push_back(ws);
         boff += (P + RT_BUF_ALIGN - 1) / RT_BUF_ALIGN * RT_BUF_ALIGN; tiles += nt;
     }
     const int B = (int)bt_topic.size();
@@ -88,6 +91,9 @@ extern "C" int emu_assign_big(int64_t n_topics, const int64_t* topic_off, const 
     bt.nxt_pass = sel.data() + (size_t)B * N_PASS * 2;
     bt.sel_final = sel.data() + (size_t)B * N_PASS * 3; bt.all_equal = sel.data() + (size_t)B * (N_PASS * 3 + 1);
     bt.dig = digbuf.data();
+    std::vector<uint64_t> ws_key((size_t)fill_ws_elems + 1);
+    std::vector<uint32_t> ws_idx((size_t)fill_ws_elems + 1);
+    bt.fill_ws_off = fill_ws_off.data(); bt.fill_ws_key = ws_key.data(); bt.fill_ws_idx = ws_idx.data();
     bt.need_tie = need_tie.data(); bt.tile_hist = tile_hist.data();
     bt.seg0 = bt_seg0.data(); bt.seg_bt = seg_bt.data(); bt.n_segs = n_segs; bt.seg_total = seg_total.data();
     bt.ticket = ticket.data(); bt.passes_run = reinterpret_cast<int32_t*>(ticket.data() + N_PASS);

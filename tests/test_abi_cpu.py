@@ -36,7 +36,7 @@ def test_cuda_library_exports_every_declared_symbol(pkg):
     lib = ctypes.CDLL(pkg.library_path())
     for name in _declared("lagassign.h"):
         assert hasattr(lib, name), name
-    assert lib.lagassign_abi_version() == 1
+    assert lib.lagassign_abi_version() == 2
 
 
 def test_host_library_exports_every_declared_symbol(pkg):
@@ -65,6 +65,12 @@ def test_no_cpu_fallback_without_gpu(pkg):
     with pytest.raises(pkg.LagAssignError) as e:
         pkg.FlatAssignor(0)
     assert e.value.code == -5
+    with pytest.raises(pkg.LagAssignError) as e:
+        pkg.FlatAssignor([0, 1])                       # lagassign_create_multi: no device, no fallback either
+    assert e.value.code == -5
+    with pytest.raises(pkg.LagAssignError) as e:
+        pkg.FlatAssignor([])
+    assert e.value.code == -1
     with pytest.raises(pkg.LagAssignError):
         a = pkg.LagBasedPartitionAssignor()
         a.assign({"t": [pkg.TopicPartitionLag("t", 0, 1)]}, {"c": ["t"]})

@@ -85,3 +85,25 @@ def test_shard_bounds_properties():
     off = np.array([0, 10, 1 << 20, (1 << 20) + 5], dtype=np.int64)
     b = D.shard_bounds(off, 4)
     assert sum(hi - lo for lo, hi in b) == 3
+
+
+def test_exchange_format_choices():
+    """Width of the narrow result form (include/lagassign.h "Result exchange"), decided from the whole batch."""
+    from helpers import baseline_config, uniform_batch
+    from kafka_lag_based_assignor_b200 import distributed as D
+    b4, _ = baseline_config(4, scale=0.001)
+    assert D.exchange_format(b4) == (1, 0)                    # 256 partitions, P < C: ids in a byte, consumers derived
+    b3, _ = baseline_config(3, scale=0.01)
+    assert D.exchange_format(b3) == (1, 0)
+    b7, _ = baseline_config(7, scale=0.01)
+    assert D.exchange_format(b7) == (1, 2)                    # P > C: consumers travel, 16 members fit 2 bytes
+    assert D.exchange_format(uniform_batch(2, 257, 300, np.zeros(514, np.int64))) == (2, 0)
+    assert D.exchange_format(uniform_batch(1, 70000, 10, np.zeros(70000, np.int64))) == (4, 2)
+    wide = uniform_batch(1, 10, 3, np.zeros(10, np.int64))
+    wide["cset_rank"] = np.array([5, 70000, 70001], np.int32)
+    assert D.exchange_format(wide) == (1, 4)
+    neg = uniform_batch(1, 4, 8, np.zeros(4, np.int64))
+    neg["partition"] = np.array([-1, 0, 1, 2], np.int32)
+    assert D.exchange_format(neg) == (4, 0)
+    unsub = uniform_batch(2, 5, 0, np.zeros(10, np.int64))    # nobody subscribed: nothing to send for consumers
+    assert D.exchange_format(unsub) == (1, 0)

@@ -428,6 +428,151 @@ def test_config_full_size_vs_oracle_every_topic(pkg, n, totals):
         assert np.array_equal(got[k], exp[k]), k
 
 
+def test_more_than_8192_consumers_and_more_partitions(flat):
+    """P > C > 8192: multi-round fill over more consumers than fit on chip (a global-memory workspace); the
+    reference handles any shape, round 1 returned LAGASSIGN_ERR_UNSUPPORTED here. Mixed with ordinary topics."""
+    rng = np.random.default_rng(92)
+    sizes = np.array([40000, 300, 9000 * 3 + 5, 70000, 5000])
+    topic_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    lag = rng.integers(0, 1 << 44, size=int(topic_off[-1]), dtype=np.int64)
+    lag[int(topic_off[3]):] //= (1 << 30)                          # duplicates in the last two topics
+    sets = [np.arange(9000, dtype=np.int32), np.sort(rng.choice(40000, size=20000, replace=False)).astype(np.int32),
+            np.arange(100, dtype=np.int32)]
+    cset_off = np.concatenate([[0], np.cumsum([len(x) for x in sets])]).astype(np.int64)
+    b = dict(topic_off=topic_off, lag=lag, partition=None, topic_cset=np.array([0, 2, 0, 1, 1], np.int32),
+             cset_off=cset_off, cset_rank=np.concatenate(sets).astype(np.int32))
+    check(flat, b)
+
+
+# ---- multi-device context (lagassign_create_multi) ---------------------------------------------------
+
+def _multi_devices(pkg, want):
+    n = pkg.device_count()
+    return [i % n for i in range(want)]       # with fewer GPUs than ranges, devices repeat (the split is the same)
+
+
+@pytest.mark.parametrize("n_dev", [2, 3, 8])
+def test_multi_device_context_matches_oracle(pkg, n_dev):
+    """One process, several devices: contiguous topic ranges, each device copying its results into the caller's
+    arrays. Mixed bins, ragged sizes, empty topics, totals; compared bit-exactly with the oracle."""
+    rng = np.random.default_rng(40 + n_dev)
+    b = random_flat(rng, T=500, pmin=0, pmax=700, C=300, lag_kind="u40", explicit_ids="shuffled", n_sets=4)
+    big = random_flat(rng, T=6, pmin=4000, pmax=30000, C=50, lag_kind="small", n_sets=1, full_sets=True)
+    # append the large topics (their consumer set becomes set number 4)
+    b["topic_off"] = np.concatenate([b["topic_off"], b["topic_off"][-1] + big["topic_off"][1:]])
+    b["lag"] = np.concatenate([b["lag"], big["lag"]])
+    b["partition"] = np.concatenate([b["partition"], np.concatenate([np.arange(int(p), dtype=np.int32) for p in np.diff(big["topic_off"])])])
+    b["topic_cset"] = np.concatenate([b["topic_cset"], np.full(6, 4, np.int32)])
+    b["cset_off"] = np.concatenate([b["cset_off"], [b["cset_off"][-1] + len(big["cset_rank"])]]).astype(np.int64)
+    b["cset_rank"] = np.concatenate([b["cset_rank"], big["cset_rank"]]).astype(np.int32)
+    with pkg.FlatAssignor(_multi_devices(pkg, n_dev), want_totals=True) as f:
+        got = f.assign_batch(*args_of(b))
+        st = f.stats()
+        got2 = None
+        f.upload(*args_of(b)); f.execute(); got2 = f.download()       # split form
+    exp = oracle.assign_batch(*args_of(b), want_totals=True, threads=8)
+    for k in KEYS:
+        assert np.array_equal(got[k], exp[k]), k
+        assert np.array_equal(got2[k], exp[k]), k
+    assert st["n_partitions"] == len(b["lag"]) and st["topics_device"] == 6
+
+
+def test_multi_device_context_config4_slice(pkg):
+    """BASELINE config 4's shape (P < C, one consumer set) over 4 ranges, pipelined copies inside each."""
+    b, _ = baseline_config(4, scale=0.2)
+    with pkg.FlatAssignor(_multi_devices(pkg, 4)) as f:
+        got = f.assign_batch(*args_of(b))
+    exp = oracle.assign_batch(*args_of(b), threads=_all_threads())
+    assert np.array_equal(got["out_partition"], exp["out_partition"])
+    assert np.array_equal(got["out_consumer_rank"], exp["out_consumer_rank"])
+
+
+def test_multi_device_context_rejects_device_only_calls(pkg):
+    with pkg.FlatAssignor(_multi_devices(pkg, 2)) as f:
+        with pytest.raises(pkg.LagAssignError) as e:
+            f.set_option(pkg.OPT_GROUP, 1)
+        assert e.value.code == -6
+        with pytest.raises(pkg.LagAssignError) as e:
+            f.bind_device_outputs(1 << 20, 1 << 21)
+        assert e.value.code == -6
+
+
+# ---- result exchange of the one-process-per-GPU arrangement ------------------------------------------
+
+def _exchange_roundtrip(pkg, b, world):
+    """pack / unpack on ONE device, standing in for `world` ranks: every shard's results (the oracle's) are narrowed
+    into its slot, the slots are widened; must reproduce the oracle's arrays for the whole batch."""
+    import ctypes
+    import torch
+    from kafka_lag_based_assignor_b200 import distributed as D
+    L = pkg.load_library()
+    exp = oracle.assign_batch(*args_of(b), threads=8)
+    bounds = D.shard_bounds(b["topic_off"], world)
+    counts = D.partition_counts(b["topic_off"], bounds)
+    pw, cw = D.exchange_format(b)
+    slot = int(L.lagassign_exchange_slot_bytes(max(counts), pw, cw))
+    dev = torch.device("cuda", 0)
+    vp = ctypes.c_void_p
+    st = vp(torch.cuda.current_stream().cuda_stream)
+    slots = torch.full((world * max(slot, 16),), 0xAB, dtype=torch.uint8, device=dev)
+    start = 0
+    for r, n in enumerate(counts):
+        dp = torch.from_numpy(exp["out_partition"][start:start + n].copy()).to(dev) if n else torch.zeros(1, dtype=torch.int32, device=dev)
+        dc = torch.from_numpy(exp["out_consumer_rank"][start:start + n].copy()).to(dev) if n else torch.zeros(1, dtype=torch.int32, device=dev)
+        assert L.lagassign_exchange_pack(st, n, vp(dp.data_ptr()), vp(dc.data_ptr()), pw, cw, vp(slots.data_ptr() + r * slot)) == 0
+        start += n
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+    T = len(b["topic_off"]) - 1
+    d_off, d_tc, d_co = t(b["topic_off"], np.int64), t(b["topic_cset"], np.int32), t(b["cset_off"], np.int64)
+    d_cr = t(b["cset_rank"], np.int32) if len(b["cset_rank"]) else torch.zeros(1, dtype=torch.int32, device=dev)
+    d_first = t([lo for lo, _ in bounds] + [T], np.int64)
+    N = int(b["topic_off"][-1])
+    op = torch.full((max(N, 1),), -9, dtype=torch.int32, device=dev)
+    oc = torch.full((max(N, 1),), -9, dtype=torch.int32, device=dev)
+    assert L.lagassign_exchange_unpack(st, T, vp(d_off.data_ptr()), vp(d_tc.data_ptr()), vp(d_co.data_ptr()), vp(d_cr.data_ptr()),
+                                       vp(d_first.data_ptr()), world, vp(slots.data_ptr()), slot, pw, cw,
+                                       vp(op.data_ptr()), vp(oc.data_ptr())) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(op[:N].cpu().numpy(), exp["out_partition"]), (pw, cw)
+    assert np.array_equal(oc[:N].cpu().numpy(), exp["out_consumer_rank"]), (pw, cw)
+    return pw, cw
+
+
+def test_result_exchange_pack_unpack(pkg):
+    rng = np.random.default_rng(61)
+    seen = set()
+    b4, _ = baseline_config(4, scale=0.01)
+    seen.add(_exchange_roundtrip(pkg, b4, 8))                                                      # (1, 0): consumers derived
+    seen.add(_exchange_roundtrip(pkg, random_flat(rng, T=200, pmin=0, pmax=200, C=9, lag_kind="dups", n_sets=3), 3))   # (1, 2), some unsubscribed topics
+    seen.add(_exchange_roundtrip(pkg, random_flat(rng, T=40, pmin=0, pmax=3000, C=5000, lag_kind="u40", n_sets=2, full_sets=True), 2))  # (2, 0)
+    seen.add(_exchange_roundtrip(pkg, random_flat(rng, T=30, pmin=0, pmax=2000, C=50, lag_kind="small", explicit_ids="shuffled", n_sets=2), 5))  # (2, 2)
+    wide = random_flat(rng, T=3, pmin=66000, pmax=70000, C=70000, lag_kind="zero", n_sets=1, full_sets=True)
+    wide["cset_rank"] = (wide["cset_rank"].astype(np.int64) + 100000).astype(np.int32)             # ranks beyond 16 bits
+    seen.add(_exchange_roundtrip(pkg, wide, 2))                                                    # (4, 0)
+    mixed = random_flat(rng, T=4, pmin=66000, pmax=70000, C=300, lag_kind="zero", n_sets=1, full_sets=True)
+    mixed["cset_rank"] = (mixed["cset_rank"].astype(np.int64) * 300).astype(np.int32)
+    seen.add(_exchange_roundtrip(pkg, mixed, 3))                                                   # (4, 4)
+    assert {(1, 0), (1, 2), (2, 0), (2, 2), (4, 0), (4, 4)} <= seen, seen
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_nccl_gather_matches_oracle(pkg, world):
+    """torchrun, one process per GPU: kernels -> narrow -> NCCL all-gather -> widen; every rank compares BOTH
+    gathered arrays of the whole batch with the oracle (tests/dist_gpu_worker.py). Needs `world` GPUs."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = 29500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(os.path.dirname(os.path.abspath(__file__)), "dist_gpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("-> ok") == 4 * world, r.stdout
+
+
 # ---- remaining C-ABI entry points -------------------------------------------------------------------
 
 def test_profile_option_and_stats(pkg):

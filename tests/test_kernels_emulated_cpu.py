@@ -253,3 +253,11 @@ def test_radix_certificate_catches_unordered_atomics(emu_radix, monkeypatch):
         exp = oracle.assign_batch(*args_of(b), threads=4)
         assert np.array_equal(op, exp["out_partition"]) and np.array_equal(oc, exp["out_consumer_rank"])
     assert caught > 0, "host threads never reordered same-address atomics?"
+
+
+def test_radix_path_more_than_8192_consumers_and_more_partitions(emu_radix):
+    """P > C > FILL_CTA_MAX_C (8192): the round fill runs in a global-memory workspace (cta_round_fill_any).
+    Round 1 rejected this shape with LAGASSIGN_ERR_UNSUPPORTED."""
+    rng = np.random.default_rng(91)
+    b = uniform_batch(1, 9000 * 2 + 77, 9000, rng.integers(0, 1 << 30, size=9000 * 2 + 77, dtype=np.int64))
+    check(emu_radix, b, True, radix_min_p=0)
