@@ -22,6 +22,9 @@ final class NativeLagAssign {
     /** lagassign_create: returns the context handle; throws IllegalStateException when no GPU is usable. */
     static native long create(int device);
 
+    /** lagassign_create_multi: one context that shards the topics of every call over the listed devices. */
+    static native long createMulti(int[] devices);
+
     static native void destroy(long ctx);
 
     /** lagassign_host_alloc wrapped by NewDirectByteBuffer. */
@@ -38,4 +41,17 @@ final class NativeLagAssign {
                                    long nTopics, ByteBuffer topicOff, ByteBuffer lag, ByteBuffer partition,
                                    ByteBuffer topicCset, long nCsets, ByteBuffer csetOff, ByteBuffer csetRank,
                                    ByteBuffer outPartition, ByteBuffer outConsumerRank);
+
+    /**
+     * The same call fed with raw offsets instead of lags (lagassign_upload_offsets + execute + download):
+     * computePartitionLag of LagBasedPartitionAssignor.java:376-404 runs on the device.
+     * {@code hasCommitted} holds one byte per partition (committed metadata != null, :384);
+     * {@code resetLatest} = auto.offset.reset equalsIgnoreCase "latest" (:391).
+     */
+    static native void assignBatchOffsets(long ctx,
+                                          long nTopics, ByteBuffer topicOff, ByteBuffer partition,
+                                          ByteBuffer topicCset, long nCsets, ByteBuffer csetOff, ByteBuffer csetRank,
+                                          ByteBuffer beginOffset, ByteBuffer endOffset, ByteBuffer committed,
+                                          ByteBuffer hasCommitted, boolean resetLatest,
+                                          ByteBuffer outPartition, ByteBuffer outConsumerRank);
 }

@@ -40,6 +40,19 @@ void Java_com_github_grantneale_kafka_NativeLagAssign_freePinned(JNIEnv *, jclas
 void Java_com_github_grantneale_kafka_NativeLagAssign_assignBatch(JNIEnv *, jclass, jlong, jlong, jobject, jobject, jobject,
                                                                   jobject, jlong, jobject, jobject, jobject, jobject);
 
+jlong Java_com_github_grantneale_kafka_NativeLagAssign_createMulti(JNIEnv *, jclass, jintArray);
+void Java_com_github_grantneale_kafka_NativeLagAssign_assignBatchOffsets(JNIEnv *, jclass, jlong, jlong, jobject, jobject, jobject, jlong,
+                                                                         jobject, jobject, jobject, jobject, jobject, jobject, jboolean,
+                                                                         jobject, jobject);
+
+/* a fake int[]: length, then the elements */
+typedef struct { jsize n; jint v[8]; } fake_int_array;
+static jsize f_GetArrayLength(JNIEnv *env, jarray a) { (void)env; return ((fake_int_array *)a)->n; }
+static void f_GetIntArrayRegion(JNIEnv *env, jintArray a, jsize start, jsize len, jint *buf) {
+    (void)env;
+    memcpy(buf, ((fake_int_array *)a)->v + start, (size_t)len * sizeof(jint));
+}
+
 static jobject wrap(JNIEnv *env, void *p, size_t n) { return f_NewDirectByteBuffer(env, p, (jlong)n); }
 
 int main(int argc, char **argv) {
@@ -49,6 +62,8 @@ int main(int argc, char **argv) {
     table.NewDirectByteBuffer = f_NewDirectByteBuffer;
     table.GetDirectBufferAddress = f_GetDirectBufferAddress;
     table.GetDirectBufferCapacity = f_GetDirectBufferCapacity;
+    table.GetArrayLength = f_GetArrayLength;
+    table.GetIntArrayRegion = f_GetIntArrayRegion;
     JNIEnv env_obj = &table;
     JNIEnv *env = &env_obj;
     const char *mode = argc > 1 ? argv[1] : "nogpu";
@@ -87,6 +102,36 @@ int main(int argc, char **argv) {
         wrap(env, bad_rank, sizeof bad_rank), wrap(env, out_p, sizeof out_p), wrap(env, out_c, sizeof out_c));
     if (strcmp(pending_class, "java/lang/RuntimeException") != 0) { printf("FAIL: expected RuntimeException, got '%s'\n", pending_class); return 1; }
     printf("ok: invalid input throws %s: %s\n", pending_class, pending_msg);
+
+    /* createMulti over {0, 0} (two shards on one GPU) + raw offsets: two topics so that each shard gets one.
+     * LagBasedPartitionAssignorTest.java:21-80 vectors as the offsets of topic A: lags 4444, 0, 0 (latest), and
+     * topic B: begin 1111 end 9999 no commit, reset earliest would give 8888 but this call passes latest -> 0;
+     * committed 5000 of end 9999 -> 4999; committed beyond the end -> 0 (the max() of Main:402). */
+    {
+        fake_int_array devs = {2, {0, 0}};
+        pending_class[0] = 0;
+        jlong mctx = Java_com_github_grantneale_kafka_NativeLagAssign_createMulti(env, NULL, &devs);
+        if (mctx == 0) { printf("FAIL: createMulti: %s: %s\n", pending_class, pending_msg); return 1; }
+        int64_t toff[3] = {0, 3, 6}, coff[2] = {0, 2};
+        int32_t tcs[2] = {0, 0}, cr[2] = {0, 1}, op[6], oc[6];
+        int64_t beg[6] = {1111, 0, 1111, 1111, 0, 0}, end[6] = {9999, 0, 9999, 9999, 9999, 100};
+        int64_t com[6] = {5555, 5555, 0, 0, 5000, 200};
+        uint8_t has[6] = {1, 1, 0, 0, 1, 1};
+        Java_com_github_grantneale_kafka_NativeLagAssign_assignBatchOffsets(
+            env, NULL, mctx, 2, wrap(env, toff, sizeof toff), NULL, wrap(env, tcs, sizeof tcs), 1, wrap(env, coff, sizeof coff),
+            wrap(env, cr, sizeof cr), wrap(env, beg, sizeof beg), wrap(env, end, sizeof end), wrap(env, com, sizeof com),
+            wrap(env, has, sizeof has), 1, wrap(env, op, sizeof op), wrap(env, oc, sizeof oc));
+        if (pending_class[0]) { printf("FAIL: assignBatchOffsets threw %s: %s\n", pending_class, pending_msg); return 1; }
+        /* topic A lags 4444, 0, 0 -> order p0, p1, p2 -> C0, C1, C1 (p2: equal counts, C1 has the smaller total); topic B lags 0, 4999, 0 -> order p1, p0, p2 -> C0, C1, C1 */
+        const int32_t ep[6] = {0, 1, 2, 1, 0, 2}, ec[6] = {0, 1, 1, 0, 1, 1};
+        if (memcmp(op, ep, sizeof ep) || memcmp(oc, ec, sizeof ec)) {
+            printf("FAIL: offsets path got partitions %d %d %d %d %d %d consumers %d %d %d %d %d %d\n",
+                   op[0], op[1], op[2], op[3], op[4], op[5], oc[0], oc[1], oc[2], oc[3], oc[4], oc[5]);
+            return 1;
+        }
+        Java_com_github_grantneale_kafka_NativeLagAssign_destroy(env, NULL, mctx);
+        printf("ok: createMulti + assignBatchOffsets (fused computePartitionLag) through the JNI shim\n");
+    }
 
     jobject pin = Java_com_github_grantneale_kafka_NativeLagAssign_allocPinned(env, NULL, 4096);
     if (!pin || !f_GetDirectBufferAddress(env, pin)) { printf("FAIL: allocPinned\n"); return 1; }

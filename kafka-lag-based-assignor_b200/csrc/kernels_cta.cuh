@@ -161,7 +161,7 @@ k_cta_topics(DevBatch b, const int32_t* __restrict__ list, int n_list) {
         for (int r = 0; r < EPT; ++r) {
             const int m = r * NT + tid;
             const bool live = m < P;
-            key[r] = live ? ((uint64_t)ld_stream(b.lag + off + m) ^ LAG_KEY_MASK) : KEY_SENTINEL;
+            key[r] = live ? ((uint64_t)lag_load<LAG_EITHER>(b, off + m) ^ LAG_KEY_MASK) : KEY_SENTINEL;
             pay[r] = live ? (uint32_t)m : PAY_SENTINEL;
         }
         bool use_tab = false;
@@ -190,7 +190,7 @@ k_cta_topics(DevBatch b, const int32_t* __restrict__ list, int n_list) {
                     const int q = tid * EPT + r;
                     const bool live = q < P;
                     if (live) tab[q] = (uint32_t)k2[r] ^ 0x80000000u;
-                    key[r] = live ? ((uint64_t)b.lag[off + p2[r]] ^ LAG_KEY_MASK) : KEY_SENTINEL;
+                    key[r] = live ? ((uint64_t)lag_load<LAG_EITHER>(b, off + p2[r]) ^ LAG_KEY_MASK) : KEY_SENTINEL;
                     pay[r] = live ? (uint32_t)q : PAY_SENTINEL;
                 }
                 use_tab = true;
@@ -218,7 +218,7 @@ k_cta_topics(DevBatch b, const int32_t* __restrict__ list, int n_list) {
 #pragma unroll
             for (int r = 0; r < EPT; ++r) {
                 const int q = tid * EPT + r;
-                if (q < P) skey[q] = keys_exact ? key[r] : ((uint64_t)b.lag[off + pay[r]] ^ LAG_KEY_MASK);
+                if (q < P) skey[q] = keys_exact ? key[r] : ((uint64_t)lag_load<LAG_EITHER>(b, off + pay[r]) ^ LAG_KEY_MASK);
             }
         }
         __syncthreads();

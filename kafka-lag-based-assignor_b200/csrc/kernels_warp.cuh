@@ -176,7 +176,9 @@ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_c
 
 // PLAIN: the batch has no explicit partition ids and no totals/counts outputs (the common
 // call); the paths for those are compiled out.
-template <int EPT, bool PLAIN>
+// LAGMODE: where the lags come from (types.cuh): with raw offsets, computePartitionLag (Main:376-404) is evaluated
+// right here, as the keys are built, and the lags never exist in memory.
+template <int EPT, bool PLAIN, int LAGMODE>
 __device__ __forceinline__ void warp_topic(const DevBatch& b, int t, WarpScratch& ws) {
     const unsigned lane = lane_id();
     const int64_t off = b.topic_off[t];
@@ -185,18 +187,18 @@ __device__ __forceinline__ void warp_topic(const DevBatch& b, int t, WarpScratch
     const int64_t coff = b.cset_off[s];
     const int64_t C64 = b.cset_off[s + 1] - coff;
     const int32_t* __restrict__ cset = b.cset_rank + coff;
-    const int64_t* __restrict__ lagp = b.lag + off;
+    auto lag_at = [&](int m) -> uint64_t { return (uint64_t)lag_load<LAGMODE>(b, off + m); };
 
     uint64_t key[EPT];
     uint32_t pay[EPT];
     // Coalesced load; which register slot an element lands in does not matter,
     // the payload carries its list position (Main:228 sorts the whole list).
-    const uint64_t ref = (uint64_t)__ldg(lagp) ^ LAG_KEY_MASK;   // element 0 is live (P >= 1)
+    const uint64_t ref = lag_at(0) ^ LAG_KEY_MASK;   // element 0 is live (P >= 1)
 #pragma unroll
     for (int r = 0; r < EPT; ++r) {
         const int m = r * 32 + (int)lane;
         const bool live = m < P;
-        key[r] = live ? ((uint64_t)ld_stream(lagp + m) ^ LAG_KEY_MASK) : ref;
+        key[r] = live ? (lag_at(m) ^ LAG_KEY_MASK) : ref;
         pay[r] = live ? (uint32_t)m : PAY_SENTINEL;
     }
 
@@ -230,7 +232,7 @@ __device__ __forceinline__ void warp_topic(const DevBatch& b, int t, WarpScratch
                     const int i = (int)lane * EPT + r;
                     const bool live = i < P;
                     if (live) ws.part_tab[i] = (uint32_t)k2[r] ^ 0x80000000u;
-                    key[r] = live ? ((uint64_t)lagp[p2[r]] ^ LAG_KEY_MASK) : ref;
+                    key[r] = live ? (lag_at((int)p2[r]) ^ LAG_KEY_MASK) : ref;
                     pay[r] = live ? (uint32_t)i : PAY_SENTINEL;
                 }
                 use_tab = true;
@@ -261,7 +263,7 @@ __device__ __forceinline__ void warp_topic(const DevBatch& b, int t, WarpScratch
 #pragma unroll
         for (int r = 0; r < EPT; ++r) {
             const int i = (int)lane * EPT + r;
-            if (i < P) ws.lag_key[i] = keys_exact ? key[r] : ((uint64_t)lagp[pay[r]] ^ LAG_KEY_MASK);
+            if (i < P) ws.lag_key[i] = keys_exact ? key[r] : (lag_at((int)pay[r]) ^ LAG_KEY_MASK);
         }
     }
     int32_t* __restrict__ outp = b.out_part + off;
@@ -356,7 +358,7 @@ static __device__ __noinline__ void warp_rounds_path(int P, int C, const int32_t
 }
 
 // One warp per topic of `list` (topics with 1 <= P <= 256 and a non-empty consumer set).
-template <bool PLAIN>
+template <bool PLAIN, int LAGMODE>
 __global__ void __launch_bounds__(SMALL_WARPS * 32, LAGASSIGN_WARP_MINBLOCKS)
 k_warp_topics(DevBatch b, const int32_t* __restrict__ list, int n_list) {
     __shared__ WarpScratch scratch[SMALL_WARPS];
@@ -366,10 +368,10 @@ k_warp_topics(DevBatch b, const int32_t* __restrict__ list, int n_list) {
     const int t = list[idx];
     const int P = (int)(b.topic_off[t + 1] - b.topic_off[t]);
     WarpScratch& ws = scratch[warp];
-    if (P <= 32) warp_topic<1, PLAIN>(b, t, ws);
-    else if (P <= 64) warp_topic<2, PLAIN>(b, t, ws);
-    else if (P <= 128) warp_topic<4, PLAIN>(b, t, ws);
-    else warp_topic<8, PLAIN>(b, t, ws);
+    if (P <= 32) warp_topic<1, PLAIN, LAGMODE>(b, t, ws);
+    else if (P <= 64) warp_topic<2, PLAIN, LAGMODE>(b, t, ws);
+    else if (P <= 128) warp_topic<4, PLAIN, LAGMODE>(b, t, ws);
+    else warp_topic<8, PLAIN, LAGMODE>(b, t, ws);
 }
 
 

@@ -42,19 +42,15 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-// elementwise computePartitionLag (LagBasedPartitionAssignor.java:376-404)
+// elementwise computePartitionLag (LagBasedPartitionAssignor.java:376-404); only lagassign_download_lags() launches
+// it (the assignment kernels evaluate lag_from_offsets themselves while building their keys)
 __global__ void __launch_bounds__(256)
 k_compute_lag(int64_t n, const int64_t* __restrict__ begin_off, const int64_t* __restrict__ end_off,
               const int64_t* __restrict__ committed, const uint8_t* __restrict__ has_committed,
               int reset_latest, int64_t* __restrict__ lag) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t end = end_off[i];
-        int64_t next;
-        if (has_committed[i]) next = committed[i];            // Main:384-386
-        else next = reset_latest ? end : begin_off[i];        // Main:391-396
-        const int64_t d = (int64_t)((uint64_t)end - (uint64_t)next);   // Java long '-' wraps
-        lag[i] = d > 0 ? d : 0;                               // Main:402
-    }
+    const LagOffsets o{begin_off, end_off, committed, has_committed, reset_latest};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        lag[i] = lag_from_offsets(o, i);
 }
 
 }  // namespace
@@ -301,6 +297,13 @@ DevBatch make_dev_batch(lagassign_ctx* ctx) {
     DevBatch b{};
     b.topic_off = ctx->d_topic_off.as<int64_t>();
     b.lag = ctx->d_lag.as<int64_t>();
+    if (ctx->has_offsets) {
+        b.offs.begin = ctx->d_begin.as<int64_t>();
+        b.offs.end = ctx->d_end.as<int64_t>();
+        b.offs.committed = ctx->d_committed.as<int64_t>();
+        b.offs.has = ctx->d_hascommitted.as<uint8_t>();
+        b.offs.reset_latest = ctx->reset_latest;
+    }
     b.part = ctx->has_part ? ctx->d_part.as<int32_t>() : nullptr;
     b.topic_cset = ctx->d_topic_cset.as<int32_t>();
     b.cset_off = ctx->d_cset_off.as<int64_t>();
@@ -852,14 +855,9 @@ int lagassign_execute(lagassign_ctx* ctx) {
     DevBatch b = make_dev_batch(ctx);
     const int sms = ctx->sm_count;
 
-    if (ctx->has_offsets && ctx->N > 0) {
-        int grid = (int)std::min<int64_t>((ctx->N + 255) / 256, (int64_t)sms * 16);
-        ProfScope ps(ctx, K_COMPUTE_LAG);
-        k_compute_lag<<<grid, 256, 0, st>>>(ctx->N, ctx->d_begin.as<int64_t>(), ctx->d_end.as<int64_t>(),
-                                            ctx->d_committed.as<int64_t>(), ctx->d_hascommitted.as<uint8_t>(),
-                                            ctx->reset_latest, ctx->d_lag.as<int64_t>());
-        ++launches;
-    }
+    // With raw offsets (lagassign_upload_offsets) there is no separate lag kernel: computePartitionLag (Main:376-404)
+    // is evaluated inside the kernels below as they build their sort keys (k_warp_topics<.., LAG_OFFS>,
+    // k_cta_topics, k_big_hist).
     if (ctx->want_totals && ctx->total_tc > 0) {
         CUDA_TRY(ctx, cudaMemsetAsync(b.out_total, 0, (size_t)ctx->total_tc * sizeof(int64_t), st));
         CUDA_TRY(ctx, cudaMemsetAsync(b.out_count, 0, (size_t)ctx->total_tc * sizeof(int32_t), st));
@@ -928,7 +926,7 @@ int lagassign_execute(lagassign_ctx* ctx) {
         }
         {
             ProfScope ps(ctx, K_HIST);
-            launch_big_hist(bt, b.lag, b.part, sms, st);
+            launch_big_hist(bt, b.lag, b.offs, b.part, sms, st);
             ++launches;
         }
         {
@@ -1104,6 +1102,14 @@ int lagassign_download_lags(lagassign_ctx* ctx, int64_t* lag_out) {
     if (!lag_out) return fail(ctx, LAGASSIGN_ERR_ARG, "lag_out is NULL");
     if (!ctx->executed) return fail(ctx, LAGASSIGN_ERR_STATE, "download_lags() before execute()");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (ctx->has_offsets && ctx->N) {
+        // The kernels compute the lags on the fly and never store them (except for radix-path topics): materialise
+        // them here, for this check only, with the same formula (lag_from_offsets).
+        const int grid = (int)std::min<int64_t>((ctx->N + 255) / 256, (int64_t)ctx->sm_count * 16);
+        k_compute_lag<<<grid, 256, 0, ctx->stream>>>(ctx->N, ctx->d_begin.as<int64_t>(), ctx->d_end.as<int64_t>(),
+                                                     ctx->d_committed.as<int64_t>(), ctx->d_hascommitted.as<uint8_t>(),
+                                                     ctx->reset_latest, ctx->d_lag.as<int64_t>());
+    }
     if (ctx->N) CUDA_TRY(ctx, cudaMemcpyAsync(lag_out, ctx->d_lag.p, (size_t)ctx->N * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return LAGASSIGN_OK;

@@ -70,10 +70,11 @@ void launch_big_order_check(const BigTopics& bt, const int32_t* part, int sms, c
     k_big_order_check<<<std::min(bt.n_tiles, sms * 8), 256, 0, st>>>(bt, part);
 }
 
-void launch_big_hist(const BigTopics& bt, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st) {
+void launch_big_hist(const BigTopics& bt, const int64_t* lag, const LagOffsets& offs, const int32_t* part, int sms, cudaStream_t st) {
     const int grid = std::min(bt.n_tiles, sms * 6);
-    if (part) k_big_hist<true><<<grid, RT_THREADS, 0, st>>>(bt, lag, part);
-    else k_big_hist<false><<<grid, RT_THREADS, 0, st>>>(bt, lag, nullptr);
+    int64_t* lg = const_cast<int64_t*>(lag);   // written only with raw offsets (the context's own buffer)
+    if (part) k_big_hist<true><<<grid, RT_THREADS, 0, st>>>(bt, lg, offs, part);
+    else k_big_hist<false><<<grid, RT_THREADS, 0, st>>>(bt, lg, offs, nullptr);
 }
 
 void launch_big_scan(const BigTopics& bt, int first_pass, cudaStream_t st) {

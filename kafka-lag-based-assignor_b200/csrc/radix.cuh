@@ -50,7 +50,7 @@ k_big_order_check(BigTopics bt, const int32_t* __restrict__ part) {
 // ---- 2. digit histograms of every pass, per topic -------------------------------------
 template <bool HAS_PART>
 __global__ void __launch_bounds__(RT_THREADS)
-k_big_hist(BigTopics bt, const int64_t* __restrict__ lag, const int32_t* __restrict__ part) {
+k_big_hist(BigTopics bt, int64_t* __restrict__ lag, LagOffsets offs, const int32_t* __restrict__ part) {
     __shared__ uint32_t h[N_PASS][256];
     for (int i = threadIdx.x; i < N_PASS * 256; i += blockDim.x) (&h[0][0])[i] = 0;
     __syncthreads();
@@ -74,20 +74,27 @@ k_big_hist(BigTopics bt, const int64_t* __restrict__ lag, const int32_t* __restr
         if (b != cur_b) { flush(cur_b); cur_b = b; }
         const int64_t P = bt.P[b];
         const int64_t t0 = (int64_t)(g - bt.tile0[b]) * RT_TILE;
-        const int64_t* lg = lag + bt.off[b];
+        int64_t* lg = lag + bt.off[b];
         const bool tie = HAS_PART && bt.need_tie[b] != 0;
+        // With raw offsets (lagassign_upload_offsets) this is where computePartitionLag (Main:376-404) runs for the
+        // radix path: the lag is computed as the key is built and stored for the later passes, which read `lag`.
+        const bool from_offsets = offs.end != nullptr;
         // A digit on which all keys of the tile agree (the high bytes of small lags, every byte of an idle
         // topic) is counted with ONE atomic for the tile instead of one same-address atomic per element
         // (B200: config 5, all-zero lags, 0.218 -> 0.126 ms; uniform 63-bit keys pay 14 % for the test).
         __shared__ uint32_t red[RT_WARPS][4];
         uint64_t key[RT_IPT];
         uint64_t o = 0, a = ~0ull;
-#pragma unroll
         uint8_t* dg = bt.dig + bt.boff[b];
+#pragma unroll
         for (int k = 0; k < RT_IPT; ++k) {
             const int64_t e = t0 + k * RT_THREADS + threadIdx.x;
-            key[k] = (e < P) ? ((uint64_t)ld_stream(lg + e) ^ LAG_KEY_MASK) : 0ull;
+            key[k] = 0ull;
             if (e < P) {
+                int64_t lv;
+                if (from_offsets) { lv = lag_from_offsets(offs, bt.off[b] + e); lg[e] = lv; }
+                else lv = ld_stream(lg + e);
+                key[k] = (uint64_t)lv ^ LAG_KEY_MASK;
                 o |= key[k]; a &= key[k];
                 dg[e] = (uint8_t)key[k];      // digit of the first lag pass, for its counting kernel (4a) when it is the topic's first pass
             }

@@ -7,9 +7,21 @@
 
 namespace lagassign {
 
+// Raw offsets of the fused lag computation (lagassign_upload_offsets; reference computePartitionLag,
+// LagBasedPartitionAssignor.java:376-404). end == nullptr: the batch carries lags.
+struct LagOffsets {
+    const int64_t* begin;       // [N]
+    const int64_t* end;         // [N]
+    const int64_t* committed;   // [N]
+    const uint8_t* has;         // [N]
+    int reset_latest;
+};
+
 struct DevBatch {
     const int64_t* topic_off;   // [T+1]
-    const int64_t* lag;         // [N]
+    const int64_t* lag;         // [N]  (with offsets: the context's own buffer; only the radix path's topics are
+                                //       materialised there, by k_big_hist)
+    LagOffsets offs;            // see above
     const int32_t* part;        // [N] or null
     const int32_t* topic_cset;  // [T]
     const int64_t* cset_off;    // [S+1]
@@ -20,6 +32,25 @@ struct DevBatch {
     int64_t* out_total;         // null unless enabled
     int32_t* out_count;
 };
+
+// Main:376-404 for element e: max(end - (has ? committed : (latest ? end : begin)), 0), wrapping subtract
+__device__ __forceinline__ int64_t lag_from_offsets(const LagOffsets& o, int64_t e) {
+    const int64_t end = ld_stream(o.end + e);
+    int64_t next;
+    if (o.has[e]) next = ld_stream(o.committed + e);          // Main:384-386
+    else next = o.reset_latest ? end : ld_stream(o.begin + e);   // Main:391-396
+    const int64_t d = (int64_t)((uint64_t)end - (uint64_t)next);
+    return d > 0 ? d : 0;                                        // Main:402
+}
+// Where a kernel's lags come from: LAG_PLAIN = the lag array, LAG_OFFS = computed from the raw offsets while the
+// sort keys are built (no lag array exists), LAG_EITHER = decided at run time (uniform over the grid).
+enum : int { LAG_PLAIN = 0, LAG_OFFS = 1, LAG_EITHER = 2 };
+template <int MODE>
+__device__ __forceinline__ int64_t lag_load(const DevBatch& b, int64_t e) {
+    if constexpr (MODE == LAG_PLAIN) return ld_stream(b.lag + e);
+    else if constexpr (MODE == LAG_OFFS) return lag_from_offsets(b.offs, e);
+    else return b.offs.end != nullptr ? lag_from_offsets(b.offs, e) : ld_stream(b.lag + e);
+}
 
 #ifndef LAGASSIGN_RT_THREADS
 #define LAGASSIGN_RT_THREADS 256
@@ -108,7 +139,7 @@ constexpr int N_CTA_CLASSES = 4;   // topics of 257..512 / ..1024 / ..2048 / ..4
 inline int cta_class_of(int64_t P) { return P <= 512 ? 0 : P <= 1024 ? 1 : P <= 2048 ? 2 : 3; }
 void launch_cta_topics(const DevBatch& b, const int32_t* list, int n, int cls, int sms, cudaStream_t st);
 void launch_big_order_check(const BigTopics& bt, const int32_t* part, int sms, cudaStream_t st);
-void launch_big_hist(const BigTopics& bt, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st);
+void launch_big_hist(const BigTopics& bt, const int64_t* lag, const LagOffsets& offs, const int32_t* part, int sms, cudaStream_t st);
 void launch_big_scan(const BigTopics& bt, int first_pass, cudaStream_t st);
 void launch_big_tile_hist(const BigTopics& bt, int pass, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st);
 void launch_big_pass_scans(const BigTopics& bt, int pass, cudaStream_t st);   // two kernels

@@ -15,6 +15,7 @@
 using namespace lagassign;
 
 namespace {
+LagOffsets g_offs{};   // raw offsets for the NEXT emu_assign_big call (k_big_hist then computes and stores the lags)
 template <class K> void launch(int grid, int block, K k) { if (grid > 0) emu::launch(grid, block, k); }
 }
 
@@ -22,10 +23,17 @@ template <class K> void launch(int grid, int block, K k) { if (grid > 0) emu::la
 // path (the product uses it above 4096; smaller thresholds exercise short last tiles and one-tile topics).
 // `sms` scales the grids like the SM count does in the product (small values force grid-stride loops).
 // Returns the number of topics processed, -1 for an unsupported shape.
+extern "C" void emu_big_set_offsets(const int64_t* begin, const int64_t* end, const int64_t* committed,
+                                    const uint8_t* has, int reset_latest) {
+    g_offs = LagOffsets{begin, end, committed, has, reset_latest};
+}
+
 extern "C" int emu_assign_big(int64_t n_topics, const int64_t* topic_off, const int64_t* lag, const int32_t* partition,
                               const int32_t* topic_cset, const int64_t* cset_off, const int32_t* cset_rank,
                               const int64_t* tc_off, int32_t* out_partition, int32_t* out_consumer_rank,
                               int64_t* out_total, int32_t* out_count, int64_t min_big_p, int sms, int* passes_run_out) {
+    const LagOffsets offs = g_offs;
+    g_offs = LagOffsets{};
     std::vector<int32_t> bt_topic, bt_tile0, tile_bt, l_fill, bt_seg0, seg_bt;
     std::vector<int64_t> bt_off, bt_P, bt_boff, fill_ws_off;
     int64_t fill_ws_elems = 0;
@@ -73,7 +81,7 @@ extern "C" int emu_assign_big(int64_t n_topics, const int64_t* topic_off, const 
     int64_t* lag_base = lag_store.data() + 2;
     if ((reinterpret_cast<uintptr_t>(lag_base) & 15u) != 0) ++lag_base;          // 16-byte aligned
     lag_base += lag_shift;                                                       // or deliberately only 8-byte aligned
-    std::copy(lag, lag + n_total, lag_base);
+    if (offs.end == nullptr) std::copy(lag, lag + n_total, lag_base);   // with raw offsets the buffer starts zeroed
     lag = lag_base;
     std::vector<uint32_t> ghist((size_t)B * N_PASS * 256, 0), gbase((size_t)B * N_PASS * 256, 0);
     std::vector<int8_t> sel((size_t)B * (3 * N_PASS + 2), 0);
@@ -114,8 +122,8 @@ extern "C" int emu_assign_big(int64_t n_topics, const int64_t* topic_off, const 
     const int first_pass = has_part ? 0 : N_TIE_PASS;
     const int n_tiles = (int)tiles;
     if (has_part) launch(std::min(n_tiles, sms * 8), 256, [&] { k_big_order_check(bt, partition); });
-    if (has_part) launch(std::min(n_tiles, sms * 6), RT_THREADS, [&] { k_big_hist<true>(bt, lag, partition); });
-    else launch(std::min(n_tiles, sms * 6), RT_THREADS, [&] { k_big_hist<false>(bt, lag, nullptr); });
+    if (has_part) launch(std::min(n_tiles, sms * 6), RT_THREADS, [&] { k_big_hist<true>(bt, lag_base, offs, partition); });
+    else launch(std::min(n_tiles, sms * 6), RT_THREADS, [&] { k_big_hist<false>(bt, lag_base, offs, nullptr); });
     launch(B, 256, [&] { k_big_scan(bt, first_pass); });
     for (int p = first_pass; p < N_PASS; ++p) {
         if (bt.pass_any[p] == 0) continue;

@@ -309,11 +309,7 @@ def test_argument_errors(pkg):
         with pytest.raises(pkg.LagAssignError) as e:   # execute before upload
             f.execute()
         assert e.value.code == -4
-        # more consumers than the multi-round fill covers -> explicit error, no fallback
-        P, C = 10000, 9000
-        with pytest.raises(pkg.LagAssignError) as e:
-            f.assign_batch([0, P], np.zeros(P, np.int64), None, [0], [0, C], np.arange(C, dtype=np.int32))
-        assert e.value.code == -6
+        # (P > C > 8192 was LAGASSIGN_ERR_UNSUPPORTED in round 1; it is computed now: test_more_than_8192_consumers_*)
 
 
 def test_fused_lag_computation(pkg):

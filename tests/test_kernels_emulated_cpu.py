@@ -261,3 +261,59 @@ def test_radix_path_more_than_8192_consumers_and_more_partitions(emu_radix):
     rng = np.random.default_rng(91)
     b = uniform_batch(1, 9000 * 2 + 77, 9000, rng.integers(0, 1 << 30, size=9000 * 2 + 77, dtype=np.int64))
     check(emu_radix, b, True, radix_min_p=0)
+
+
+# ---- fused computePartitionLag (Main:376-404): the kernels build their keys from raw offsets -------------------
+
+def _offsets_for(rng, n):
+    end = rng.integers(0, 1 << 40, size=n, dtype=np.int64)
+    begin = (end * rng.random(n)).astype(np.int64)
+    committed = rng.integers(0, 1 << 40, size=n, dtype=np.int64)      # sometimes beyond end -> clamped to 0
+    has = (rng.random(n) < 0.7).astype(np.uint8)
+    # a few wrapping cases: end - committed overflows int64 and wraps like Java's long subtraction
+    k = min(n, 5)
+    end[:k] = np.iinfo(np.int64).max - np.arange(k)
+    committed[:k] = -(1 << 62) - np.arange(k)
+    has[:k] = 1
+    return begin, end, committed, has
+
+
+def _lags_of(begin, end, committed, has, latest):
+    return np.array([oracle.compute_partition_lag(int(committed[i]) if has[i] else None, int(begin[i]), int(end[i]),
+                                                  "latest" if latest else "earliest") for i in range(len(end))], dtype=np.int64)
+
+
+@pytest.mark.parametrize("latest", [0, 1])
+@pytest.mark.parametrize("ids,totals", [(None, False), ("shuffled", True)])
+def test_onchip_kernels_from_raw_offsets(emu, latest, ids, totals):
+    """k_warp_topics<PLAIN, LAG_OFFS>, k_warp_topics<false, LAG_EITHER> and k_cta_topics evaluate the lag formula
+    themselves: the lag array handed to them is poisoned."""
+    rng = np.random.default_rng(5 + latest)
+    b = random_flat(rng, T=14, pmin=1, pmax=700, C=40, lag_kind="u40", explicit_ids=ids, n_sets=2)
+    n = len(b["lag"])
+    begin, end, committed, has = _offsets_for(rng, n)
+    exp_lag = _lags_of(begin, end, committed, has, latest)
+    poisoned = dict(b, lag=np.full(n, 0x5555555555555555, np.int64))
+    emu.emu_onchip_set_offsets.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int]
+    emu.emu_onchip_set_offsets(_ptr(begin), _ptr(end), _ptr(committed), _ptr(has), latest)
+    got = run_emulated(emu, poisoned, totals)
+    exp = oracle.assign_batch(*args_of(dict(b, lag=exp_lag)), want_totals=True, threads=4)
+    assert np.array_equal(got["out_partition"], exp["out_partition"])
+    assert np.array_equal(got["out_consumer_rank"], exp["out_consumer_rank"])
+    if totals:
+        assert np.array_equal(got["out_total"], exp["out_total"]) and np.array_equal(got["out_count"], exp["out_count"])
+
+
+def test_radix_path_from_raw_offsets(emu_radix):
+    """k_big_hist computes the lags from the offsets while it builds the keys and stores them for the later passes."""
+    rng = np.random.default_rng(17)
+    b = random_flat(rng, T=2, pmin=4200, pmax=7000, C=900, lag_kind="u40", n_sets=1)
+    n = len(b["lag"])
+    begin, end, committed, has = _offsets_for(rng, n)
+    exp_lag = _lags_of(begin, end, committed, has, 0)
+    emu_radix.emu_big_set_offsets.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int]
+    emu_radix.emu_big_set_offsets(_ptr(begin), _ptr(end), _ptr(committed), _ptr(has), 0)
+    got, _ = run_emulated_radix(emu_radix, dict(b, lag=np.full(n, -1, np.int64)), True, 4096)
+    exp = oracle.assign_batch(*args_of(dict(b, lag=exp_lag)), want_totals=True, threads=4)
+    for k in ("out_partition", "out_consumer_rank", "out_total", "out_count"):
+        assert np.array_equal(got[k], exp[k]), k
