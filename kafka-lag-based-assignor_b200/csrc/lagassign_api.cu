@@ -55,10 +55,10 @@ k_compute_lag(int64_t n, const int64_t* __restrict__ begin_off, const int64_t* _
 
 }  // namespace
 
-enum KernelKind { K_COMPUTE_LAG = 0, K_UNASSIGNED, K_WARP, K_CTA, K_ORDER, K_HIST, K_SCAN, K_TILE_HIST, K_PASS_SCANS,
+enum KernelKind { K_COMPUTE_LAG = 0, K_UNASSIGNED, K_WARP, K_CTA, K_ORDER, K_RANGE, K_SCAN, K_TILE_HIST, K_PASS_SCANS,
                   K_SCATTER, K_VERIFY, K_FINALIZE, K_FILL, K_GROUP, K_KINDS };
 static const char* const kKernelNames[K_KINDS] = {"k_compute_lag", "k_unassigned_topics", "k_warp_topics",
-                                                  "k_cta_topics", "k_big_order_check", "k_big_hist",
+                                                  "k_cta_topics", "k_big_order_check", "k_big_range",
                                                   "k_big_scan", "k_big_tile_hist", "k_big_seg_scan+k_big_topic_scan",
                                                   "k_big_scatter", "k_big_verify", "k_big_finalize", "k_big_fill",
                                                   "k_group_keys+finalize+offsets"};
@@ -99,7 +99,7 @@ struct lagassign_ctx {
     int64_t fill_ws_elems = 0;
     // radix workspaces
     DevBuf d_fill_ws_off, d_fill_ws_key, d_fill_ws_idx;
-    DevBuf d_keyA, d_keyB, d_payA, d_payB, d_dig, d_ghist, d_gbase, d_sel, d_need_tie, d_status, d_ticket;
+    DevBuf d_keyA, d_keyB, d_payA, d_payB, d_dig, d_range, d_pass_rec, d_sel, d_need_tie, d_status, d_ticket;
     // outputs
     DevBuf d_out_part, d_out_cons, d_out_total, d_out_count;
     int32_t* bound_part = nullptr;
@@ -329,8 +329,8 @@ BigTopics make_big(lagassign_ctx* ctx) {
     bt.tile_desc = ctx->d_tile_desc.as<int4>();
     bt.keyA = ctx->d_keyA.as<uint64_t>(); bt.keyB = ctx->d_keyB.as<uint64_t>();
     bt.payA = ctx->d_payA.as<uint32_t>(); bt.payB = ctx->d_payB.as<uint32_t>();
-    bt.ghist = ctx->d_ghist.as<uint32_t>();
-    bt.gbase = ctx->d_gbase.as<uint32_t>();
+    bt.range = ctx->d_range.as<uint64_t>();
+    bt.pass_rec = ctx->d_pass_rec.as<uint32_t>();
     int8_t* sel = ctx->d_sel.as<int8_t>();
     bt.sel_src = sel;
     bt.sel_dst = sel + (size_t)ctx->n_big * N_PASS;
@@ -493,9 +493,8 @@ int do_upload(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_off
         CUDA_TRY(ctx, ctx->d_keyB.ensure(nb * sizeof(uint64_t)));
         CUDA_TRY(ctx, ctx->d_payA.ensure(nb * sizeof(uint32_t)));
         CUDA_TRY(ctx, ctx->d_payB.ensure(nb * sizeof(uint32_t)));
-        const size_t hb = (size_t)ctx->n_big * N_PASS * 256 * sizeof(uint32_t);
-        CUDA_TRY(ctx, ctx->d_ghist.ensure(hb));
-        CUDA_TRY(ctx, ctx->d_gbase.ensure(hb));
+        CUDA_TRY(ctx, ctx->d_range.ensure((size_t)ctx->n_big * 4 * sizeof(uint64_t)));
+        CUDA_TRY(ctx, ctx->d_pass_rec.ensure((size_t)ctx->n_tiles * N_PASS * sizeof(uint32_t)));
         CUDA_TRY(ctx, ctx->d_sel.ensure((size_t)ctx->n_big * (3 * N_PASS + 2)));
         CUDA_TRY(ctx, ctx->d_dig.ensure(nb));
         CUDA_TRY(ctx, ctx->d_fill_ws_key.ensure(std::max<size_t>((size_t)ctx->fill_ws_elems, 1) * sizeof(uint64_t)));
@@ -782,7 +781,7 @@ void lagassign_destroy(lagassign_ctx* ctx) {
                       &ctx->d_hascommitted, &ctx->d_list_warp, &ctx->d_list_cta[0], &ctx->d_list_cta[1], &ctx->d_list_cta[2], &ctx->d_list_cta[3], &ctx->d_list_none,
                       &ctx->d_list_fill, &ctx->d_bt_topic, &ctx->d_bt_off, &ctx->d_bt_P, &ctx->d_bt_boff,
                       &ctx->d_bt_tile0, &ctx->d_tile_bt, &ctx->d_keyA, &ctx->d_keyB, &ctx->d_payA,
-                      &ctx->d_payB, &ctx->d_dig, &ctx->d_fill_ws_off, &ctx->d_fill_ws_key, &ctx->d_fill_ws_idx, &ctx->d_ghist, &ctx->d_gbase, &ctx->d_sel, &ctx->d_need_tie,
+                      &ctx->d_payB, &ctx->d_dig, &ctx->d_fill_ws_off, &ctx->d_fill_ws_key, &ctx->d_fill_ws_idx, &ctx->d_range, &ctx->d_pass_rec, &ctx->d_sel, &ctx->d_need_tie,
                       &ctx->d_status, &ctx->d_seg_total, &ctx->d_bt_seg0, &ctx->d_seg_bt, &ctx->d_tile_desc, &ctx->d_ticket, &ctx->d_out_part, &ctx->d_out_cons,
                       &ctx->d_out_total, &ctx->d_out_count};
     for (DevBuf* b : bufs) b->release();
@@ -857,7 +856,7 @@ int lagassign_execute(lagassign_ctx* ctx) {
 
     // With raw offsets (lagassign_upload_offsets) there is no separate lag kernel: computePartitionLag (Main:376-404)
     // is evaluated inside the kernels below as they build their sort keys (k_warp_topics<.., LAG_OFFS>,
-    // k_cta_topics, k_big_hist).
+    // k_cta_topics, k_big_range).
     if (ctx->want_totals && ctx->total_tc > 0) {
         CUDA_TRY(ctx, cudaMemsetAsync(b.out_total, 0, (size_t)ctx->total_tc * sizeof(int64_t), st));
         CUDA_TRY(ctx, cudaMemsetAsync(b.out_count, 0, (size_t)ctx->total_tc * sizeof(int32_t), st));
@@ -914,8 +913,7 @@ int lagassign_execute(lagassign_ctx* ctx) {
     }
     if (ctx->n_big > 0) {
         BigTopics bt = make_big(ctx);
-        const size_t hb = (size_t)ctx->n_big * N_PASS * 256 * sizeof(uint32_t);
-        CUDA_TRY(ctx, cudaMemsetAsync(bt.ghist, 0, hb, st));
+        CUDA_TRY(ctx, cudaMemsetAsync(bt.range, 0, (size_t)ctx->n_big * 4 * sizeof(uint64_t), st));
         CUDA_TRY(ctx, cudaMemsetAsync(bt.need_tie, 0, (size_t)ctx->n_big * sizeof(int32_t), st));
         CUDA_TRY(ctx, cudaMemsetAsync(bt.ticket, 0, RT_TICKET_WORDS * sizeof(uint32_t), st));
         const int first_pass = ctx->has_part ? 0 : N_TIE_PASS;
@@ -925,8 +923,8 @@ int lagassign_execute(lagassign_ctx* ctx) {
             ++launches;
         }
         {
-            ProfScope ps(ctx, K_HIST);
-            launch_big_hist(bt, b.lag, b.offs, b.part, sms, st);
+            ProfScope ps(ctx, K_RANGE);
+            launch_big_range(bt, b.lag, b.offs, b.part, sms, st);
             ++launches;
         }
         {
@@ -958,16 +956,18 @@ int lagassign_execute(lagassign_ctx* ctx) {
             launches += 4;
             any_pass = true;
         }
-        if (any_pass && !ctx->exact_rank) {
-            // certificate of the fast ranking (radix.cuh 4d/4e); its verdict is read at the end of this call
+        // certificate of the fast ranking (radix.cuh 4d/4e); its verdict is read at the end of this call. It rides on
+        // the finalize kernel's read of the sorted sequence; the sort-only mode (grouping) has no finalize.
+        const bool certify = any_pass && !ctx->exact_rank;
+        if (certify && ctx->sort_only) {
             ProfScope ps(ctx, K_VERIFY);
             launch_big_verify(bt, b.part, sms, st);
             ++launches;
-            verify_pending = true;
         }
+        verify_pending = certify;
         if (!ctx->sort_only) {
             ProfScope ps(ctx, K_FINALIZE);
-            launch_big_finalize(bt, b, sms, st);
+            launch_big_finalize(bt, b, certify, sms, st);
             ++launches;
         }
         if (ctx->n_fill > 0 && !ctx->sort_only) {

@@ -70,11 +70,11 @@ void launch_big_order_check(const BigTopics& bt, const int32_t* part, int sms, c
     k_big_order_check<<<std::min(bt.n_tiles, sms * 8), 256, 0, st>>>(bt, part);
 }
 
-void launch_big_hist(const BigTopics& bt, const int64_t* lag, const LagOffsets& offs, const int32_t* part, int sms, cudaStream_t st) {
-    const int grid = std::min(bt.n_tiles, sms * 6);
+void launch_big_range(const BigTopics& bt, const int64_t* lag, const LagOffsets& offs, const int32_t* part, int sms, cudaStream_t st) {
+    const int grid = std::min(bt.n_tiles, sms * 8);
     int64_t* lg = const_cast<int64_t*>(lag);   // written only with raw offsets (the context's own buffer)
-    if (part) k_big_hist<true><<<grid, RT_THREADS, 0, st>>>(bt, lg, offs, part);
-    else k_big_hist<false><<<grid, RT_THREADS, 0, st>>>(bt, lg, offs, nullptr);
+    if (part) k_big_range<true><<<grid, RT_THREADS, 0, st>>>(bt, lg, offs, part);
+    else k_big_range<false><<<grid, RT_THREADS, 0, st>>>(bt, lg, offs, nullptr);
 }
 
 void launch_big_scan(const BigTopics& bt, int first_pass, cudaStream_t st) {
@@ -107,9 +107,12 @@ void launch_big_verify(const BigTopics& bt, const int32_t* part, int sms, cudaSt
     k_big_verify<<<std::min(bt.n_tiles, sms * 8), 256, 0, st>>>(bt, part);
 }
 
-void launch_big_finalize(const BigTopics& bt, const DevBatch& b, int sms, cudaStream_t st) {
-    k_big_finalize<<<std::min(bt.n_tiles, sms * 8), 256, 0, st>>>(bt, b.lag, b.part, b.topic_cset, b.cset_off, b.cset_rank,
-                                                                 b.tc_off, b.out_part, b.out_cons, b.out_total, b.out_count);
+void launch_big_finalize(const BigTopics& bt, const DevBatch& b, bool verify, int sms, cudaStream_t st) {
+    const int grid = std::min(bt.n_tiles, sms * 8);
+    if (verify) k_big_finalize<true><<<grid, 256, 0, st>>>(bt, b.lag, b.part, b.topic_cset, b.cset_off, b.cset_rank,
+                                                          b.tc_off, b.out_part, b.out_cons, b.out_total, b.out_count);
+    else k_big_finalize<false><<<grid, 256, 0, st>>>(bt, b.lag, b.part, b.topic_cset, b.cset_off, b.cset_rank,
+                                                     b.tc_off, b.out_part, b.out_cons, b.out_total, b.out_count);
 }
 
 void launch_big_fill(const BigTopics& bt, const int32_t* fill_list, int n_fill, const DevBatch& b, int sms, cudaStream_t st) {

@@ -47,27 +47,45 @@ k_big_order_check(BigTopics bt, const int32_t* __restrict__ part) {
     }
 }
 
-// ---- 2. digit histograms of every pass, per topic -------------------------------------
+// ---- 2. value range of every topic: which digit passes can be skipped ----------------------
+// A pass cannot reorder a topic whose elements all carry the same digit. That is decided from the
+// bitwise OR and AND of the topic's keys (a digit is constant iff OR and AND agree on its eight bits),
+// so this kernel is one streaming read of the lags (8 B/element) with no histogram: the digit bases of
+// a pass come from that pass's own per-tile counts (4a-4c). An earlier version kept eight shared-memory
+// histograms here (one atomic per element and digit): 0.47 ms for 2^26 elements, 57 % of BASELINE
+// config 5's step. Also written here: the digit byte of the first lag pass (input of its counting
+// kernel 4a) and, with raw offsets, the lags themselves (computePartitionLag, Main:376-404, fused).
+//   range[b] = { OR of keys, OR of ~keys (= ~AND), OR of id keys, OR of ~id keys }   (zero-initialised)
 template <bool HAS_PART>
 __global__ void __launch_bounds__(RT_THREADS)
-k_big_hist(BigTopics bt, int64_t* __restrict__ lag, LagOffsets offs, const int32_t* __restrict__ part) {
-    __shared__ uint32_t h[N_PASS][256];
-    for (int i = threadIdx.x; i < N_PASS * 256; i += blockDim.x) (&h[0][0])[i] = 0;
-    __syncthreads();
-    // contiguous range of tiles per CTA so the shared histogram is flushed rarely
+k_big_range(BigTopics bt, int64_t* __restrict__ lag, LagOffsets offs, const int32_t* __restrict__ part) {
+    __shared__ unsigned long long red[RT_WARPS][4];
+    // contiguous range of tiles per CTA so that a topic's words are touched by few atomics
     const int per = (bt.n_tiles + gridDim.x - 1) / gridDim.x;
     const int g0 = blockIdx.x * per, g1 = min(bt.n_tiles, g0 + per);
+    const bool from_offsets = offs.end != nullptr;
+    uint64_t k_or = 0, k_nor = 0, i_or = 0, i_nor = 0;
     int cur_b = -1;
     auto flush = [&](int b) {
-        __syncthreads();
-        if (b >= 0) {
-            uint32_t* gh = bt.ghist + (size_t)b * N_PASS * 256;
-            for (int i = threadIdx.x; i < N_PASS * 256; i += blockDim.x) {
-                uint32_t v = (&h[0][0])[i];
-                if (v) { atomicAdd(gh + i, v); (&h[0][0])[i] = 0; }
-            }
+        if (b < 0) return;
+        const uint32_t v[8] = {(uint32_t)k_or, (uint32_t)(k_or >> 32), (uint32_t)k_nor, (uint32_t)(k_nor >> 32),
+                               (uint32_t)i_or, (uint32_t)(i_or >> 32), (uint32_t)i_nor, (uint32_t)(i_nor >> 32)};
+        uint32_t r[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r[q] = __reduce_or_sync(0xffffffffu, v[q]);
+        if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) red[threadIdx.x >> 5][q] = ((unsigned long long)r[2 * q + 1] << 32) | r[2 * q];
         }
         __syncthreads();
+        if (threadIdx.x < 4) {
+            unsigned long long x = 0;
+#pragma unroll
+            for (int w = 0; w < RT_WARPS; ++w) x |= red[w][threadIdx.x];
+            if (x) atomicOr(reinterpret_cast<unsigned long long*>(bt.range) + (size_t)b * 4 + threadIdx.x, x);
+        }
+        __syncthreads();
+        k_or = k_nor = i_or = i_nor = 0;
     };
     for (int g = g0; g < g1; ++g) {
         const int b = bt.tile_bt[g];
@@ -76,126 +94,80 @@ k_big_hist(BigTopics bt, int64_t* __restrict__ lag, LagOffsets offs, const int32
         const int64_t t0 = (int64_t)(g - bt.tile0[b]) * RT_TILE;
         int64_t* lg = lag + bt.off[b];
         const bool tie = HAS_PART && bt.need_tie[b] != 0;
-        // With raw offsets (lagassign_upload_offsets) this is where computePartitionLag (Main:376-404) runs for the
-        // radix path: the lag is computed as the key is built and stored for the later passes, which read `lag`.
-        const bool from_offsets = offs.end != nullptr;
-        // A digit on which all keys of the tile agree (the high bytes of small lags, every byte of an idle
-        // topic) is counted with ONE atomic for the tile instead of one same-address atomic per element
-        // (B200: config 5, all-zero lags, 0.218 -> 0.126 ms; uniform 63-bit keys pay 14 % for the test).
-        __shared__ uint32_t red[RT_WARPS][4];
-        uint64_t key[RT_IPT];
-        uint64_t o = 0, a = ~0ull;
         uint8_t* dg = bt.dig + bt.boff[b];
+        // all of the tile's loads first (the stores below may alias them as far as the compiler knows)
+        int64_t lv[RT_IPT];
 #pragma unroll
         for (int k = 0; k < RT_IPT; ++k) {
             const int64_t e = t0 + k * RT_THREADS + threadIdx.x;
-            key[k] = 0ull;
+            lv[k] = 0;
+            if (e < P) lv[k] = from_offsets ? lag_from_offsets(offs, bt.off[b] + e) : ld_stream(lg + e);
+        }
+#pragma unroll
+        for (int k = 0; k < RT_IPT; ++k) {
+            const int64_t e = t0 + k * RT_THREADS + threadIdx.x;
             if (e < P) {
-                int64_t lv;
-                if (from_offsets) { lv = lag_from_offsets(offs, bt.off[b] + e); lg[e] = lv; }
-                else lv = ld_stream(lg + e);
-                key[k] = (uint64_t)lv ^ LAG_KEY_MASK;
-                o |= key[k]; a &= key[k];
-                dg[e] = (uint8_t)key[k];      // digit of the first lag pass, for its counting kernel (4a) when it is the topic's first pass
-            }
-        }
-        {
-            const uint32_t o_lo = __reduce_or_sync(0xffffffffu, (uint32_t)o), o_hi = __reduce_or_sync(0xffffffffu, (uint32_t)(o >> 32));
-            const uint32_t a_lo = __reduce_and_sync(0xffffffffu, (uint32_t)a), a_hi = __reduce_and_sync(0xffffffffu, (uint32_t)(a >> 32));
-            if ((threadIdx.x & 31) == 0) {
-                uint32_t* row = red[threadIdx.x >> 5];
-                row[0] = o_lo; row[1] = o_hi; row[2] = a_lo; row[3] = a_hi;
-            }
-        }
-        __syncthreads();
-        uint64_t all_or = 0, all_and = ~0ull;
-#pragma unroll
-        for (int w = 0; w < RT_WARPS; ++w) {
-            all_or |= ((uint64_t)red[w][1] << 32) | red[w][0];
-            all_and &= ((uint64_t)red[w][3] << 32) | red[w][2];
-        }
-        const uint64_t diff = all_or ^ all_and;            // bits in which the tile's keys differ
-        const uint32_t n_valid = (uint32_t)min((int64_t)RT_TILE, P - t0);
-#pragma unroll
-        for (int d = 0; d < N_LAG_PASS; ++d) {
-            if (((diff >> (8 * d)) & 0xFFull) == 0) {      // uniform over the CTA
-                if (threadIdx.x == 0) atomicAdd(&h[N_TIE_PASS + d][digit_of(all_and, d)], n_valid);
-            } else {
-#pragma unroll
-                for (int k = 0; k < RT_IPT; ++k) {
-                    const int64_t e = t0 + k * RT_THREADS + threadIdx.x;
-                    if (e < P) atomicAdd(&h[N_TIE_PASS + d][digit_of(key[k], d)], 1u);
+                if (from_offsets) lg[e] = lv[k];
+                const uint64_t key = (uint64_t)lv[k] ^ LAG_KEY_MASK;
+                k_or |= key; k_nor |= ~key;
+                dg[e] = (uint8_t)key;      // digit of the first lag pass, for its counting kernel (4a) when it is the topic's first pass
+                if (tie) {
+                    const uint64_t pk = (uint32_t)part[bt.off[b] + e] ^ 0x80000000u;
+                    i_or |= pk; i_nor |= ~pk;
                 }
             }
         }
-        if (tie) {
-#pragma unroll 4
-            for (int k = 0; k < RT_IPT; ++k) {
-                const int64_t e = t0 + k * RT_THREADS + threadIdx.x;
-                if (e < P) {
-                    const uint32_t pk = (uint32_t)part[bt.off[b] + e] ^ 0x80000000u;
-#pragma unroll
-                    for (int d = 0; d < N_TIE_PASS; ++d) atomicAdd(&h[d][(pk >> (8 * d)) & 0xFFu], 1u);
-                }
-            }
-        }
-        __syncthreads();      // red[] is rewritten by the next tile
     }
     flush(cur_b);
 }
 
-// ---- 3. per topic: prefix sums, skip decisions, buffer ping-pong ------------------------
+// ---- 3. per topic: skip decisions, buffer ping-pong, one record per (pass, tile) ----------------
 __global__ void __launch_bounds__(256)
 k_big_scan(BigTopics bt, int first_pass) {
-    __shared__ uint32_t wsum[8];
-    __shared__ int s_cur, s_run, s_lagconst;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t P = bt.P[b];
-    if (tid == 0) { s_cur = SEL_RAW; s_run = 0; s_lagconst = 0; }
-    __syncthreads();
-    for (int p = 0; p < N_PASS; ++p) {
-        const size_t base = ((size_t)b * N_PASS + p) * 256;
-        uint32_t c = bt.ghist[base + tid];
-        bool off = p < first_pass || (p < N_TIE_PASS && bt.need_tie[b] == 0);
-        int constant = __syncthreads_or((int64_t)c == P);
-        // exclusive scan over the 256 digit values
-        uint32_t x = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-            if (lane >= d) x += y;
-        }
-        if (lane == 31) wsum[warp] = x;
-        __syncthreads();
-        uint32_t add = 0;
-        for (int w = 0; w < warp; ++w) add += wsum[w];
-        bt.gbase[base + tid] = x - c + add;
-        if (tid == 0) {
-            if (p >= N_TIE_PASS && constant) s_lagconst += 1;
-            if (off || constant) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) {
+        const uint64_t k_or = bt.range[(size_t)b * 4 + 0], k_and = ~bt.range[(size_t)b * 4 + 1];
+        const uint64_t i_or = bt.range[(size_t)b * 4 + 2], i_and = ~bt.range[(size_t)b * 4 + 3];
+        const uint64_t k_diff = k_or ^ k_and;                 // bits in which the topic's keys differ
+        const uint32_t i_diff = (uint32_t)(i_or ^ i_and);
+        const bool tie = bt.need_tie[b] != 0;
+        int cur = SEL_RAW, run = 0;
+        for (int p = 0; p < N_PASS; ++p) {
+            bool skip;
+            if (p < N_TIE_PASS) skip = p < first_pass || !tie || ((i_diff >> (8 * p)) & 0xFFu) == 0;
+            else skip = ((k_diff >> (8 * (p - N_TIE_PASS))) & 0xFFull) == 0;
+            if (skip) {
                 bt.sel_src[b * N_PASS + p] = SEL_SKIP;
                 bt.sel_dst[b * N_PASS + p] = SEL_SKIP;
             } else {
-                int dst = (s_cur == SEL_A) ? SEL_B : SEL_A;
-                bt.sel_src[b * N_PASS + p] = (int8_t)s_cur;
+                const int dst = (cur == SEL_A) ? SEL_B : SEL_A;
+                bt.sel_src[b * N_PASS + p] = (int8_t)cur;
                 bt.sel_dst[b * N_PASS + p] = (int8_t)dst;
-                s_cur = dst;
-                s_run += 1;
+                cur = dst;
+                run += 1;
                 atomicOr(&bt.pass_any[p], 1u);
             }
         }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        bt.sel_final[b] = (int8_t)s_cur;
-        bt.all_equal[b] = (int8_t)(s_lagconst == N_LAG_PASS);
-        atomicMax(bt.passes_run, s_run);
+        bt.sel_final[b] = (int8_t)cur;
+        bt.all_equal[b] = (int8_t)(k_diff == 0);
+        atomicMax(bt.passes_run, run);
         // the next executed pass after each pass (its digit byte is written by that pass's scatter)
         int nxt = -1;
         for (int p = N_PASS - 1; p >= 0; --p) {
             bt.nxt_pass[b * N_PASS + p] = (int8_t)nxt;
             if (bt.sel_src[b * N_PASS + p] != SEL_SKIP) nxt = p;
         }
+    }
+    __syncthreads();
+    // What the pass kernels need to know about a tile in a pass, as ONE word next to the tile descriptor, so
+    // that they do not chase tile -> topic -> three per-topic arrays with dependent loads:
+    //   byte 0 = source buffer, byte 1 = destination buffer, byte 2 = the topic's next executed pass (0xFF: none)
+    const int n_tiles_topic = (int)((bt.P[b] + RT_TILE - 1) / RT_TILE);
+    const int tile0 = bt.tile0[b];
+    for (int p = 0; p < N_PASS; ++p) {
+        const uint32_t rec = (uint32_t)(uint8_t)bt.sel_src[b * N_PASS + p] | ((uint32_t)(uint8_t)bt.sel_dst[b * N_PASS + p] << 8) |
+                             ((uint32_t)(uint8_t)bt.nxt_pass[b * N_PASS + p] << 16);
+        for (int k = tid; k < n_tiles_topic; k += blockDim.x) bt.pass_rec[(size_t)p * bt.n_tiles + tile0 + k] = rec;
     }
 }
 
@@ -291,7 +263,7 @@ k_big_tile_hist(BigTopics bt, int pass, const int64_t* __restrict__ lag, const i
             t.n_valid = a.z;
             t.buf_off = ((int64_t)(uint32_t)c.y << 32) | (uint32_t)c.x;
             t.raw_off = ((int64_t)(uint32_t)c.w << 32) | (uint32_t)c.z;
-            t.src = bt.sel_src[a.x * N_PASS + pass];
+            t.src = (int)(int8_t)(__ldg(bt.pass_rec + (size_t)pass * bt.n_tiles + g) & 0xFFu);
             // the digit bytes are only meaningful when src is a sort buffer; reading them anyway keeps the load
             // independent of the buffer choice (the buffer is allocated and padded for every tile)
             if (tid * 16 < t.n_valid) t.v = *reinterpret_cast<const uint4*>(bt.dig + t.buf_off + tid * 16);
@@ -308,7 +280,7 @@ k_big_tile_hist(BigTopics bt, int pass, const int64_t* __restrict__ lag, const i
             const int n_valid = cur.n_valid;
             if (cur.src != SEL_RAW || pass == N_TIE_PASS) {
                 // the scatter of the topic's previous pass left this pass's digit of every element in bt.dig
-                // (for a topic whose first pass is the first lag pass, k_big_hist did)
+                // (for a topic whose first pass is the first lag pass, k_big_range did)
                 const int i0 = tid * 16;
                 const uint32_t wds[4] = {cur.v.x, cur.v.y, cur.v.z, cur.v.w};
 #pragma unroll
@@ -365,15 +337,36 @@ k_big_seg_scan(BigTopics bt, int pass) {
 }
 
 // 4c: one CTA per topic; seg_total becomes the global start of (segment, digit) in the topic ----
+// (digit bases = exclusive scan over the digit values of the topic's totals, computed here from the
+// segment totals of this very pass)
 __global__ void __launch_bounds__(256)
 k_big_topic_scan(BigTopics bt, int pass) {
-    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ uint32_t wsum[8];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (bt.pass_any[pass] == 0) return;
     if (bt.sel_src[b * N_PASS + pass] == SEL_SKIP) return;
     const int n_tiles_topic = (int)((bt.P[b] + RT_TILE - 1) / RT_TILE);
     const int n = (n_tiles_topic + RT_SEG - 1) / RT_SEG;
     uint32_t* s = bt.seg_total + (size_t)bt.seg0[b] * 256 + tid;
-    uint32_t run = bt.gbase[((size_t)b * N_PASS + pass) * 256 + tid];
+    uint32_t total = 0;
+    for (int t = 0; t < n; t += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (t + q < n) ? s[(size_t)(t + q) * 256] : 0u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) total += v[q];
+    }
+    uint32_t x = total;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    uint32_t add = 0;
+    for (int w = 0; w < warp; ++w) add += wsum[w];
+    uint32_t run = x - total + add;              // first position of digit value `tid` in the sorted topic
     for (int t = 0; t < n; t += 8) {
         uint32_t v[8];
 #pragma unroll
@@ -427,6 +420,8 @@ struct PassSmem {
     int32_t dst_base[256];           // index in the topic of the tile's first element of each digit, minus its tile-local offset
     uint32_t wsum[8];
     alignas(8) uint64_t full_bar[RT_STAGES];
+    alignas(16) int4 desc[RT_STAGES + 2][3];   // descriptors of the tiles it .. it+RT_STAGES+1 (ring): {b, tile_in_topic, n_valid, seg},
+                                               // {buf_off, raw_off}, {pass record, -, -, -}
 };
 
 #ifdef LAGASSIGN_RT_TIMING
@@ -464,24 +459,33 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
     int t_tiles = 0;
 #endif
 
-    // A tile's geometry is one 32-byte record; the record also remembers which buffer the
-    // topic reads in this pass (-1: pass skipped for the topic, or no such tile).
+    // A tile's geometry is one 32-byte record plus the word k_big_scan wrote for (pass, tile): which buffer the
+    // topic reads / writes in this pass (-1: pass skipped for the topic, or no such tile) and its next executed pass.
+    // ONE thread fetches the records of upcoming tiles into a small ring in shared memory (three independent
+    // loads, issued a whole tile ahead of their first use); everybody else reads the current tile's record from
+    // there. (Before: every thread carried four tiles' records in registers and fetched them with dependent global
+    // loads at the top of the loop: 13 % of a tile's cycles with all warps stalled, and 128 registers.)
     struct Tile { TileDesc d; int src, dst, nxt_pass; };
-    auto load_tile = [&](int g) {
-        Tile t;
-        t.src = SEL_SKIP;
-        t.dst = SEL_SKIP;
-        t.nxt_pass = -1;
-        t.d.b = -1;
+    constexpr int DESC_SLOTS = RT_STAGES + 2;
+    constexpr int LOADER_TID = 64;
+    auto fetch_desc = [&](int g, int4& a, int4& c, int4& r) {       // global -> registers (loader thread)
+        a = make_int4(-1, 0, 0, 0); c = make_int4(0, 0, 0, 0); r = make_int4(0x00FFFFFF, 0, 0, 0);   // src = dst = nxt = -1
         if (g < n_tiles) {
-            const int4 a = __ldg(bt.tile_desc + 2 * (size_t)g), c = __ldg(bt.tile_desc + 2 * (size_t)g + 1);
-            t.d.b = a.x; t.d.tile_in_topic = a.y; t.d.n_valid = a.z; t.d.seg = a.w;
-            t.d.buf_off = ((int64_t)(uint32_t)c.y << 32) | (uint32_t)c.x;
-            t.d.raw_off = ((int64_t)(uint32_t)c.w << 32) | (uint32_t)c.z;
-            t.src = bt.sel_src[t.d.b * N_PASS + pass];
-            t.dst = bt.sel_dst[t.d.b * N_PASS + pass];
-            t.nxt_pass = bt.nxt_pass[t.d.b * N_PASS + pass];   // the topic's next executed pass (-1: none)
+            a = __ldg(bt.tile_desc + 2 * (size_t)g);
+            c = __ldg(bt.tile_desc + 2 * (size_t)g + 1);
+            r.x = (int)__ldg(bt.pass_rec + (size_t)pass * n_tiles + g);
         }
+    };
+    auto read_desc = [&](int slot) {                                   // shared memory -> registers (broadcast)
+        const int4 a = sm.desc[slot][0], c = sm.desc[slot][1];
+        const uint32_t rec = (uint32_t)sm.desc[slot][2].x;
+        Tile t;
+        t.d.b = a.x; t.d.tile_in_topic = a.y; t.d.n_valid = a.z; t.d.seg = a.w;
+        t.d.buf_off = ((int64_t)(uint32_t)c.y << 32) | (uint32_t)c.x;
+        t.d.raw_off = ((int64_t)(uint32_t)c.w << 32) | (uint32_t)c.z;
+        t.src = (int)(int8_t)(rec & 0xFFu);
+        t.dst = (int)(int8_t)((rec >> 8) & 0xFFu);
+        t.nxt_pass = (int)(int8_t)((rec >> 16) & 0xFFu);   // the topic's next executed pass (-1: none)
         return t;
     };
     // A raw source (the caller's lag array) is only 8-byte aligned: the copy then starts one element early.
@@ -507,49 +511,57 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
         }
     };
 
+    const int G = (int)gridDim.x;
+    const int g0 = (int)blockIdx.x;
     if (tid == 0) {
 #pragma unroll
         for (int j = 0; j < RT_STAGES; ++j) mbar_init(&sm.full_bar[j], 1);
         fence_mbar_init();
     }
+    if (tid >= 32 && tid < 32 + RT_STAGES + 1) {      // records of the tiles of iterations 0 .. RT_STAGES
+        int4 a, c, r;
+        fetch_desc(g0 + (tid - 32) * G, a, c, r);
+        sm.desc[tid - 32][0] = a; sm.desc[tid - 32][1] = c; sm.desc[tid - 32][2] = r;
+    }
 #pragma unroll
     for (int w = 0; w < SC_WARPS / 2; ++w)
         if (tid < 256) sm.whist[w][tid] = 0;
     __syncthreads();
-    const int G = (int)gridDim.x;
     uint32_t* const my_cnt = sm.whist[warp >> 1];      // this warp's counters: the (warp & 1) half of these words
     const int my_sh = (warp & 1) * 16;
-    const int g0 = (int)blockIdx.x;
-    // q[j] = the tile of iteration it + j, already being fetched into ring stage (it + j) % RT_STAGES; `far` is the
-    // tile after those: it is fetched into the stage of the current tile as soon as every thread has read the
-    // tile-local scatter back out of it, BEFORE the global stores are issued — so a warp that is held up by the
-    // store queue does not hold up the refill, and warps flow from their stores straight into the next tile
-    // (whose first barrier comes after its ranking).
-    Tile q[RT_STAGES];
-#pragma unroll
-    for (int j = 0; j < RT_STAGES; ++j) q[j] = load_tile(g0 + j * G);
+    // The tile of iteration it + j (j < RT_STAGES) is being fetched into ring stage (it + j) % RT_STAGES; the tile
+    // after those is fetched into the stage of the current tile as soon as every thread has read the tile-local
+    // scatter back out of it, BEFORE the global stores are issued — so a warp that is held up by the store queue
+    // does not hold up the refill, and warps flow from their stores straight into the next tile (whose first
+    // barrier comes after its ranking).
     if (tid == 0) {
 #pragma unroll
-        for (int j = 0; j < RT_STAGES; ++j) issue_loads(j, q[j]);
+        for (int j = 0; j < RT_STAGES; ++j) issue_loads(j, read_desc(j));
     }
-    Tile far = load_tile(g0 + RT_STAGES * G);
     uint32_t phase = 0u;                   // bit j: parity of the next completion of stage j's barrier
     int s = 0;                             // ring stage of the tile being processed
+    int slot = 0;                          // descriptor slot of the tile being processed
 
     for (int it = 0;; ++it) {
         const int g = g0 + it * G;
         if (g >= n_tiles) break;
-        const Tile cur = q[0];
-#pragma unroll
-        for (int j = 0; j + 1 < RT_STAGES; ++j) q[j] = q[j + 1];
-        q[RT_STAGES - 1] = far;                                    // tile it + RT_STAGES: next occupant of this stage
-        far = load_tile(g + (RT_STAGES + 1) * G);
-        const Tile refill = q[RT_STAGES - 1];
+        // loader: the record of tile it + RT_STAGES + 1 goes to the slot tile it - 1 had (nobody reads that any more:
+        // every thread read it before the first barrier of the previous iteration)
+        int4 la, lc, lr;
+        if (tid == LOADER_TID) fetch_desc(g + (RT_STAGES + 1) * G, la, lc, lr);
+        const int slot_new = (slot == 0) ? DESC_SLOTS - 1 : slot - 1;           // == (it + RT_STAGES + 1) % DESC_SLOTS
+        int slot_refill = slot + RT_STAGES; if (slot_refill >= DESC_SLOTS) slot_refill -= DESC_SLOTS;
+        const Tile cur = read_desc(slot);
+        Tile refill = cur;                     // (thread 0 only) the next occupant of this tile's stage, read now so that the
+        if (tid == 0) refill = read_desc(slot_refill);   // bulk copies below are not issued behind a shared-memory queue
+        slot = (slot + 1 == DESC_SLOTS) ? 0 : slot + 1;
         RT_TICK(0);
         const int s_cur = s;
         s = (s + 1 == RT_STAGES) ? 0 : s + 1;
         if (cur.src == SEL_SKIP) {           // this topic's digit is constant in this pass: nothing was fetched,
-            if (tid == 0) issue_loads(s_cur, refill);   // the stage is free (its last reader passed a barrier long ago)
+            if (tid == LOADER_TID) { sm.desc[slot_new][0] = la; sm.desc[slot_new][1] = lc; sm.desc[slot_new][2] = lr; }
+            __syncthreads();                 // (orders the record ring; the stage itself is free: its last reader passed a barrier long ago)
+            if (tid == 0) issue_loads(s_cur, refill);
             continue;
         }
 
@@ -608,6 +620,7 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
             }
         }
         __syncthreads();   // all counts in; every thread holds its elements in registers (the stage may be overwritten)
+        if (tid == LOADER_TID) { sm.desc[slot_new][0] = la; sm.desc[slot_new][1] = lc; sm.desc[slot_new][2] = lr; }
         RT_TICK(3);
 
         // thread d owns digit value d: offsets over warps and over digits inside the tile
@@ -685,13 +698,8 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
             for (int k = 0; k < SC_IPT; ++k) {
                 const int i = k * SC_THREADS + tid;
                 if (i < n_valid) {
-#if defined(LAGASSIGN_SC_STCS) && !defined(LAGASSIGN_HOST_EMULATION)
-                    __stcs(reinterpret_cast<unsigned long long*>(dkey + oo[k]), (unsigned long long)kk[k]);
-                    __stcs(dpay + oo[k], pp[k]);
-#else
-                    dkey[oo[k]] = kk[k];
+                    dkey[oo[k]] = kk[k];      // (streaming stores, st.global.cs, measured: no difference)
                     dpay[oo[k]] = pp[k];
-#endif
                     if (nxt_pass >= 0) ddig[oo[k]] = (uint8_t)pass_digit(nxt_pass, kk[k], pv[k]);
                 }
             }
@@ -745,12 +753,16 @@ k_big_verify(BigTopics bt, const int32_t* __restrict__ part) {
 }
 
 // ---- 5. finalize: out_partition (and out_consumer for single-round topics) ---------------
+// VERIFY: also the certificate 4e, on the same read of the sorted sequence (the separate kernel costs
+// another 12 B/element; it remains for the sort-only mode of the grouping step, which has no finalize).
+template <bool VERIFY>
 __global__ void __launch_bounds__(256)
 k_big_finalize(BigTopics bt, const int64_t* __restrict__ lag, const int32_t* __restrict__ part,
                const int32_t* __restrict__ topic_cset, const int64_t* __restrict__ cset_off,
                const int32_t* __restrict__ cset_rank, const int64_t* __restrict__ tc_off,
                int32_t* __restrict__ out_part, int32_t* __restrict__ out_cons,
                int64_t* __restrict__ out_total, int32_t* __restrict__ out_count) {
+    int bad = 0;
     for (int g = blockIdx.x; g < bt.n_tiles; g += gridDim.x) {
         const int b = bt.tile_bt[g];
         const int t = bt.topic[b];
@@ -766,28 +778,85 @@ k_big_finalize(BigTopics bt, const int64_t* __restrict__ lag, const int32_t* __r
         // member k mod C. No sequential fill is needed.
         const bool cyclic = !single_round && bt.all_equal[b] != 0;
         const int64_t t0 = (int64_t)(g - bt.tile0[b]) * RT_TILE;
-        for (int i = threadIdx.x; i < RT_TILE; i += blockDim.x) {
-            const int64_t e = t0 + i;
-            if (e >= P) break;
-            const uint32_t pay = (sel == SEL_RAW) ? (uint32_t)e : fpay[e];
-            out_part[off + e] = part ? part[off + pay] : (int32_t)pay;
-            if (single_round) {
-                out_cons[off + e] = cset_rank[coff + e];
-                if (out_total) {
-                    int64_t lg = (sel == SEL_RAW) ? lag[off + e] : (int64_t)(fkey[e] ^ LAG_KEY_MASK);
-                    out_total[tc_off[t] + e] = lg;
-                    out_count[tc_off[t] + e] = 1;
+        const bool sorted = sel != SEL_RAW;
+        const bool tie = part != nullptr && bt.need_tie[b] != 0;
+        const bool need_key = sorted && (VERIFY || (single_round && out_total != nullptr));
+        constexpr int FB = 8;                       // elements per thread and batch: all loads of a batch before its stores
+        const unsigned lane = lane_id();
+        for (int i0 = 0; i0 < RT_TILE; i0 += FB * 256) {
+            if (t0 + i0 >= P) break;                // uniform over the CTA
+            // ONE round trip to memory per batch: everything that does not depend on loaded data is requested up front
+            // (own element, the consumer of the slot, and — lane 31 only — the successor element for the certificate)
+            uint32_t pay[FB], p1x[FB];
+            uint64_t key[FB], k1x[FB];
+            int32_t pid[FB], cons[FB];
+#pragma unroll
+            for (int q = 0; q < FB; ++q) {
+                const int64_t e = t0 + i0 + q * 256 + (int)threadIdx.x;
+                pay[q] = (uint32_t)e; p1x[q] = (uint32_t)(e + 1);
+                key[q] = 0; k1x[q] = 0;
+                cons[q] = 0;
+                if (e < P) {
+                    if (sorted) {
+                        pay[q] = fpay[e];
+                        if (need_key) key[q] = fkey[e];
+                        if (VERIFY && lane == 31 && e + 1 < P) { k1x[q] = fkey[e + 1]; p1x[q] = fpay[e + 1]; }
+                    }
+                    if (single_round) cons[q] = cset_rank[coff + e];
+                    else if (cyclic) cons[q] = cset_rank[coff + e % C];
                 }
-            } else if (cyclic) {
-                out_cons[off + e] = cset_rank[coff + e % C];
-                if (out_total && e < C) {
-                    const int64_t cnt = P / C + (e < P % C ? 1 : 0);
-                    out_total[tc_off[t] + e] = (int64_t)((uint64_t)cnt * (uint64_t)lag[off]);   // wraps like repeated addition
-                    out_count[tc_off[t] + e] = (int32_t)cnt;
+            }
+#pragma unroll
+            for (int q = 0; q < FB; ++q) {
+                const int64_t e = t0 + i0 + q * 256 + (int)threadIdx.x;
+                pid[q] = (int32_t)pay[q];
+                if (e < P && part != nullptr) pid[q] = part[off + pay[q]];
+            }
+            if (VERIFY && sorted) {
+                // strictly increasing in (key, id when the ids had to be ordered, position): the successor of an
+                // element is the next lane's
+#pragma unroll
+                for (int q = 0; q < FB; ++q) {
+                    const int64_t e = t0 + i0 + q * 256 + (int)threadIdx.x;
+                    uint64_t k1 = __shfl_down_sync(0xffffffffu, key[q], 1);
+                    uint32_t p1 = __shfl_down_sync(0xffffffffu, pay[q], 1);
+                    int32_t i1 = __shfl_down_sync(0xffffffffu, pid[q], 1);
+                    if (lane == 31) {
+                        k1 = k1x[q];
+                        p1 = p1x[q];
+                        i1 = (part != nullptr && e + 1 < P) ? part[off + p1] : (int32_t)p1;
+                    }
+                    if (e + 1 < P) {
+                        bool ok = key[q] < k1;
+                        if (key[q] == k1) ok = tie ? (pid[q] < i1 || (pid[q] == i1 && pay[q] < p1)) : (pay[q] < p1);
+                        bad |= !ok;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < FB; ++q) {
+                const int64_t e = t0 + i0 + q * 256 + (int)threadIdx.x;
+                if (e >= P) continue;
+                out_part[off + e] = pid[q];
+                if (single_round) {
+                    out_cons[off + e] = cons[q];
+                    if (out_total) {
+                        const int64_t lg = sorted ? (int64_t)(key[q] ^ LAG_KEY_MASK) : lag[off + e];
+                        out_total[tc_off[t] + e] = lg;
+                        out_count[tc_off[t] + e] = 1;
+                    }
+                } else if (cyclic) {
+                    out_cons[off + e] = cons[q];
+                    if (out_total && e < C) {
+                        const int64_t cnt = P / C + (e < P % C ? 1 : 0);
+                        out_total[tc_off[t] + e] = (int64_t)((uint64_t)cnt * (uint64_t)lag[off]);   // wraps like repeated addition
+                        out_count[tc_off[t] + e] = (int32_t)cnt;
+                    }
                 }
             }
         }
     }
+    if (VERIFY && bad) atomicOr(bt.verify_fail, 1u);
 }
 
 // ---- 6. round fill of a large topic: one CTA per topic -----------------------------------

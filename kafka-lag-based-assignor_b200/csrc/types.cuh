@@ -20,7 +20,7 @@ struct LagOffsets {
 struct DevBatch {
     const int64_t* topic_off;   // [T+1]
     const int64_t* lag;         // [N]  (with offsets: the context's own buffer; only the radix path's topics are
-                                //       materialised there, by k_big_hist)
+                                //       materialised there, by k_big_range)
     LagOffsets offs;            // see above
     const int32_t* part;        // [N] or null
     const int32_t* topic_cset;  // [T]
@@ -102,8 +102,8 @@ struct BigTopics {
     uint32_t* payA; uint32_t* payB;
     uint8_t* dig;              // [sum P] digit of every element in the topic's NEXT executed pass, in the order of the
                                //         buffer the last scatter wrote (input of k_big_tile_hist)
-    uint32_t* ghist;           // [B][N_PASS][256] digit counts
-    uint32_t* gbase;           // [B][N_PASS][256] exclusive prefix of ghist
+    uint64_t* range;           // [B][4] OR of keys, OR of ~keys, OR of id keys, OR of ~id keys (k_big_range)
+    uint32_t* pass_rec;        // [N_PASS][G] per (pass, tile): source | destination << 8 | next executed pass << 16 (k_big_scan)
     int8_t* sel_src;           // [B][N_PASS]  SEL_* (SEL_SKIP = pass skipped for this topic)
     int8_t* sel_dst;           // [B][N_PASS]
     int8_t* nxt_pass;          // [B][N_PASS]  the topic's next executed pass after this one (-1: none)
@@ -139,14 +139,14 @@ constexpr int N_CTA_CLASSES = 4;   // topics of 257..512 / ..1024 / ..2048 / ..4
 inline int cta_class_of(int64_t P) { return P <= 512 ? 0 : P <= 1024 ? 1 : P <= 2048 ? 2 : 3; }
 void launch_cta_topics(const DevBatch& b, const int32_t* list, int n, int cls, int sms, cudaStream_t st);
 void launch_big_order_check(const BigTopics& bt, const int32_t* part, int sms, cudaStream_t st);
-void launch_big_hist(const BigTopics& bt, const int64_t* lag, const LagOffsets& offs, const int32_t* part, int sms, cudaStream_t st);
+void launch_big_range(const BigTopics& bt, const int64_t* lag, const LagOffsets& offs, const int32_t* part, int sms, cudaStream_t st);
 void launch_big_scan(const BigTopics& bt, int first_pass, cudaStream_t st);
 void launch_big_tile_hist(const BigTopics& bt, int pass, const int64_t* lag, const int32_t* part, int sms, cudaStream_t st);
 void launch_big_pass_scans(const BigTopics& bt, int pass, cudaStream_t st);   // two kernels
 void launch_big_scatter(const BigTopics& bt, int pass, const int64_t* lag, const int32_t* part, bool exact, int sms, cudaStream_t st);
 void launch_big_verify(const BigTopics& bt, const int32_t* part, int sms, cudaStream_t st);
 cudaError_t probe_atomic_lane_order(int* in_order, cudaStream_t st);
-void launch_big_finalize(const BigTopics& bt, const DevBatch& b, int sms, cudaStream_t st);
+void launch_big_finalize(const BigTopics& bt, const DevBatch& b, bool verify, int sms, cudaStream_t st);
 void launch_big_fill(const BigTopics& bt, const int32_t* fill_list, int n_fill, const DevBatch& b, int sms, cudaStream_t st);
 void launch_group_keys(int64_t n, const int32_t* out_cons, int64_t n_members, int64_t* glag, int sms, cudaStream_t st);
 void launch_group_finalize(const BigTopics& bt, const int64_t* glag, int64_t n_members, int64_t n_unassigned,

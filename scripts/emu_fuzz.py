@@ -8,8 +8,6 @@ import numpy as np, ctypes
 import oracle
 from helpers import random_flat, args_of
 import test_kernels_emulated_cpu as tk
-L = ctypes.CDLL(os.environ.get("EMU_LIB") or os.path.join(ROOT, "tests", "emu", "_build", "libemu_onchip.so"))   # EMU_LIB: a variant build
-L.emu_assign_onchip.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 11
 seed0 = int(sys.argv[1]); n = int(sys.argv[2])
 t0 = time.time(); fails = 0
 if len(sys.argv) > 3 and sys.argv[3] == "radix":
@@ -29,6 +27,8 @@ if len(sys.argv) > 3 and sys.argv[3] == "radix":
             print("FAIL seed", s, kind, ids, C, str(e)[:200], flush=True)
     print(f"radix seeds {seed0}..{seed0+n-1}: {fails} failures in {time.time()-t0:.0f} s", flush=True)
     sys.exit(1 if fails else 0)
+L = ctypes.CDLL(os.environ.get("EMU_LIB") or os.path.join(ROOT, "tests", "emu", "_build", "libemu_onchip.so"))   # EMU_LIB: a variant build
+L.emu_assign_onchip.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 11
 for s in range(seed0, seed0 + n):
     rng = np.random.default_rng(s)
     kind = ["small", "dups", "u40", "full"][int(rng.integers(0, 4))]

@@ -1,5 +1,5 @@
 // emu_radix.cpp — TEST INFRASTRUCTURE: the device-wide path of the product (radix.cuh: k_big_order_check,
-// k_big_hist, k_big_scan, k_big_tile_hist, k_big_seg_scan, k_big_topic_scan, k_big_scatter, k_big_finalize,
+// k_big_range, k_big_scan, k_big_tile_hist, k_big_seg_scan, k_big_topic_scan, k_big_scatter, k_big_finalize,
 // k_big_fill) compiled for the HOST with the stand-in of cuda_emu.hpp and run one CTA at a time, in the
 // launch order of lagassign_execute(). The planning below restates the big-topic part of validate_and_plan()
 // (lagassign_api.cu) and is test code: it may disagree with the product, which is the point of checking.
@@ -83,7 +83,8 @@ extern "C" int emu_assign_big(int64_t n_topics, const int64_t* topic_off, const 
     lag_base += lag_shift;                                                       // or deliberately only 8-byte aligned
     if (offs.end == nullptr) std::copy(lag, lag + n_total, lag_base);   // with raw offsets the buffer starts zeroed
     lag = lag_base;
-    std::vector<uint32_t> ghist((size_t)B * N_PASS * 256, 0), gbase((size_t)B * N_PASS * 256, 0);
+    std::vector<uint64_t> range((size_t)B * 4, 0);
+    std::vector<uint32_t> pass_rec((size_t)tiles * N_PASS, 0xEEEEEEEEu);
     std::vector<int8_t> sel((size_t)B * (3 * N_PASS + 2), 0);
     std::vector<int32_t> need_tie((size_t)B, 0);
     std::vector<uint32_t> tile_hist((size_t)tiles * 256, 0), seg_total((size_t)n_segs * 256, 0), ticket(RT_TICKET_WORDS, 0);
@@ -94,7 +95,7 @@ extern "C" int emu_assign_big(int64_t n_topics, const int64_t* topic_off, const 
     bt.tile0 = bt_tile0.data(); bt.tile_bt = tile_bt.data();
     bt.tile_desc = reinterpret_cast<const int4*>(tile_desc.data());
     bt.keyA = keyA.data(); bt.keyB = keyB.data(); bt.payA = payA.data(); bt.payB = payB.data();
-    bt.ghist = ghist.data(); bt.gbase = gbase.data();
+    bt.range = range.data(); bt.pass_rec = pass_rec.data();
     bt.sel_src = sel.data(); bt.sel_dst = sel.data() + (size_t)B * N_PASS;
     bt.nxt_pass = sel.data() + (size_t)B * N_PASS * 2;
     bt.sel_final = sel.data() + (size_t)B * N_PASS * 3; bt.all_equal = sel.data() + (size_t)B * (N_PASS * 3 + 1);
@@ -122,8 +123,8 @@ extern "C" int emu_assign_big(int64_t n_topics, const int64_t* topic_off, const 
     const int first_pass = has_part ? 0 : N_TIE_PASS;
     const int n_tiles = (int)tiles;
     if (has_part) launch(std::min(n_tiles, sms * 8), 256, [&] { k_big_order_check(bt, partition); });
-    if (has_part) launch(std::min(n_tiles, sms * 6), RT_THREADS, [&] { k_big_hist<true>(bt, lag_base, offs, partition); });
-    else launch(std::min(n_tiles, sms * 6), RT_THREADS, [&] { k_big_hist<false>(bt, lag_base, offs, nullptr); });
+    if (has_part) launch(std::min(n_tiles, sms * 8), RT_THREADS, [&] { k_big_range<true>(bt, lag_base, offs, partition); });
+    else launch(std::min(n_tiles, sms * 8), RT_THREADS, [&] { k_big_range<false>(bt, lag_base, offs, nullptr); });
     launch(B, 256, [&] { k_big_scan(bt, first_pass); });
     for (int p = first_pass; p < N_PASS; ++p) {
         if (bt.pass_any[p] == 0) continue;
@@ -134,11 +135,16 @@ extern "C" int emu_assign_big(int64_t n_topics, const int64_t* topic_off, const 
         if (has_part) launch(std::min(n_tiles, sms * 2), SC_THREADS, [&] { (exact ? k_big_scatter<true, true>(bt, p, lag, partition) : k_big_scatter<true, false>(bt, p, lag, partition)); });
         else launch(std::min(n_tiles, sms * 2), SC_THREADS, [&] { (exact ? k_big_scatter<false, true>(bt, p, lag, nullptr) : k_big_scatter<false, false>(bt, p, lag, nullptr)); });
     }
+    // the certificate rides on the finalize kernel (the stand-alone k_big_verify serves the sort-only mode: both are run
+    // here and must agree)
     launch(std::min(n_tiles, sms * 8), 256, [&] { k_big_verify(bt, partition); });
-    if (*bt.verify_fail != 0) return -2;      // the certificate of the sort failed
+    const uint32_t standalone_verdict = *bt.verify_fail;
+    *bt.verify_fail = 0;
     launch(std::min(n_tiles, sms * 8), 256, [&] {
-        k_big_finalize(bt, lag, partition, topic_cset, cset_off, cset_rank, tc_off, out_partition, out_consumer_rank, out_total, out_count);
+        k_big_finalize<true>(bt, lag, partition, topic_cset, cset_off, cset_rank, tc_off, out_partition, out_consumer_rank, out_total, out_count);
     });
+    if ((*bt.verify_fail != 0) != (standalone_verdict != 0)) return -3;   // the two forms of the certificate disagree
+    if (*bt.verify_fail != 0) return -2;      // the certificate of the sort failed
     if (!l_fill.empty()) {
         const int n_fill = (int)l_fill.size();
         launch(std::min(n_fill, sms), BIGFILL_THREADS, [&] {

@@ -305,7 +305,7 @@ def test_onchip_kernels_from_raw_offsets(emu, latest, ids, totals):
 
 
 def test_radix_path_from_raw_offsets(emu_radix):
-    """k_big_hist computes the lags from the offsets while it builds the keys and stores them for the later passes."""
+    """k_big_range computes the lags from the offsets while it builds the keys and stores them for the later passes."""
     rng = np.random.default_rng(17)
     b = random_flat(rng, T=2, pmin=4200, pmax=7000, C=900, lag_kind="u40", n_sets=1)
     n = len(b["lag"])
