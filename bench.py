@@ -289,6 +289,18 @@ def main():
         b_.record(stream)
         torch.cuda.synchronize()
     t_unprofiled_ms = sum(a.elapsed_time(b_) for a, b_ in ev_u) / len(ev_u)
+    exchange_ms = None
+    if world > 1:          # where the exchange's time goes (not the headline: separate steps with four more events each)
+        acc = [0.0, 0.0, 0.0]
+        for _ in range(5):
+            flush()
+            f.execute()
+            e4 = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            sh.gather(events=e4)
+            torch.cuda.synchronize()
+            for j in range(3):
+                acc[j] += e4[j].elapsed_time(e4[j + 1]) / 5
+        exchange_ms = {"narrow": acc[0], "all_gather": acc[1], "widen": acc[2]}
     t_compute_ms = sum(a.elapsed_time(m) for a, m, b_ in ev)
     launches_per_step = f.stats()["kernel_launches"]
     stats = f.stats()
@@ -323,33 +335,47 @@ def main():
     n_loc = len(loc["lag"])
     h_op = pkg.pinned_empty(n_loc, np.int32)
     h_oc = pkg.pinned_empty(n_loc, np.int32)
+    h_npart = pkg.pinned_empty(4 * n_loc, np.uint8)      # narrow form: at most 4 bytes per entry
+    h_ncons = pkg.pinned_empty(4 * n_loc, np.uint8)
+    a_in = (loc["topic_off"], h_lag, h_part, loc["topic_cset"], loc["cset_off"], loc["cset_rank"])
+    t_e2e_narrow = float("inf")
+    narrow_fmt = None
     if args.hot_path_only:
         # ncu launch lists: nothing but the execute() steps above may launch kernels
         e2e_steps = 1
         t_e2e = t_e2e_replan = float("inf")
-        st2 = st2_replan = {"h2d_bytes": 0, "d2h_bytes": 0}
+        st2 = st2_replan = st2_narrow = {"h2d_bytes": 0, "d2h_bytes": 0}
     else:
         e2e_steps = max(3, min(args.steps, 10))
-        for _ in range(2):
-            f2.assign_batch(loc["topic_off"], h_lag, h_part, loc["topic_cset"], loc["cset_off"], loc["cset_rank"], h_op, h_oc)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            f2.assign_batch(loc["topic_off"], h_lag, h_part, loc["topic_cset"], loc["cset_off"], loc["cset_rank"], h_op, h_oc)
-        torch.cuda.synchronize()
-        t_e2e = time.perf_counter() - t0
-        st2 = f2.stats()
-        parity_ok = parity_ok and bool(np.array_equal(h_op[:n_el], exp["out_partition"][:n_el]))
-        # the same calls with the plan cache off: every call validates, plans and uploads the metadata again
-        f2.set_option(pkg.OPT_PLAN_CACHE, 0)
-        f2.assign_batch(loc["topic_off"], h_lag, h_part, loc["topic_cset"], loc["cset_off"], loc["cset_rank"], h_op, h_oc)
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            f2.assign_batch(loc["topic_off"], h_lag, h_part, loc["topic_cset"], loc["cset_off"], loc["cset_rank"], h_op, h_oc)
-        torch.cuda.synchronize()
-        t_e2e_replan = time.perf_counter() - t0
-        st2_replan = f2.stats()
 
+        def timed_calls(call):
+            for _ in range(2):
+                call()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                call()
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0
+        # (a) the int32 result arrays of lagassign_result
+        t_e2e = timed_calls(lambda: f2.assign_batch(*a_in, h_op, h_oc))
+        st2 = f2.stats()
+        parity_ok = parity_ok and bool(np.array_equal(h_op[:n_el], exp["out_partition"][:n_el])) and \
+            bool(np.array_equal(h_oc[:n_el], exp["out_consumer_rank"][:n_el]))
+        # (b) the narrow result form (lagassign_assign_batch_narrow): same information, fewer bytes device -> host
+        got_n = {}
+        t_e2e_narrow = timed_calls(lambda: got_n.update(f2.assign_batch_narrow(*a_in, h_npart, h_ncons)))
+        st2_narrow = f2.stats()
+        narrow_fmt = (got_n["part_width"], got_n["cons_width"])
+        parity_ok = parity_ok and bool(np.array_equal(got_n["out_partition"][:n_el].astype(np.int64), exp["out_partition"][:n_el]))
+        if got_n["cons_width"]:
+            c_n = got_n["out_consumer_rank"][:n_el].astype(np.int64)
+            c_n[c_n == (1 << (8 * got_n["cons_width"])) - 1] = -1
+            parity_ok = parity_ok and bool(np.array_equal(c_n, exp["out_consumer_rank"][:n_el]))
+        # (c) the int32 call with the plan cache off: every call validates, plans and uploads the metadata again
+        f2.set_option(pkg.OPT_PLAN_CACHE, 0)
+        t_e2e_replan = timed_calls(lambda: f2.assign_batch(*a_in, h_op, h_oc))
+        st2_replan = f2.stats()
 
     # ---- the two "next" rows of SURVEY 8(f) that are built, measured beside the hot path (N = 1) ----
     next_rows = None
@@ -390,11 +416,11 @@ def main():
                                                         "raw offsets instead of 8 B of lags"}}
 
     # ---- reduce over ranks --------------------------------------------------------------------
-    times = torch.tensor([t_total_ms, t_compute_ms, t_e2e * 1e3, 0.0 if parity_ok else 1.0, t_e2e_replan * 1e3],
+    times = torch.tensor([t_total_ms, t_compute_ms, t_e2e * 1e3, 0.0 if parity_ok else 1.0, t_e2e_replan * 1e3, t_e2e_narrow * 1e3],
                          dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_total_ms, t_compute_ms, t_e2e_ms, bad, t_e2e_replan_ms = [float(x) for x in times.tolist()]
+    t_total_ms, t_compute_ms, t_e2e_ms, bad, t_e2e_replan_ms, t_e2e_narrow_ms = [float(x) for x in times.tolist()]
 
     if rank == 0:
         peak, peak_src = hbm_peak()
@@ -432,12 +458,20 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": config_obj,
             "clocks": clocks,
-            "e2e": {"value": N_total * e2e_steps / (t_e2e_ms * 1e-3), "unit": "assignments/s",
-                    "h2d_bytes_per_step": st2["h2d_bytes"], "d2h_bytes_per_step": st2["d2h_bytes"],
-                    "steps": e2e_steps, "api": "lagassign_assign_batch (C ABI), pinned host buffers, per-rank shard",
+            "e2e": {"value": N_total * e2e_steps / (t_e2e_narrow_ms * 1e-3), "unit": "assignments/s",
+                    "h2d_bytes_per_step": st2_narrow["h2d_bytes"], "d2h_bytes_per_step": st2_narrow["d2h_bytes"],
+                    "steps": e2e_steps,
+                    "api": "lagassign_assign_batch_narrow (C ABI), pinned host buffers, per-rank shard; result form: "
+                           f"partition ids in {narrow_fmt[0] if narrow_fmt else '?'} byte(s), consumers in "
+                           f"{narrow_fmt[1] if narrow_fmt else '?'} byte(s) (0 = every topic has P <= C: the consumer of sorted "
+                           "partition k is the k-th member of the topic's set, which the caller holds; include/lagassign.h)",
                     "note": "batch shape repeats between calls (as between rebalances), so the plan and the metadata on the "
-                            "device are reused and only lags go up; value_replanned = plan cache off, every call plans again",
-                    "value_replanned": N_total * e2e_steps / (t_e2e_replan_ms * 1e-3),
+                            "device are reused and only lags go up. value_int32 = the same call returning the two int32 arrays "
+                            "of lagassign_result (lagassign_assign_batch); value_int32_replanned = that call with the plan cache "
+                            "off (every call validates, plans and uploads the metadata again)",
+                    "value_int32": N_total * e2e_steps / (t_e2e_ms * 1e-3),
+                    "d2h_bytes_per_step_int32": st2["d2h_bytes"],
+                    "value_int32_replanned": N_total * e2e_steps / (t_e2e_replan_ms * 1e-3),
                     "h2d_bytes_per_step_replanned": st2_replan["h2d_bytes"]},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -448,6 +482,7 @@ def main():
             "ms_per_step_unprofiled": t_unprofiled_ms,
             "compute_ms_per_step": step_ms,
             "gather_ms_per_step": (t_total_ms - t_compute_ms) / args.steps,
+            "exchange_ms": exchange_ms,
             "parity_spot_check": "ok" if bad == 0.0 else "MISMATCH",
             "next_rows": next_rows,
             "stats": stats,

@@ -62,7 +62,7 @@
 extern "C" {
 #endif
 
-#define LAGASSIGN_ABI_VERSION 2
+#define LAGASSIGN_ABI_VERSION 3
 
 #define LAGASSIGN_OK               0
 #define LAGASSIGN_ERR_ARG         -1  /* NULL pointer, non-monotone offsets, unsorted set ... */
@@ -179,6 +179,27 @@ int  lagassign_set_option(lagassign_ctx *ctx, int option, int64_t value);
  * Main:149. Equivalent to upload + execute + download. Blocking. */
 int  lagassign_assign_batch(lagassign_ctx *ctx, const lagassign_batch *in,
                             const lagassign_result *out);
+
+/* The same call with the results in their NARROW form (optional; for callers that read bytes as cheaply as ints,
+ * e.g. a JVM over direct buffers): at BASELINE config 4 the device-to-host copy shrinks from 8 bytes per partition
+ * to 1, which leaves the host-to-device copy of the lags as the only PCIe leg of the call.
+ *   out_partition      [N] entries of part_width bytes (unsigned): 1 when the batch has no explicit ids and every
+ *                      topic has at most 256 partitions, 2 up to 65536, else 4 (always 4 with explicit ids)
+ *   out_consumer_rank  [N] entries of cons_width bytes: 0 — nothing is written — when every topic of the batch has
+ *                      P <= C or no subscriber: the consumer of sorted partition k is then cset_rank[cset_off[s] + k]
+ *                      (Main:240-263 on all-zero totals; -1 for a topic without subscribers), which
+ *                      the caller reads from its own table; else 2 (all ones = no subscriber) when there are fewer
+ *                      than 65535 members, else 4 (int32)
+ * Both buffers must hold 4 * N bytes unless the caller knows the widths from an earlier call on the same shape;
+ * part_width / cons_width are set by the call. Works on single- and multi-device contexts. */
+typedef struct lagassign_result_narrow {
+    void   *out_partition;
+    void   *out_consumer_rank;
+    int32_t part_width;          /* out */
+    int32_t cons_width;          /* out */
+} lagassign_result_narrow;
+int  lagassign_assign_batch_narrow(lagassign_ctx *ctx, const lagassign_batch *in,
+                                   lagassign_result_narrow *out);
 
 /* Split form. upload: validate, plan (bin topics by size), copy inputs to HBM.
  * execute: enqueue the kernels (asynchronous, except that batches with topics of

@@ -186,6 +186,8 @@ public class GpuLagBasedPartitionAssignor implements ConsumerPartitionAssignor, 
         int[] topicCset;
         List<int[]> sets;                 // de-duplicated consumer sets (ranks ascending)
         long n;
+        int partWidth = 4;                // bytes per entry of the result buffers (NativeLagAssign.assignBatchNarrow)
+        int consWidth = 4;
     }
 
     private static Map<String, List<TopicPartition>> emptyAssignment(Map<String, List<String>> subscriptions) {
@@ -332,9 +334,13 @@ public class GpuLagBasedPartitionAssignor implements ConsumerPartitionAssignor, 
             NativeLagAssign.assignBatchOffsets(ctx, T, topicOff, part, topicCset, f.sets.size(), csetOff, csetRank,
                 pinned.get("begin"), pinned.get("end"), pinned.get("committed"), pinned.get("has"), latest,
                 outPartition, outConsumer);
+            f.partWidth = 4;
+            f.consWidth = 4;
         } else {
-            NativeLagAssign.assignBatch(ctx, T, topicOff, pinned.get("lag"), part, topicCset,
+            final int w = NativeLagAssign.assignBatchNarrow(ctx, T, topicOff, pinned.get("lag"), part, topicCset,
                 f.sets.size(), csetOff, csetRank, outPartition, outConsumer);                 // replaces Main:177-184
+            f.partWidth = w & 0xFF;
+            f.consWidth = w >> 8;
         }
     }
 
@@ -348,10 +354,20 @@ public class GpuLagBasedPartitionAssignor implements ConsumerPartitionAssignor, 
         long k = 0;
         for (int t = 0; t < f.topics.size(); t++) {
             final String topic = f.topics.get(t);
+            final int[] set = f.sets.get(f.topicCset[t]);
+            final long start = f.topicOff[t];
             for (final long end = f.topicOff[t + 1]; k < end; k++) {
-                final int m = outConsumer.getInt((int) (4 * k));
+                final int i = (int) k;
+                final int m;
+                switch (f.consWidth) {
+                    case 0:  m = set.length == 0 ? -1 : set[(int) (k - start)]; break;     // P <= C: k-th member of the set
+                    case 2:  { final int v = outConsumer.getShort(2 * i) & 0xFFFF; m = v == 0xFFFF ? -1 : v; break; }
+                    default: m = outConsumer.getInt(4 * i);
+                }
                 if (m >= 0) {
-                    byRankList.get(m).add(new TopicPartition(topic, outPartition.getInt((int) (4 * k))));
+                    final int id = f.partWidth == 1 ? outPartition.get(i) & 0xFF
+                                 : f.partWidth == 2 ? outPartition.getShort(2 * i) & 0xFFFF : outPartition.getInt(4 * i);
+                    byRankList.get(m).add(new TopicPartition(topic, id));
                 }
             }
         }

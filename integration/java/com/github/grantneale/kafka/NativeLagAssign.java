@@ -54,4 +54,16 @@ final class NativeLagAssign {
                                           ByteBuffer beginOffset, ByteBuffer endOffset, ByteBuffer committed,
                                           ByteBuffer hasCommitted, boolean resetLatest,
                                           ByteBuffer outPartition, ByteBuffer outConsumerRank);
+
+    /**
+     * lagassign_assign_batch_narrow: like {@link #assignBatch}, but {@code outPartition} receives entries of
+     * {@code w & 0xFF} bytes (1, 2 or 4, unsigned) and {@code outConsumerRank} entries of {@code w >> 8} bytes
+     * (0: nothing written, every topic has P <= C and sorted partition k belongs to the k-th member of the topic's
+     * consumer set; 2: unsigned, 0xFFFF = no subscriber; 4: int), where {@code w} is the return value. Both buffers
+     * need 4 bytes per partition of capacity.
+     */
+    static native int assignBatchNarrow(long ctx,
+                                        long nTopics, ByteBuffer topicOff, ByteBuffer lag, ByteBuffer partition,
+                                        ByteBuffer topicCset, long nCsets, ByteBuffer csetOff, ByteBuffer csetRank,
+                                        ByteBuffer outPartition, ByteBuffer outConsumerRank);
 }

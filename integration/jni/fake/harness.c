@@ -45,6 +45,9 @@ void Java_com_github_grantneale_kafka_NativeLagAssign_assignBatchOffsets(JNIEnv 
                                                                          jobject, jobject, jobject, jobject, jobject, jobject, jboolean,
                                                                          jobject, jobject);
 
+jint Java_com_github_grantneale_kafka_NativeLagAssign_assignBatchNarrow(JNIEnv *, jclass, jlong, jlong, jobject, jobject, jobject, jobject,
+                                                                        jlong, jobject, jobject, jobject, jobject);
+
 /* a fake int[]: length, then the elements */
 typedef struct { jsize n; jint v[8]; } fake_int_array;
 static jsize f_GetArrayLength(JNIEnv *env, jarray a) { (void)env; return ((fake_int_array *)a)->n; }
@@ -93,6 +96,22 @@ int main(int argc, char **argv) {
         return 1;
     }
     printf("ok: README example through the JNI shim: C0=[p0] C1=[p2,p1]\n");
+
+    /* the same example in the narrow result form: 3 partitions over 2 consumers is a multi-round fill -> 1-byte ids, 2-byte consumers */
+    {
+        uint8_t np[12] = {0}, nc[12] = {0};
+        jint w = Java_com_github_grantneale_kafka_NativeLagAssign_assignBatchNarrow(
+            env, NULL, ctx, 1, wrap(env, topic_off, sizeof topic_off), wrap(env, lag, sizeof lag), NULL,
+            wrap(env, topic_cset, sizeof topic_cset), 1, wrap(env, cset_off, sizeof cset_off),
+            wrap(env, cset_rank, sizeof cset_rank), wrap(env, np, sizeof np), wrap(env, nc, sizeof nc));
+        if (pending_class[0]) { printf("FAIL: assignBatchNarrow threw %s: %s\n", pending_class, pending_msg); return 1; }
+        const uint16_t *c16 = (const uint16_t *)nc;
+        if (w != (1 | (2 << 8)) || np[0] != 0 || np[1] != 2 || np[2] != 1 || c16[0] != 0 || c16[1] != 1 || c16[2] != 1) {
+            printf("FAIL: narrow form: widths %d, ids %d %d %d, consumers %d %d %d\n", (int)w, np[0], np[1], np[2], c16[0], c16[1], c16[2]);
+            return 1;
+        }
+        printf("ok: README example in the narrow result form (1-byte ids, 2-byte consumers)\n");
+    }
 
     /* error mapping: a malformed batch must surface as RuntimeException */
     int32_t bad_rank[2] = {1, 1};

@@ -131,3 +131,32 @@ JNIEXPORT void JNICALL Java_com_github_grantneale_kafka_NativeLagAssign_assignBa
     if (rc == LAGASSIGN_OK) rc = lagassign_download(ctx, &out);
     if (rc != LAGASSIGN_OK) throw_runtime(env, "java/lang/RuntimeException", lagassign_last_error(ctx));
 }
+
+/* lagassign_assign_batch_narrow: results as entries of part_width / cons_width bytes (include/lagassign.h); returns
+ * part_width | cons_width << 8. The JVM reads bytes from a direct buffer as cheaply as ints, and at BASELINE config 4
+ * the device-to-host copy shrinks from 8 bytes per partition to 1. */
+JNIEXPORT jint JNICALL Java_com_github_grantneale_kafka_NativeLagAssign_assignBatchNarrow(
+    JNIEnv *env, jclass k, jlong ctxh, jlong nTopics, jobject topicOff, jobject lag, jobject partition,
+    jobject topicCset, jlong nCsets, jobject csetOff, jobject csetRank, jobject outPartition, jobject outConsumerRank) {
+    (void)k;
+    lagassign_ctx *ctx = (lagassign_ctx *)(intptr_t)ctxh;
+    lagassign_batch in;
+    in.n_topics = nTopics;
+    in.topic_off = (const int64_t *)addr(env, topicOff);
+    in.lag = (const int64_t *)addr(env, lag);
+    in.partition = (const int32_t *)addr(env, partition);
+    in.topic_cset = (const int32_t *)addr(env, topicCset);
+    in.n_csets = nCsets;
+    in.cset_off = (const int64_t *)addr(env, csetOff);
+    in.cset_rank = (const int32_t *)addr(env, csetRank);
+    lagassign_result_narrow out;
+    out.out_partition = addr(env, outPartition);
+    out.out_consumer_rank = addr(env, outConsumerRank);
+    out.part_width = out.cons_width = 4;
+    int rc = lagassign_assign_batch_narrow(ctx, &in, &out);
+    if (rc != LAGASSIGN_OK) {
+        throw_runtime(env, "java/lang/RuntimeException", lagassign_last_error(ctx));
+        return 0;
+    }
+    return (jint)(out.part_width | (out.cons_width << 8));
+}

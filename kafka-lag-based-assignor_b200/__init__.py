@@ -50,6 +50,11 @@ class _Result(ctypes.Structure):
                 ("out_total", ctypes.c_void_p), ("out_count", ctypes.c_void_p)]
 
 
+class _ResultNarrow(ctypes.Structure):
+    _fields_ = [("out_partition", ctypes.c_void_p), ("out_consumer_rank", ctypes.c_void_p),
+                ("part_width", ctypes.c_int32), ("cons_width", ctypes.c_int32)]
+
+
 class _Offsets(ctypes.Structure):
     _fields_ = [("begin_offset", ctypes.c_void_p), ("end_offset", ctypes.c_void_p),
                 ("committed", ctypes.c_void_p), ("has_committed", ctypes.c_void_p),
@@ -100,6 +105,7 @@ def load_library() -> ctypes.CDLL:
     L.lagassign_last_error.restype = ctypes.c_char_p
     L.lagassign_set_option.argtypes = [vp, i32, i64]
     L.lagassign_assign_batch.argtypes = [vp, ctypes.POINTER(_Batch), ctypes.POINTER(_Result)]
+    L.lagassign_assign_batch_narrow.argtypes = [vp, ctypes.POINTER(_Batch), ctypes.POINTER(_ResultNarrow)]
     L.lagassign_upload.argtypes = [vp, ctypes.POINTER(_Batch)]
     L.lagassign_upload_offsets.argtypes = [vp, ctypes.POINTER(_Batch), ctypes.POINTER(_Offsets)]
     L.lagassign_execute.argtypes = [vp]
@@ -121,7 +127,7 @@ def load_library() -> ctypes.CDLL:
     L.lagassign_host_free.argtypes = [vp]
     for name in ("lagassign_device_count", "lagassign_create", "lagassign_create_on_stream", "lagassign_create_multi",
                  "lagassign_shard_count",
-                 "lagassign_set_option", "lagassign_assign_batch", "lagassign_upload",
+                 "lagassign_set_option", "lagassign_assign_batch", "lagassign_assign_batch_narrow", "lagassign_upload",
                  "lagassign_upload_offsets", "lagassign_execute", "lagassign_sync", "lagassign_download",
                  "lagassign_bind_device_outputs", "lagassign_download_lags", "lagassign_get_stats",
                  "lagassign_profile_count", "lagassign_profile_entry",
@@ -322,6 +328,23 @@ class FlatAssignor:
         self._check(self._L.lagassign_assign_batch(self._ctx, ctypes.byref(b), ctypes.byref(r)))
         self._shape = shape
         return dict(out_partition=op, out_consumer_rank=oc, out_total=ot, out_count=on)
+
+    def assign_batch_narrow(self, topic_off, lag, partition, topic_cset, cset_off, cset_rank,
+                            out_partition=None, out_consumer_rank=None):
+        """lagassign_assign_batch_narrow(): results as arrays of part_width / cons_width bytes (see lagassign.h).
+        Returns dict(out_partition=uint8/16/32 array, out_consumer_rank=uint16/uint32 array or None when cons_width
+        is 0, part_width, cons_width). Buffers given by the caller must be uint8 arrays of 4 * N bytes."""
+        b, keep, shape = self._batch(topic_off, lag, partition, topic_cset, cset_off, cset_rank)
+        T, N, total_tc = shape
+        op = np.empty(4 * N, np.uint8) if out_partition is None else out_partition
+        oc = np.empty(4 * N, np.uint8) if out_consumer_rank is None else out_consumer_rank
+        r = _ResultNarrow(_ptr(op), _ptr(oc), 0, 0)
+        self._check(self._L.lagassign_assign_batch_narrow(self._ctx, ctypes.byref(b), ctypes.byref(r)))
+        self._shape = shape
+        dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}
+        part = op[:N * r.part_width].view(dt[r.part_width])
+        cons = None if r.cons_width == 0 else oc[:N * r.cons_width].view(dt[r.cons_width])
+        return dict(out_partition=part, out_consumer_rank=cons, part_width=int(r.part_width), cons_width=int(r.cons_width))
 
     def profile(self) -> dict:
         """{kernel name: (milliseconds, launches)} of the last execute() (OPT_PROFILE on)."""

@@ -86,11 +86,41 @@ k_exchange_unpack(UnpackArgs a) {
     }
 }
 
+// narrow form with separate destinations (lagassign_assign_batch_narrow): entry e of `part` / `cons` -> dp[e] / dc[e]
+template <int PW, int CW>
+__global__ void __launch_bounds__(256)
+k_narrow_results(int64_t n, const int32_t* __restrict__ part, const int32_t* __restrict__ cons,
+                 uint8_t* __restrict__ dpart, uint8_t* __restrict__ dcons) {
+    using PT = typename Narrow<PW>::type;
+    PT* dp = reinterpret_cast<PT*>(dpart);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        dp[e] = (PT)(uint32_t)part[e];
+        if constexpr (CW != 0) {
+            using CT = typename Narrow<CW>::type;
+            reinterpret_cast<CT*>(dcons)[e] = (CT)(uint32_t)cons[e];        // -1 (no subscriber) becomes all ones
+        }
+    }
+}
+
 thread_local const char* g_exch_err = "";
 
 int exch_fail(const char* m) { g_exch_err = m; return LAGASSIGN_ERR_ARG; }
 
 }  // namespace
+
+namespace lagassign {
+// every (pw, cw) of lagassign_narrow_widths except (4, 4), which is the int32 arrays themselves; false otherwise
+bool launch_narrow_results(cudaStream_t st, int64_t n, const int32_t* part, const int32_t* cons, int pw, int cw,
+                           uint8_t* dpart, uint8_t* dcons) {
+    if (n <= 0) return true;
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+#define NARROW_CASE(PW, CW) if (pw == PW && cw == CW) { k_narrow_results<PW, CW><<<grid, 256, 0, st>>>(n, part, cons, dpart, dcons); return true; }
+    NARROW_CASE(1, 0) NARROW_CASE(2, 0) NARROW_CASE(4, 0) NARROW_CASE(1, 2) NARROW_CASE(2, 2) NARROW_CASE(4, 2)
+    NARROW_CASE(1, 4) NARROW_CASE(2, 4)
+#undef NARROW_CASE
+    return false;
+}
+}  // namespace lagassign
 
 extern "C" {
 

@@ -111,6 +111,12 @@ struct lagassign_ctx {
     std::vector<cudaEvent_t> pipe_events;
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};   // execute(): size bins on concurrent streams
     int64_t pipe_chunk_elems = 0;   // 0 = default (LAGASSIGN_OPT_PIPE_CHUNK)
+    // narrow result form (lagassign_assign_batch_narrow): widths this batch's shape allows (set with the plan),
+    // widths imposed by a multi-device parent (0 = none), and the device staging buffers
+    int64_t plan_max_p = 0;
+    bool plan_multi_round = false;
+    int forced_pw = 0, forced_cw = -1;
+    DevBuf d_narrow_part, d_narrow_cons;
     // Plan cache: a consumer group is rebalanced again and again over the same topics and
     // subscriptions with fresh lags, so the batch SHAPE (everything but lag / partition ids /
     // offsets) usually repeats. When it does, the plan and the metadata already on the device
@@ -142,6 +148,32 @@ struct lagassign_ctx {
 };
 
 namespace {
+
+// Where a call's results go: the int32 arrays of lagassign_result (pw = cw = 4, copied as they are) or the narrow
+// form of lagassign_result_narrow (entries of pw / cw bytes, packed on the device before they cross PCIe).
+struct OutSpec {
+    int pw = 4, cw = 4;
+    bool narrow = false;
+    uint8_t* h_part = nullptr;     // host destinations; null = not wanted
+    uint8_t* h_cons = nullptr;
+    int64_t* h_total = nullptr;
+    int32_t* h_count = nullptr;
+};
+
+OutSpec spec_of(const lagassign_result* out) {
+    OutSpec o;
+    o.h_part = reinterpret_cast<uint8_t*>(out->out_partition);
+    o.h_cons = reinterpret_cast<uint8_t*>(out->out_consumer_rank);
+    o.h_total = out->out_total;
+    o.h_count = out->out_count;
+    return o;
+}
+
+// widths of the narrow form for a planned batch (include/lagassign.h, lagassign_assign_batch_narrow)
+void narrow_widths_of(bool has_part, int64_t max_p, bool multi_round, int64_t n_members, int* pw, int* cw) {
+    *pw = has_part ? 4 : (max_p <= 256 ? 1 : (max_p <= 65536 ? 2 : 4));
+    *cw = !multi_round ? 0 : (n_members < 65535 ? 2 : 4);      // 0xFFFF stands for "no subscriber" (-1)
+}
 
 int fail(lagassign_ctx* ctx, int code, const char* fmt, ...) {
     char buf[512];
@@ -234,13 +266,16 @@ int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
     tc_off.assign((size_t)T + 1, 0);
     ctx->n_segs = 0;
     ctx->fill_ws_elems = 0;
-    int64_t boff = 0, tiles = 0, assigned = 0;
+    int64_t boff = 0, tiles = 0, assigned = 0, max_p = 0;
+    bool multi_round = false;
     for (int64_t t = 0; t < T; ++t) {
         const int32_t s = in->topic_cset[t];
         if (s < 0 || s >= S) return fail(ctx, LAGASSIGN_ERR_ARG, "topic_cset[%lld] out of range", (long long)t);
         const int64_t P = in->topic_off[t + 1] - in->topic_off[t];
         const int64_t C = in->cset_off[s + 1] - in->cset_off[s];
         tc_off[(size_t)t + 1] = tc_off[(size_t)t] + C;
+        max_p = std::max(max_p, P);
+        multi_round = multi_round || (C > 0 && P > C);
         if (P == 0) continue;
         if (C == 0 && !ctx->sort_only) { l_none.push_back((int32_t)t); continue; }
         assigned += P;
@@ -287,6 +322,8 @@ int validate_and_plan(lagassign_ctx* ctx, const lagassign_batch* in,
     }
     ctx->T = T; ctx->N = N; ctx->S = S; ctx->R = R;
     ctx->n_members = n_members;
+    ctx->plan_max_p = max_p;
+    ctx->plan_multi_round = multi_round;
     ctx->total_tc = tc_off[(size_t)T];
     ctx->n_assigned = assigned;
     ctx->big_elems = boff;
@@ -555,7 +592,7 @@ constexpr int64_t PIPE_CHUNK_ELEMS = 3 << 20;    // ~24 MB of lags per chunk
 // into contiguous topic ranges and the three legs (H2D of the lags, kernels, D2H of
 // the results) of successive chunks overlap on three streams. PCIe is full duplex,
 // so the call approaches max(H2D, D2H) instead of their sum.
-int assign_batch_pipelined_impl(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_result* out, std::vector<cudaEvent_t>& tev) {
+int assign_batch_pipelined_impl(lagassign_ctx* ctx, const lagassign_batch* in, const OutSpec& out, std::vector<cudaEvent_t>& tev) {
     if (!ctx->stream_in) {
         CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking));
         CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking));
@@ -635,16 +672,27 @@ int assign_batch_pipelined_impl(lagassign_ctx* ctx, const lagassign_batch* in, c
             slice(ctx->h_list_cta[c2], lo, hi);
             if (hi > lo) { launch_cta_topics(b, ctx->d_list_cta[c2].as<int32_t>() + lo, hi - lo, c2, ctx->sm_count, ctx->stream); ++launches; }
         }
+        const uint8_t* d2h_part = reinterpret_cast<const uint8_t*>(src_part + e0);
+        const uint8_t* d2h_cons = reinterpret_cast<const uint8_t*>(src_cons + e0);
+        if (n && out.narrow) {
+            // the chunk's results in their narrow form (one small kernel behind the chunk's sort kernels)
+            uint8_t* np = ctx->d_narrow_part.as<uint8_t>() + e0 * out.pw;
+            uint8_t* nc = ctx->d_narrow_cons.as<uint8_t>() + e0 * out.cw;
+            if (!launch_narrow_results(ctx->stream, (int64_t)n, src_part + e0, src_cons + e0, out.pw, out.cw, np, nc))
+                return fail(ctx, LAGASSIGN_ERR_ARG, "narrow result widths %d / %d", out.pw, out.cw);
+            ++launches;
+            d2h_part = np; d2h_cons = nc;
+        }
         CUDA_TRY(ctx, cudaEventRecord(ev_out, ctx->stream));
         if (ctx->trace) CUDA_TRY(ctx, cudaEventRecord(tev[2 + 3 * c], ctx->stream));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_out, ev_out, 0));
-        if (n && out->out_partition) {
-            CUDA_TRY(ctx, cudaMemcpyAsync(out->out_partition + e0, src_part + e0, n * 4, cudaMemcpyDeviceToHost, ctx->stream_out));
-            ctx->stats.d2h_bytes += (int64_t)n * 4;
+        if (n && out.h_part) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(out.h_part + e0 * out.pw, d2h_part, n * out.pw, cudaMemcpyDeviceToHost, ctx->stream_out));
+            ctx->stats.d2h_bytes += (int64_t)n * out.pw;
         }
-        if (n && out->out_consumer_rank) {
-            CUDA_TRY(ctx, cudaMemcpyAsync(out->out_consumer_rank + e0, src_cons + e0, n * 4, cudaMemcpyDeviceToHost, ctx->stream_out));
-            ctx->stats.d2h_bytes += (int64_t)n * 4;
+        if (n && out.h_cons && out.cw) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(out.h_cons + e0 * out.cw, d2h_cons, n * out.cw, cudaMemcpyDeviceToHost, ctx->stream_out));
+            ctx->stats.d2h_bytes += (int64_t)n * out.cw;
         }
         if (ctx->trace) CUDA_TRY(ctx, cudaEventRecord(tev[3 + 3 * c], ctx->stream_out));
         t_lo = t_hi;
@@ -671,7 +719,7 @@ int assign_batch_pipelined_impl(lagassign_ctx* ctx, const lagassign_batch* in, c
     return LAGASSIGN_OK;
 }
 
-int assign_batch_pipelined(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_result* out) {
+int assign_batch_pipelined(lagassign_ctx* ctx, const lagassign_batch* in, const OutSpec& out) {
     std::vector<cudaEvent_t> tev;
     const int rc = assign_batch_pipelined_impl(ctx, in, out, tev);
     if (rc != LAGASSIGN_OK) {
@@ -745,6 +793,7 @@ int multi_execute(lagassign_ctx* ctx);
 int multi_sync(lagassign_ctx* ctx);
 int multi_download(lagassign_ctx* ctx, const lagassign_result* out);
 int multi_assign_batch(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_result* out);
+int multi_assign_batch_narrow(lagassign_ctx* ctx, const lagassign_batch* in, lagassign_result_narrow* out);
 
 }  // namespace
 
@@ -781,7 +830,7 @@ void lagassign_destroy(lagassign_ctx* ctx) {
                       &ctx->d_hascommitted, &ctx->d_list_warp, &ctx->d_list_cta[0], &ctx->d_list_cta[1], &ctx->d_list_cta[2], &ctx->d_list_cta[3], &ctx->d_list_none,
                       &ctx->d_list_fill, &ctx->d_bt_topic, &ctx->d_bt_off, &ctx->d_bt_P, &ctx->d_bt_boff,
                       &ctx->d_bt_tile0, &ctx->d_tile_bt, &ctx->d_keyA, &ctx->d_keyB, &ctx->d_payA,
-                      &ctx->d_payB, &ctx->d_dig, &ctx->d_fill_ws_off, &ctx->d_fill_ws_key, &ctx->d_fill_ws_idx, &ctx->d_range, &ctx->d_pass_rec, &ctx->d_sel, &ctx->d_need_tie,
+                      &ctx->d_payB, &ctx->d_dig, &ctx->d_narrow_part, &ctx->d_narrow_cons, &ctx->d_fill_ws_off, &ctx->d_fill_ws_key, &ctx->d_fill_ws_idx, &ctx->d_range, &ctx->d_pass_rec, &ctx->d_sel, &ctx->d_need_tie,
                       &ctx->d_status, &ctx->d_seg_total, &ctx->d_bt_seg0, &ctx->d_seg_bt, &ctx->d_tile_desc, &ctx->d_ticket, &ctx->d_out_part, &ctx->d_out_cons,
                       &ctx->d_out_total, &ctx->d_out_count};
     for (DevBuf* b : bufs) b->release();
@@ -1027,33 +1076,39 @@ int lagassign_sync(lagassign_ctx* ctx) {
     return LAGASSIGN_OK;
 }
 
-int lagassign_download(lagassign_ctx* ctx, const lagassign_result* out) {
-    if (ctx && !ctx->shards.empty()) return multi_download(ctx, out);
-    if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
-    if (!out) return fail(ctx, LAGASSIGN_ERR_ARG, "result is NULL");
+static int download_spec(lagassign_ctx* ctx, const OutSpec& out) {
     if (!ctx->executed) return fail(ctx, LAGASSIGN_ERR_STATE, "download() before execute()");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t N = (size_t)ctx->N;
     ctx->stats.d2h_bytes = 0;
     const int32_t* src_part = ctx->bound_part ? ctx->bound_part : ctx->d_out_part.as<int32_t>();
     const int32_t* src_cons = ctx->bound_cons ? ctx->bound_cons : ctx->d_out_cons.as<int32_t>();
-    if (N && out->out_partition) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(out->out_partition, src_part, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        ctx->stats.d2h_bytes += (int64_t)N * 4;
+    const uint8_t* d2h_part = reinterpret_cast<const uint8_t*>(src_part);
+    const uint8_t* d2h_cons = reinterpret_cast<const uint8_t*>(src_cons);
+    if (N && out.narrow) {
+        if (!launch_narrow_results(ctx->stream, (int64_t)N, src_part, src_cons, out.pw, out.cw,
+                                   ctx->d_narrow_part.as<uint8_t>(), ctx->d_narrow_cons.as<uint8_t>()))
+            return fail(ctx, LAGASSIGN_ERR_ARG, "narrow result widths %d / %d", out.pw, out.cw);
+        d2h_part = ctx->d_narrow_part.as<uint8_t>();
+        d2h_cons = ctx->d_narrow_cons.as<uint8_t>();
     }
-    if (N && out->out_consumer_rank) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(out->out_consumer_rank, src_cons, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        ctx->stats.d2h_bytes += (int64_t)N * 4;
+    if (N && out.h_part) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(out.h_part, d2h_part, N * out.pw, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += (int64_t)N * out.pw;
     }
-    if ((out->out_total || out->out_count) && !ctx->want_totals)
+    if (N && out.h_cons && out.cw) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(out.h_cons, d2h_cons, N * out.cw, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += (int64_t)N * out.cw;
+    }
+    if ((out.h_total || out.h_count) && !ctx->want_totals)
         return fail(ctx, LAGASSIGN_ERR_STATE, "out_total/out_count requested but LAGASSIGN_OPT_TOTALS was not enabled before upload()");
     const size_t TC = (size_t)ctx->total_tc;
-    if (TC && out->out_total) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(out->out_total, ctx->d_out_total.p, TC * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (TC && out.h_total) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(out.h_total, ctx->d_out_total.p, TC * 8, cudaMemcpyDeviceToHost, ctx->stream));
         ctx->stats.d2h_bytes += (int64_t)TC * 8;
     }
-    if (TC && out->out_count) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(out->out_count, ctx->d_out_count.p, TC * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (TC && out.h_count) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(out.h_count, ctx->d_out_count.p, TC * 4, cudaMemcpyDeviceToHost, ctx->stream));
         ctx->stats.d2h_bytes += (int64_t)TC * 4;
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1065,13 +1120,30 @@ int lagassign_download(lagassign_ctx* ctx, const lagassign_result* out) {
     return LAGASSIGN_OK;
 }
 
-int lagassign_assign_batch(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_result* out) {
-    if (ctx && !ctx->shards.empty()) return multi_assign_batch(ctx, in, out);
+int lagassign_download(lagassign_ctx* ctx, const lagassign_result* out) {
+    if (ctx && !ctx->shards.empty()) return multi_download(ctx, out);
     if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
     if (!out) return fail(ctx, LAGASSIGN_ERR_ARG, "result is NULL");
+    return download_spec(ctx, spec_of(out));
+}
+
+// upload (plan cache) + kernels + download for one device; `narrow`: results leave in the narrow form, whose widths
+// are decided here from the plan (or imposed by the multi-device parent) and reported back
+static int assign_batch_one(lagassign_ctx* ctx, const lagassign_batch* in, OutSpec out, bool narrow, int* pw_out, int* cw_out) {
     const auto t0 = std::chrono::steady_clock::now();
     TRY(do_upload(ctx, in, nullptr, /*defer_data=*/true));     // plan + metadata; the large arrays follow
-    if (ctx->n_big == 0 && !ctx->want_totals && !ctx->want_group && ctx->N >= PIPE_MIN_ELEMS && !out->out_total && !out->out_count) {
+    if (narrow) {
+        narrow_widths_of(ctx->has_part, ctx->plan_max_p, ctx->plan_multi_round, ctx->n_members, &out.pw, &out.cw);
+        if (ctx->forced_pw) { out.pw = ctx->forced_pw; out.cw = ctx->forced_cw; }
+        out.narrow = !(out.pw == 4 && out.cw == 4);
+        if (pw_out) *pw_out = out.pw;
+        if (cw_out) *cw_out = out.cw;
+        if (out.narrow) {
+            CUDA_TRY(ctx, ctx->d_narrow_part.ensure(std::max<size_t>((size_t)ctx->N * out.pw, 16)));
+            CUDA_TRY(ctx, ctx->d_narrow_cons.ensure(std::max<size_t>((size_t)ctx->N * out.cw, 16)));
+        }
+    }
+    if (ctx->n_big == 0 && !ctx->want_totals && !ctx->want_group && ctx->N >= PIPE_MIN_ELEMS && !out.h_total && !out.h_count) {
         const auto t1 = std::chrono::steady_clock::now();
         const int rc = assign_batch_pipelined(ctx, in, out);
         if (ctx->trace) {
@@ -1083,7 +1155,28 @@ int lagassign_assign_batch(lagassign_ctx* ctx, const lagassign_batch* in, const 
     }
     TRY(upload_data_now(ctx, in));
     TRY(lagassign_execute(ctx));
-    return lagassign_download(ctx, out);
+    return download_spec(ctx, out);
+}
+
+int lagassign_assign_batch(lagassign_ctx* ctx, const lagassign_batch* in, const lagassign_result* out) {
+    if (ctx && !ctx->shards.empty()) return multi_assign_batch(ctx, in, out);
+    if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
+    if (!out) return fail(ctx, LAGASSIGN_ERR_ARG, "result is NULL");
+    return assign_batch_one(ctx, in, spec_of(out), /*narrow=*/false, nullptr, nullptr);
+}
+
+int lagassign_assign_batch_narrow(lagassign_ctx* ctx, const lagassign_batch* in, lagassign_result_narrow* out) {
+    if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
+    if (!out) return fail(ctx, LAGASSIGN_ERR_ARG, "result is NULL");
+    if (!ctx->shards.empty()) return multi_assign_batch_narrow(ctx, in, out);
+    OutSpec o;
+    o.h_part = static_cast<uint8_t*>(out->out_partition);
+    o.h_cons = static_cast<uint8_t*>(out->out_consumer_rank);
+    int pw = 4, cw = 4;
+    const int rc = assign_batch_one(ctx, in, o, /*narrow=*/true, &pw, &cw);
+    out->part_width = pw;
+    out->cons_width = cw;
+    return rc;
 }
 
 int lagassign_bind_device_outputs(lagassign_ctx* ctx, int32_t* d_out_partition, int32_t* d_out_consumer_rank) {
@@ -1346,6 +1439,43 @@ int multi_assign_batch(lagassign_ctx* ctx, const lagassign_batch* in, const laga
         const lagassign_batch b = shard_batch(ctx, in, i);
         const lagassign_result o = shard_result(ctx, out, i);
         return lagassign_assign_batch(ctx->shards[i], &b, &o);
+    });
+    multi_collect_stats(ctx);
+    ctx->uploaded = ctx->executed = rc == LAGASSIGN_OK;
+    return rc;
+}
+
+// Narrow form over several devices: the widths are those of the WHOLE batch (every shard writes entries of the same
+// size into the caller's arrays at its range's offset).
+int multi_assign_batch_narrow(lagassign_ctx* ctx, const lagassign_batch* in, lagassign_result_narrow* out) {
+    ctx->uploaded = ctx->executed = false;
+    TRY(multi_split(ctx, in));
+    int64_t max_p = 0, n_members = 0;
+    bool multi_round = false;
+    for (int64_t t = 0; t < in->n_topics; ++t) {
+        const int64_t P = in->topic_off[t + 1] - in->topic_off[t];
+        const int32_t s = in->topic_cset[t];
+        const int64_t C = in->cset_off[s + 1] - in->cset_off[s];
+        max_p = std::max(max_p, P);
+        multi_round = multi_round || (C > 0 && P > C);
+    }
+    if (in->cset_rank)
+        for (int64_t j = 0; j < in->cset_off[in->n_csets]; ++j) n_members = std::max<int64_t>(n_members, (int64_t)in->cset_rank[j] + 1);
+    int pw = 4, cw = 4;
+    narrow_widths_of(in->partition != nullptr, max_p, multi_round, n_members, &pw, &cw);
+    out->part_width = pw;
+    out->cons_width = cw;
+    const int rc = multi_for_each(ctx, [&](size_t i) {
+        const lagassign_batch b = shard_batch(ctx, in, i);
+        const auto& r = ctx->shard_ranges[i];
+        lagassign_result_narrow o = *out;
+        o.out_partition = out->out_partition ? static_cast<uint8_t*>(out->out_partition) + r.e0 * pw : nullptr;
+        o.out_consumer_rank = out->out_consumer_rank ? static_cast<uint8_t*>(out->out_consumer_rank) + r.e0 * cw : nullptr;
+        ctx->shards[i]->forced_pw = pw;
+        ctx->shards[i]->forced_cw = cw;
+        const int rc1 = lagassign_assign_batch_narrow(ctx->shards[i], &b, &o);
+        ctx->shards[i]->forced_pw = 0;
+        return rc1;
     });
     multi_collect_stats(ctx);
     ctx->uploaded = ctx->executed = rc == LAGASSIGN_OK;

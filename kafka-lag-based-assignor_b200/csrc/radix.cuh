@@ -420,8 +420,6 @@ struct PassSmem {
     int32_t dst_base[256];           // index in the topic of the tile's first element of each digit, minus its tile-local offset
     uint32_t wsum[8];
     alignas(8) uint64_t full_bar[RT_STAGES];
-    alignas(16) int4 desc[RT_STAGES + 2][3];   // descriptors of the tiles it .. it+RT_STAGES+1 (ring): {b, tile_in_topic, n_valid, seg},
-                                               // {buf_off, raw_off}, {pass record, -, -, -}
 };
 
 #ifdef LAGASSIGN_RT_TIMING
@@ -459,33 +457,24 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
     int t_tiles = 0;
 #endif
 
-    // A tile's geometry is one 32-byte record plus the word k_big_scan wrote for (pass, tile): which buffer the
-    // topic reads / writes in this pass (-1: pass skipped for the topic, or no such tile) and its next executed pass.
-    // ONE thread fetches the records of upcoming tiles into a small ring in shared memory (three independent
-    // loads, issued a whole tile ahead of their first use); everybody else reads the current tile's record from
-    // there. (Before: every thread carried four tiles' records in registers and fetched them with dependent global
-    // loads at the top of the loop: 13 % of a tile's cycles with all warps stalled, and 128 registers.)
+    // A tile's geometry is one 32-byte record; the record also remembers which buffer the
+    // topic reads in this pass (-1: pass skipped for the topic, or no such tile).
     struct Tile { TileDesc d; int src, dst, nxt_pass; };
-    constexpr int DESC_SLOTS = RT_STAGES + 2;
-    constexpr int LOADER_TID = 64;
-    auto fetch_desc = [&](int g, int4& a, int4& c, int4& r) {       // global -> registers (loader thread)
-        a = make_int4(-1, 0, 0, 0); c = make_int4(0, 0, 0, 0); r = make_int4(0x00FFFFFF, 0, 0, 0);   // src = dst = nxt = -1
-        if (g < n_tiles) {
-            a = __ldg(bt.tile_desc + 2 * (size_t)g);
-            c = __ldg(bt.tile_desc + 2 * (size_t)g + 1);
-            r.x = (int)__ldg(bt.pass_rec + (size_t)pass * n_tiles + g);
-        }
-    };
-    auto read_desc = [&](int slot) {                                   // shared memory -> registers (broadcast)
-        const int4 a = sm.desc[slot][0], c = sm.desc[slot][1];
-        const uint32_t rec = (uint32_t)sm.desc[slot][2].x;
+    auto load_tile = [&](int g) {
         Tile t;
-        t.d.b = a.x; t.d.tile_in_topic = a.y; t.d.n_valid = a.z; t.d.seg = a.w;
-        t.d.buf_off = ((int64_t)(uint32_t)c.y << 32) | (uint32_t)c.x;
-        t.d.raw_off = ((int64_t)(uint32_t)c.w << 32) | (uint32_t)c.z;
-        t.src = (int)(int8_t)(rec & 0xFFu);
-        t.dst = (int)(int8_t)((rec >> 8) & 0xFFu);
-        t.nxt_pass = (int)(int8_t)((rec >> 16) & 0xFFu);   // the topic's next executed pass (-1: none)
+        t.src = SEL_SKIP;
+        t.dst = SEL_SKIP;
+        t.nxt_pass = -1;
+        t.d.b = -1;
+        if (g < n_tiles) {
+            const int4 a = __ldg(bt.tile_desc + 2 * (size_t)g), c = __ldg(bt.tile_desc + 2 * (size_t)g + 1);
+            t.d.b = a.x; t.d.tile_in_topic = a.y; t.d.n_valid = a.z; t.d.seg = a.w;
+            t.d.buf_off = ((int64_t)(uint32_t)c.y << 32) | (uint32_t)c.x;
+            t.d.raw_off = ((int64_t)(uint32_t)c.w << 32) | (uint32_t)c.z;
+            t.src = bt.sel_src[t.d.b * N_PASS + pass];
+            t.dst = bt.sel_dst[t.d.b * N_PASS + pass];
+            t.nxt_pass = bt.nxt_pass[t.d.b * N_PASS + pass];   // the topic's next executed pass (-1: none)
+        }
         return t;
     };
     // A raw source (the caller's lag array) is only 8-byte aligned: the copy then starts one element early.
@@ -511,57 +500,49 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
         }
     };
 
-    const int G = (int)gridDim.x;
-    const int g0 = (int)blockIdx.x;
     if (tid == 0) {
 #pragma unroll
         for (int j = 0; j < RT_STAGES; ++j) mbar_init(&sm.full_bar[j], 1);
         fence_mbar_init();
     }
-    if (tid >= 32 && tid < 32 + RT_STAGES + 1) {      // records of the tiles of iterations 0 .. RT_STAGES
-        int4 a, c, r;
-        fetch_desc(g0 + (tid - 32) * G, a, c, r);
-        sm.desc[tid - 32][0] = a; sm.desc[tid - 32][1] = c; sm.desc[tid - 32][2] = r;
-    }
 #pragma unroll
     for (int w = 0; w < SC_WARPS / 2; ++w)
         if (tid < 256) sm.whist[w][tid] = 0;
     __syncthreads();
+    const int G = (int)gridDim.x;
     uint32_t* const my_cnt = sm.whist[warp >> 1];      // this warp's counters: the (warp & 1) half of these words
     const int my_sh = (warp & 1) * 16;
-    // The tile of iteration it + j (j < RT_STAGES) is being fetched into ring stage (it + j) % RT_STAGES; the tile
-    // after those is fetched into the stage of the current tile as soon as every thread has read the tile-local
-    // scatter back out of it, BEFORE the global stores are issued — so a warp that is held up by the store queue
-    // does not hold up the refill, and warps flow from their stores straight into the next tile (whose first
-    // barrier comes after its ranking).
+    const int g0 = (int)blockIdx.x;
+    // q[j] = the tile of iteration it + j, already being fetched into ring stage (it + j) % RT_STAGES; `far` is the
+    // tile after those: it is fetched into the stage of the current tile as soon as every thread has read the
+    // tile-local scatter back out of it, BEFORE the global stores are issued — so a warp that is held up by the
+    // store queue does not hold up the refill, and warps flow from their stores straight into the next tile
+    // (whose first barrier comes after its ranking).
+    Tile q[RT_STAGES];
+#pragma unroll
+    for (int j = 0; j < RT_STAGES; ++j) q[j] = load_tile(g0 + j * G);
     if (tid == 0) {
 #pragma unroll
-        for (int j = 0; j < RT_STAGES; ++j) issue_loads(j, read_desc(j));
+        for (int j = 0; j < RT_STAGES; ++j) issue_loads(j, q[j]);
     }
+    Tile far = load_tile(g0 + RT_STAGES * G);
     uint32_t phase = 0u;                   // bit j: parity of the next completion of stage j's barrier
     int s = 0;                             // ring stage of the tile being processed
-    int slot = 0;                          // descriptor slot of the tile being processed
 
     for (int it = 0;; ++it) {
         const int g = g0 + it * G;
         if (g >= n_tiles) break;
-        // loader: the record of tile it + RT_STAGES + 1 goes to the slot tile it - 1 had (nobody reads that any more:
-        // every thread read it before the first barrier of the previous iteration)
-        int4 la, lc, lr;
-        if (tid == LOADER_TID) fetch_desc(g + (RT_STAGES + 1) * G, la, lc, lr);
-        const int slot_new = (slot == 0) ? DESC_SLOTS - 1 : slot - 1;           // == (it + RT_STAGES + 1) % DESC_SLOTS
-        int slot_refill = slot + RT_STAGES; if (slot_refill >= DESC_SLOTS) slot_refill -= DESC_SLOTS;
-        const Tile cur = read_desc(slot);
-        Tile refill = cur;                     // (thread 0 only) the next occupant of this tile's stage, read now so that the
-        if (tid == 0) refill = read_desc(slot_refill);   // bulk copies below are not issued behind a shared-memory queue
-        slot = (slot + 1 == DESC_SLOTS) ? 0 : slot + 1;
+        const Tile cur = q[0];
+#pragma unroll
+        for (int j = 0; j + 1 < RT_STAGES; ++j) q[j] = q[j + 1];
+        q[RT_STAGES - 1] = far;                                    // tile it + RT_STAGES: next occupant of this stage
+        far = load_tile(g + (RT_STAGES + 1) * G);
+        const Tile refill = q[RT_STAGES - 1];
         RT_TICK(0);
         const int s_cur = s;
         s = (s + 1 == RT_STAGES) ? 0 : s + 1;
         if (cur.src == SEL_SKIP) {           // this topic's digit is constant in this pass: nothing was fetched,
-            if (tid == LOADER_TID) { sm.desc[slot_new][0] = la; sm.desc[slot_new][1] = lc; sm.desc[slot_new][2] = lr; }
-            __syncthreads();                 // (orders the record ring; the stage itself is free: its last reader passed a barrier long ago)
-            if (tid == 0) issue_loads(s_cur, refill);
+            if (tid == 0) issue_loads(s_cur, refill);   // the stage is free (its last reader passed a barrier long ago)
             continue;
         }
 
@@ -620,7 +601,6 @@ k_big_scatter(BigTopics bt, int pass, const int64_t* __restrict__ lag, const int
             }
         }
         __syncthreads();   // all counts in; every thread holds its elements in registers (the stage may be overwritten)
-        if (tid == LOADER_TID) { sm.desc[slot_new][0] = la; sm.desc[slot_new][1] = lc; sm.desc[slot_new][2] = lr; }
         RT_TICK(3);
 
         // thread d owns digit value d: offsets over warps and over digits inside the tile
@@ -763,26 +743,53 @@ k_big_finalize(BigTopics bt, const int64_t* __restrict__ lag, const int32_t* __r
                int32_t* __restrict__ out_part, int32_t* __restrict__ out_cons,
                int64_t* __restrict__ out_total, int32_t* __restrict__ out_count) {
     int bad = 0;
+    // What a tile needs to know about its topic sits behind three levels of dependent loads (tile -> topic ->
+    // consumer set): ~2 us of latency against < 1 us of copying per tile. The next tile's are fetched while the
+    // current tile is processed (BASELINE config 5: this kernel 0.22 -> see profiles/).
+    struct Meta { int b, t, sel, tile0; int64_t P, off, boff, coff, C; int8_t all_equal; };
+    auto load_meta = [&](int g) {
+        Meta m;
+        m.b = -1; m.t = 0; m.sel = SEL_RAW; m.tile0 = 0; m.P = 0; m.off = 0; m.boff = 0; m.coff = 0; m.C = 0; m.all_equal = 0;
+        if (g < bt.n_tiles) {
+            m.b = bt.tile_bt[g];
+            m.t = bt.topic[m.b];
+            m.P = bt.P[m.b]; m.off = bt.off[m.b]; m.boff = bt.boff[m.b];
+            m.sel = bt.sel_final[m.b];
+            m.all_equal = bt.all_equal[m.b];
+            m.tile0 = bt.tile0[m.b];
+            const int s = topic_cset[m.t];
+            m.coff = cset_off[s];
+            m.C = cset_off[s + 1] - m.coff;
+        }
+        return m;
+    };
+    Meta nxt = load_meta((int)blockIdx.x);
     for (int g = blockIdx.x; g < bt.n_tiles; g += gridDim.x) {
-        const int b = bt.tile_bt[g];
-        const int t = bt.topic[b];
-        const int64_t P = bt.P[b], off = bt.off[b], boff = bt.boff[b];
-        const int sel = bt.sel_final[b];
+        const Meta cur = nxt;
+        nxt = load_meta(g + (int)gridDim.x);
+        const int b = cur.b;
+        const int t = cur.t;
+        const int64_t P = cur.P, off = cur.off, boff = cur.boff;
+        const int sel = cur.sel;
         const uint64_t* fkey = (sel == SEL_A) ? bt.keyA + boff : bt.keyB + boff;
         const uint32_t* fpay = (sel == SEL_A) ? bt.payA + boff : bt.payB + boff;
-        const int s = topic_cset[t];
-        const int64_t coff = cset_off[s], C = cset_off[s + 1] - coff;
+        const int64_t coff = cur.coff, C = cur.C;
         const bool single_round = P <= C;
         // All lags equal (an idle topic: zero everywhere): every round starts with equal
         // totals, so its picks are the members in id order and the sorted partition k goes to
         // member k mod C. No sequential fill is needed.
-        const bool cyclic = !single_round && bt.all_equal[b] != 0;
-        const int64_t t0 = (int64_t)(g - bt.tile0[b]) * RT_TILE;
+        const bool cyclic = !single_round && cur.all_equal != 0;
+        const int64_t t0 = (int64_t)(g - cur.tile0) * RT_TILE;
         const bool sorted = sel != SEL_RAW;
         const bool tie = part != nullptr && bt.need_tie[b] != 0;
         const bool need_key = sorted && (VERIFY || (single_round && out_total != nullptr));
         constexpr int FB = 8;                       // elements per thread and batch: all loads of a batch before its stores
         const unsigned lane = lane_id();
+        // cyclic topics: position e goes to member e mod C. One 64-bit modulo per thread and tile; the elements of a
+        // thread are 256 apart, so the rest is additions (a 64-bit modulo per element made this kernel compute-bound:
+        // BASELINE config 5, 76 M elements, 0.26 ms)
+        const uint32_t cstep = cyclic ? (uint32_t)(256 % C) : 0u;
+        uint32_t cmod = cyclic ? (uint32_t)((t0 + (int64_t)threadIdx.x) % C) : 0u;
         for (int i0 = 0; i0 < RT_TILE; i0 += FB * 256) {
             if (t0 + i0 >= P) break;                // uniform over the CTA
             // ONE round trip to memory per batch: everything that does not depend on loaded data is requested up front
@@ -803,7 +810,11 @@ k_big_finalize(BigTopics bt, const int64_t* __restrict__ lag, const int32_t* __r
                         if (VERIFY && lane == 31 && e + 1 < P) { k1x[q] = fkey[e + 1]; p1x[q] = fpay[e + 1]; }
                     }
                     if (single_round) cons[q] = cset_rank[coff + e];
-                    else if (cyclic) cons[q] = cset_rank[coff + e % C];
+                    else if (cyclic) cons[q] = cset_rank[coff + cmod];
+                }
+                if (cyclic) {                       // (for every q, also past the end: keeps cmod = (t0 + i0 + q*256 + tid) mod C)
+                    cmod += cstep;
+                    if ((int64_t)cmod >= C) cmod -= (uint32_t)C;
                 }
             }
 #pragma unroll

@@ -154,4 +154,8 @@ void launch_group_finalize(const BigTopics& bt, const int64_t* glag, int64_t n_m
                            int32_t* grp_part, int64_t* member_start, int64_t* member_off, int64_t n_assigned, int sms,
                            cudaStream_t st);
 
+// narrow copy of a result range (exchange.cu): entries of pw / cw bytes; cw == 0: consumers are not copied
+bool launch_narrow_results(cudaStream_t st, int64_t n, const int32_t* part, const int32_t* cons, int pw, int cw,
+                           uint8_t* dpart, uint8_t* dcons);
+
 }  // namespace lagassign

@@ -165,26 +165,32 @@ class ShardedAssignor:
         if gather:
             self.gather()
 
-    def gather(self):
-        """Narrow, all-gather, widen (no-op on one rank)."""
+    def gather(self, events=None):
+        """Narrow, all-gather, widen (no-op on one rank). `events`: four torch.cuda.Event recorded before the narrowing,
+        before and after the collective and after the widening (bench.py's breakdown of the exchange)."""
         import ctypes
         import torch
         import torch.distributed as dist
         if self.world == 1:
             return
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        cur = torch.cuda.current_stream()
+        st = ctypes.c_void_p(cur.cuda_stream)
+        if events: events[0].record(cur)
         vp = ctypes.c_void_p
         my = self.slots[self.rank * self.slot_bytes:(self.rank + 1) * self.slot_bytes]
         rc = self.L.lagassign_exchange_pack(st, self.counts[self.rank], vp(self.loc_part.data_ptr()), vp(self.loc_cons.data_ptr()),
                                             self.pw, self.cw, vp(my.data_ptr()))
         assert rc == 0, rc
+        if events: events[1].record(cur)
         dist.all_gather_into_tensor(self.slots[:self.world * self.slot_bytes], my, group=self.group)
+        if events: events[2].record(cur)
         rc = self.L.lagassign_exchange_unpack(st, self.n_topics, vp(self.d_topic_off.data_ptr()), vp(self.d_topic_cset.data_ptr()),
                                               vp(self.d_cset_off.data_ptr()), vp(self.d_cset_rank.data_ptr()),
                                               vp(self.d_first.data_ptr()), self.world, vp(self.slots.data_ptr()),
                                               self.slot_bytes, self.pw, self.cw,
                                               vp(self.full_part.data_ptr()), vp(self.full_cons.data_ptr()))
         assert rc == 0, rc
+        if events: events[3].record(cur)
 
     def results(self):
         """(out_partition, out_consumer_rank) of the whole batch as contiguous 1-D tensors."""

@@ -7,5 +7,5 @@ timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 
 python - <<PY
 import json
 d=json.load(open("gpurun_out/scale_n$N.json"))
-print("N=$N value=%.4e ms/step=%.4f compute=%.4f gather=%.4f e2e=%.3e parity=%s"%(d["value"],d["ms_per_step"],d["compute_ms_per_step"],d["gather_ms_per_step"],d["e2e"]["value"],d["parity_spot_check"]))
+print("N=$N value=%.4e ms/step=%.4f compute=%.4f gather=%.4f e2e=%.3e parity=%s exchange=%s"%(d["value"],d["ms_per_step"],d["compute_ms_per_step"],d["gather_ms_per_step"],d["e2e"]["value"],d["parity_spot_check"],d.get("exchange_ms")))
 PY

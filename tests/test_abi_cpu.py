@@ -36,7 +36,7 @@ def test_cuda_library_exports_every_declared_symbol(pkg):
     lib = ctypes.CDLL(pkg.library_path())
     for name in _declared("lagassign.h"):
         assert hasattr(lib, name), name
-    assert lib.lagassign_abi_version() == 2
+    assert lib.lagassign_abi_version() == 3
 
 
 def test_host_library_exports_every_declared_symbol(pkg):

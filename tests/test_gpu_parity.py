@@ -483,6 +483,55 @@ def test_multi_device_context_config4_slice(pkg):
     assert np.array_equal(got["out_consumer_rank"], exp["out_consumer_rank"])
 
 
+def _check_narrow(got, b, exp):
+    """The narrow form carries the same information as the int32 arrays (include/lagassign.h)."""
+    off = np.asarray(b["topic_off"])
+    assert np.array_equal(got["out_partition"].astype(np.int64), exp["out_partition"].astype(np.int64))
+    if got["cons_width"] == 0:
+        # every topic has P <= C or no subscriber: sorted partition k -> k-th member of the topic's set
+        cs = np.asarray(b["topic_cset"]); coff = np.asarray(b["cset_off"]); cr = np.asarray(b["cset_rank"])
+        for t in range(len(off) - 1):
+            lo, hi = int(off[t]), int(off[t + 1])
+            C = int(coff[cs[t] + 1] - coff[cs[t]])
+            want = cr[coff[cs[t]]:coff[cs[t]] + hi - lo] if C else np.full(hi - lo, -1, np.int32)
+            assert np.array_equal(exp["out_consumer_rank"][lo:hi], want), t
+    else:
+        c = got["out_consumer_rank"].astype(np.int64)
+        c[c == (1 << (8 * got["cons_width"])) - 1] = -1
+        assert np.array_equal(c, exp["out_consumer_rank"].astype(np.int64))
+
+
+@pytest.mark.parametrize("case", ["config4", "multi_round_small", "wide_ids", "explicit_ids", "big_topics", "empty_sets"])
+@pytest.mark.parametrize("n_dev", [1, 3])
+def test_assign_batch_narrow(pkg, case, n_dev):
+    """lagassign_assign_batch_narrow: 1 / 2 / 4-byte partition ids, 0 / 2-byte consumers, pipelined and plain paths,
+    one device and a multi-device context."""
+    rng = np.random.default_rng(99)
+    if case == "config4":
+        b, _ = baseline_config(4, scale=0.12); want = (1, 0)                    # pipelined path (3 M partitions)
+    elif case == "multi_round_small":
+        b = random_flat(rng, T=400, pmin=0, pmax=256, C=7, lag_kind="u40", n_sets=3); want = (1, 2)
+    elif case == "wide_ids":
+        b = random_flat(rng, T=60, pmin=0, pmax=3000, C=5000, lag_kind="small", n_sets=2, full_sets=True); want = (2, 0)
+    elif case == "explicit_ids":
+        b = random_flat(rng, T=50, pmin=0, pmax=700, C=20, lag_kind="dups", explicit_ids="shuffled", n_sets=2); want = (4, 2)
+    elif case == "big_topics":
+        b = random_flat(rng, T=3, pmin=66000, pmax=80000, C=300, lag_kind="full", n_sets=1, full_sets=True); want = (4, 2)
+    else:
+        b = random_flat(rng, T=30, pmin=1, pmax=200, C=300, lag_kind="small", n_sets=3, full_sets=True)
+        b["cset_off"] = np.concatenate([b["cset_off"], b["cset_off"][-1:]])      # one more, empty, set ...
+        b["topic_cset"] = b["topic_cset"].copy(); b["topic_cset"][::5] = len(b["cset_off"]) - 2   # ... for every fifth topic
+        want = (1, 0)
+    dev = 0 if n_dev == 1 else _multi_devices(pkg, n_dev)
+    with pkg.FlatAssignor(dev) as f:
+        got = f.assign_batch_narrow(*args_of(b))
+        got2 = f.assign_batch_narrow(*args_of(b))          # plan-cache hit: same widths, same result
+    assert (got["part_width"], got["cons_width"]) == want == (got2["part_width"], got2["cons_width"])
+    exp = oracle.assign_batch(*args_of(b), threads=_all_threads())
+    _check_narrow(got, b, exp)
+    _check_narrow(got2, b, exp)
+
+
 def test_multi_device_context_rejects_device_only_calls(pkg):
     with pkg.FlatAssignor(_multi_devices(pkg, 2)) as f:
         with pytest.raises(pkg.LagAssignError) as e:
