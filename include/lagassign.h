@@ -241,6 +241,30 @@ int  lagassign_exchange_unpack(void *cuda_stream, int64_t n_topics, const int64_
                                int64_t slot_bytes, int part_width, int cons_width,
                                int32_t *d_out_partition, int32_t *d_out_consumer_rank);
 
+/* consumersPerTopic (Main:410-426, called at Main:176) and the de-duplication of consumer sets, on the device
+ * (SURVEY 8f row 3): from the subscriptions as integers — members in rank order (String.compareTo), every entry the
+ * index of a subscribed topic in the caller's topic order — to the consumer-set part of lagassign_batch:
+ *   topic_cset [T]          set of every topic
+ *   cset_off   [n_csets+1]  (capacity T + 1)
+ *   cset_rank  [...]        members of each set, ascending rank (capacity: number of subscription entries)
+ * Sets are numbered in order of first appearance over the topics; a member that lists a topic twice counts once (as
+ * in the reference, whose per-topic maps are keyed by member id, Main:216-225); a topic nobody lists gets the empty set.
+ * Stateless: allocates and frees its own device memory on `device`. Host pointers in and out. */
+typedef struct lagassign_subscriptions {
+    int64_t        n_members;   /* M */
+    int64_t        n_topics;    /* T */
+    const int64_t *sub_off;     /* [M+1] entries of member (rank) m are [sub_off[m], sub_off[m+1]) */
+    const int32_t *sub_topic;   /* [sub_off[M]] topic indices in [0, T) */
+} lagassign_subscriptions;
+typedef struct lagassign_consumer_sets {
+    int64_t  n_csets;           /* out */
+    int32_t *topic_cset;        /* [T] */
+    int64_t *cset_off;          /* capacity T + 1 */
+    int32_t *cset_rank;         /* capacity sub_off[M] */
+} lagassign_consumer_sets;
+int  lagassign_invert_subscriptions(int device, const lagassign_subscriptions *in, lagassign_consumer_sets *out);
+const char *lagassign_subscriptions_last_error(void);
+
 /* Device copy of the computed lags (valid after execute(); for tests of the
  * fused lag computation). */
 int  lagassign_download_lags(lagassign_ctx *ctx, int64_t *lag_out);

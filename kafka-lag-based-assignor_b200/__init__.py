@@ -55,6 +55,16 @@ class _ResultNarrow(ctypes.Structure):
                 ("part_width", ctypes.c_int32), ("cons_width", ctypes.c_int32)]
 
 
+class _Subscriptions(ctypes.Structure):
+    _fields_ = [("n_members", ctypes.c_int64), ("n_topics", ctypes.c_int64), ("sub_off", ctypes.c_void_p),
+                ("sub_topic", ctypes.c_void_p)]
+
+
+class _ConsumerSets(ctypes.Structure):
+    _fields_ = [("n_csets", ctypes.c_int64), ("topic_cset", ctypes.c_void_p), ("cset_off", ctypes.c_void_p),
+                ("cset_rank", ctypes.c_void_p)]
+
+
 class _Offsets(ctypes.Structure):
     _fields_ = [("begin_offset", ctypes.c_void_p), ("end_offset", ctypes.c_void_p),
                 ("committed", ctypes.c_void_p), ("has_committed", ctypes.c_void_p),
@@ -123,6 +133,8 @@ def load_library() -> ctypes.CDLL:
     L.lagassign_exchange_slot_bytes.restype = i64
     L.lagassign_exchange_pack.argtypes = [vp, i64, vp, vp, i32, i32, vp]
     L.lagassign_exchange_unpack.argtypes = [vp, i64, vp, vp, vp, vp, vp, i32, vp, i64, i32, i32, vp, vp]
+    L.lagassign_invert_subscriptions.argtypes = [i32, ctypes.POINTER(_Subscriptions), ctypes.POINTER(_ConsumerSets)]
+    L.lagassign_subscriptions_last_error.restype = ctypes.c_char_p
     L.lagassign_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
     L.lagassign_host_free.argtypes = [vp]
     for name in ("lagassign_device_count", "lagassign_create", "lagassign_create_on_stream", "lagassign_create_multi",
@@ -132,7 +144,7 @@ def load_library() -> ctypes.CDLL:
                  "lagassign_bind_device_outputs", "lagassign_download_lags", "lagassign_get_stats",
                  "lagassign_profile_count", "lagassign_profile_entry",
                  "lagassign_group_sizes", "lagassign_download_grouping",
-                 "lagassign_exchange_pack", "lagassign_exchange_unpack",
+                 "lagassign_exchange_pack", "lagassign_exchange_unpack", "lagassign_invert_subscriptions",
                  "lagassign_host_alloc", "lagassign_host_free"):
         getattr(L, name).restype = i32
     _lib = L
@@ -174,6 +186,27 @@ def pinned_empty(n: int, dtype) -> np.ndarray:
     return np.frombuffer(buf, dtype=dtype, count=n)
 
 
+
+
+def invert_subscriptions(n_topics: int, sub_off, sub_topic, device: int = 0) -> dict:
+    """lagassign_invert_subscriptions(): consumersPerTopic (Main:410-426) + consumer-set de-duplication on the device.
+    sub_off[M+1] / sub_topic: the topic indices every member (in rank order) subscribes to. Returns the consumer-set
+    part of the flat batch: dict(topic_cset, cset_off, cset_rank)."""
+    L = load_library()
+    sub_off = _arr(sub_off, np.int64, "sub_off")
+    sub_topic = _arr(sub_topic, np.int32, "sub_topic")
+    M = len(sub_off) - 1
+    R = int(sub_off[-1]) if M >= 0 and len(sub_off) else 0
+    tc = np.empty(max(n_topics, 1), np.int32)
+    co = np.empty(n_topics + 1, np.int64)
+    cr = np.empty(max(R, 1), np.int32)
+    s_in = _Subscriptions(max(M, 0), n_topics, _ptr(sub_off), _ptr(sub_topic))
+    s_out = _ConsumerSets(0, _ptr(tc), _ptr(co), _ptr(cr))
+    rc = L.lagassign_invert_subscriptions(device, ctypes.byref(s_in), ctypes.byref(s_out))
+    if rc != 0:
+        raise LagAssignError(rc, L.lagassign_subscriptions_last_error().decode())
+    S = int(s_out.n_csets)
+    return dict(topic_cset=tc[:n_topics].copy(), cset_off=co[:S + 1].copy(), cset_rank=cr[:int(co[S]) if n_topics else 0].copy())
 
 
 class FlatAssignor:

@@ -68,6 +68,18 @@ k_exchange_unpack(UnpackArgs a) {
         const PT* sp = reinterpret_cast<const PT*>(slot) + (off - start);
         const int s = a.topic_cset[t];
         const int64_t coff = a.cset_off[s], C = a.cset_off[s + 1] - coff;
+        if constexpr (PW == 1 && CW == 0) {
+            // the common shape (ids below 256, P <= C, partition counts that are multiples of 4): four entries per
+            // lane and step, 4-byte loads of the ids, 16-byte loads of the members and 16-byte stores
+            if (((P | off | (off - start) | coff) & 3) == 0 && C > 0) {
+                for (int64_t k = (int64_t)lane * 4; k < P; k += 128) {
+                    const uchar4 v = *reinterpret_cast<const uchar4*>(sp + k);
+                    *reinterpret_cast<int4*>(a.out_part + off + k) = make_int4(v.x, v.y, v.z, v.w);
+                    *reinterpret_cast<int4*>(a.out_cons + off + k) = *reinterpret_cast<const int4*>(a.cset_rank + coff + k);
+                }
+                continue;
+            }
+        }
         if constexpr (CW == 0) {
             // every topic of the batch has P <= C (or no subscriber): consumers from the table
             for (int64_t k = lane; k < P; k += 32) {

@@ -783,85 +783,247 @@ k_big_finalize(BigTopics bt, const int64_t* __restrict__ lag, const int32_t* __r
         const bool sorted = sel != SEL_RAW;
         const bool tie = part != nullptr && bt.need_tie[b] != 0;
         const bool need_key = sorted && (VERIFY || (single_round && out_total != nullptr));
-        constexpr int FB = 8;                       // elements per thread and batch: all loads of a batch before its stores
+        const int n_valid = (int)min((int64_t)RT_TILE, P - t0);
         const unsigned lane = lane_id();
-        // cyclic topics: position e goes to member e mod C. One 64-bit modulo per thread and tile; the elements of a
-        // thread are 256 apart, so the rest is additions (a 64-bit modulo per element made this kernel compute-bound:
-        // BASELINE config 5, 76 M elements, 0.26 ms)
-        const uint32_t cstep = cyclic ? (uint32_t)(256 % C) : 0u;
-        uint32_t cmod = cyclic ? (uint32_t)((t0 + (int64_t)threadIdx.x) % C) : 0u;
-        for (int i0 = 0; i0 < RT_TILE; i0 += FB * 256) {
-            if (t0 + i0 >= P) break;                // uniform over the CTA
-            // ONE round trip to memory per batch: everything that does not depend on loaded data is requested up front
-            // (own element, the consumer of the slot, and — lane 31 only — the successor element for the certificate)
-            uint32_t pay[FB], p1x[FB];
-            uint64_t key[FB], k1x[FB];
-            int32_t pid[FB], cons[FB];
-#pragma unroll
-            for (int q = 0; q < FB; ++q) {
-                const int64_t e = t0 + i0 + q * 256 + (int)threadIdx.x;
-                pay[q] = (uint32_t)e; p1x[q] = (uint32_t)(e + 1);
-                key[q] = 0; k1x[q] = 0;
-                cons[q] = 0;
-                if (e < P) {
-                    if (sorted) {
-                        pay[q] = fpay[e];
-                        if (need_key) key[q] = fkey[e];
-                        if (VERIFY && lane == 31 && e + 1 < P) { k1x[q] = fkey[e + 1]; p1x[q] = fpay[e + 1]; }
+        // Topics that needed no pass (idle topics: every lag equal; BASELINE config 5) only GENERATE their result:
+        // position -> itself, member -> position mod C. Kept apart from the general code below, whose 64-bit index
+        // arithmetic and per-element case distinctions cost 64 instructions per element there (ncu) — more than the
+        // 8 bytes per element this path has to write.
+        if (!sorted && part == nullptr && out_total == nullptr && (single_round || cyclic)) {
+            int32_t* __restrict__ op = out_part + off + t0;
+            int32_t* __restrict__ oc = out_cons + off + t0;
+            const int32_t* __restrict__ cs = cset_rank + coff;
+            const uint32_t e0 = (uint32_t)t0;                                   // positions are below 2^31 (RT_MAX_P)
+            const uint32_t wrap = cyclic ? (uint32_t)C : 0xFFFFFFFFu;           // single round: member index = position
+            const uint32_t step = cyclic ? (uint32_t)(256 % C) : 256u;
+            uint32_t m = cyclic ? (uint32_t)((t0 + (int64_t)threadIdx.x) % C) : e0 + threadIdx.x;
+#pragma unroll 4
+            for (int i = (int)threadIdx.x; i < n_valid; i += 256) {
+                op[i] = (int32_t)(e0 + (uint32_t)i);
+                oc[i] = cs[m];
+                m += step;
+                if (m >= wrap) m -= wrap;
+            }
+            continue;
+        }
+        // Two mappings of a tile onto the CTA, chosen by the alignment of the caller's slice (uniform over the CTA):
+        // 16-byte aligned -> four consecutive elements per thread, 16-byte loads and stores; otherwise -> elements 256
+        // apart, coalesced 4-byte accesses (16-byte stores at an odd offset would split every sector four ways).
+        const bool vec_out = ((reinterpret_cast<uintptr_t>(out_part + off + t0) | reinterpret_cast<uintptr_t>(out_cons + off + t0)) & 15u) == 0;
+        if (vec_out) {
+            // A thread owns groups of FOUR consecutive elements (group gq = q*256 + tid, q = 0..3): 16-byte loads of the
+            // sorted payloads / keys and 16-byte stores of the two result arrays when the caller's slice is 16-byte aligned
+            // (topic offset a multiple of 4). ONE round trip to memory per tile: everything that does not depend on loaded
+            // data is requested up front (own elements, the consumers of the slots, and — lane 31 only — the first element
+            // of the next group for the certificate).
+            constexpr int GQ = RT_TILE / (4 * 256);
+            static_assert(GQ * 4 * 256 == RT_TILE, "a tile is 256 threads x GQ groups x 4 elements");
+            // cyclic topics: position e goes to member e mod C; one modulo per thread and tile, then additions
+            const uint32_t cstep = cyclic ? (uint32_t)(1024 % C) : 0u;
+            uint32_t cmod = cyclic ? (uint32_t)((t0 + 4 * (int64_t)threadIdx.x) % C) : 0u;
+            uint32_t pay[GQ][4], p1x[GQ];
+            uint64_t key[GQ][4], k1x[GQ];
+            int32_t pid[GQ][4], cons[GQ][4];
+    #pragma unroll
+            for (int q = 0; q < GQ; ++q) {
+                const int i = 4 * (q * 256 + (int)threadIdx.x);            // first element of the group inside the tile
+                const int64_t e = t0 + i;
+    #pragma unroll
+                for (int x = 0; x < 4; ++x) { pay[q][x] = (uint32_t)(e + x); key[q][x] = 0; cons[q][x] = 0; }
+                p1x[q] = (uint32_t)(e + 4); k1x[q] = 0;
+                if (i < n_valid) {
+                    if (sorted) {                                          // (the sort buffers are padded to 16 elements per topic)
+                        const uint4 pv = *reinterpret_cast<const uint4*>(fpay + e);
+                        pay[q][0] = pv.x; pay[q][1] = pv.y; pay[q][2] = pv.z; pay[q][3] = pv.w;
+                        if (need_key) {
+                            const ulonglong2 ka = *reinterpret_cast<const ulonglong2*>(fkey + e), kb = *reinterpret_cast<const ulonglong2*>(fkey + e + 2);
+                            key[q][0] = ka.x; key[q][1] = ka.y; key[q][2] = kb.x; key[q][3] = kb.y;
+                        }
+                        if (VERIFY && lane == 31 && i + 4 < n_valid) { k1x[q] = fkey[e + 4]; p1x[q] = fpay[e + 4]; }
                     }
-                    if (single_round) cons[q] = cset_rank[coff + e];
-                    else if (cyclic) cons[q] = cset_rank[coff + cmod];
+                    if (single_round) {
+    #pragma unroll
+                        for (int x = 0; x < 4; ++x) if (i + x < n_valid) cons[q][x] = cset_rank[coff + e + x];
+                    } else if (cyclic) {
+                        uint32_t m = cmod;
+    #pragma unroll
+                        for (int x = 0; x < 4; ++x) {
+                            cons[q][x] = cset_rank[coff + m];
+                            m = (m + 1 == (uint32_t)C) ? 0u : m + 1;
+                        }
+                    }
                 }
-                if (cyclic) {                       // (for every q, also past the end: keeps cmod = (t0 + i0 + q*256 + tid) mod C)
+                if (cyclic) {                       // (for every q: keeps cmod = (t0 + 4 * (q*256 + tid)) mod C)
                     cmod += cstep;
                     if ((int64_t)cmod >= C) cmod -= (uint32_t)C;
                 }
             }
-#pragma unroll
-            for (int q = 0; q < FB; ++q) {
-                const int64_t e = t0 + i0 + q * 256 + (int)threadIdx.x;
-                pid[q] = (int32_t)pay[q];
-                if (e < P && part != nullptr) pid[q] = part[off + pay[q]];
+    #pragma unroll
+            for (int q = 0; q < GQ; ++q) {
+                const int i = 4 * (q * 256 + (int)threadIdx.x);
+    #pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    pid[q][x] = (int32_t)pay[q][x];
+                    if (part != nullptr && i + x < n_valid) pid[q][x] = part[off + pay[q][x]];
+                }
             }
             if (VERIFY && sorted) {
-                // strictly increasing in (key, id when the ids had to be ordered, position): the successor of an
-                // element is the next lane's
-#pragma unroll
-                for (int q = 0; q < FB; ++q) {
-                    const int64_t e = t0 + i0 + q * 256 + (int)threadIdx.x;
-                    uint64_t k1 = __shfl_down_sync(0xffffffffu, key[q], 1);
-                    uint32_t p1 = __shfl_down_sync(0xffffffffu, pay[q], 1);
-                    int32_t i1 = __shfl_down_sync(0xffffffffu, pid[q], 1);
+                // strictly increasing in (key, id when the ids had to be ordered, position); the successor of a group's
+                // last element is the next lane's first (lane 31 fetched it; the first group of the next tile is checked
+                // by that tile's predecessor check below)
+    #pragma unroll
+                for (int q = 0; q < GQ; ++q) {
+                    const int i = 4 * (q * 256 + (int)threadIdx.x);
+                    uint64_t k1 = __shfl_down_sync(0xffffffffu, key[q][0], 1);
+                    uint32_t p1 = __shfl_down_sync(0xffffffffu, pay[q][0], 1);
+                    int32_t i1 = __shfl_down_sync(0xffffffffu, pid[q][0], 1);
                     if (lane == 31) {
                         k1 = k1x[q];
                         p1 = p1x[q];
-                        i1 = (part != nullptr && e + 1 < P) ? part[off + p1] : (int32_t)p1;
+                        i1 = (part != nullptr && i + 4 < n_valid) ? part[off + p1] : (int32_t)p1;
                     }
-                    if (e + 1 < P) {
-                        bool ok = key[q] < k1;
-                        if (key[q] == k1) ok = tie ? (pid[q] < i1 || (pid[q] == i1 && pay[q] < p1)) : (pay[q] < p1);
-                        bad |= !ok;
+    #pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const uint64_t kn = x < 3 ? key[q][x + 1] : k1;
+                        const uint32_t pn = x < 3 ? pay[q][x + 1] : p1;
+                        const int32_t in = x < 3 ? pid[q][x + 1] : i1;
+                        if (i + x + 1 < n_valid) {
+                            bool ok = key[q][x] < kn;
+                            if (key[q][x] == kn) ok = tie ? (pid[q][x] < in || (pid[q][x] == in && pay[q][x] < pn)) : (pay[q][x] < pn);
+                            bad |= !ok;
+                        }
+                    }
+                }
+                // the pair that straddles two tiles of a topic: this tile's first element against its predecessor
+                if (threadIdx.x == 0 && t0 > 0) {
+                    const uint64_t kp = fkey[t0 - 1];
+                    const uint32_t pp = fpay[t0 - 1];
+                    bool ok = kp < key[0][0];
+                    if (kp == key[0][0]) {
+                        if (tie) {
+                            const int32_t ip = part[off + pp];
+                            ok = ip < pid[0][0] || (ip == pid[0][0] && pp < pay[0][0]);
+                        } else {
+                            ok = pp < pay[0][0];
+                        }
+                    }
+                    bad |= !ok;
+                }
+            }
+    #pragma unroll
+            for (int q = 0; q < GQ; ++q) {
+                const int i = 4 * (q * 256 + (int)threadIdx.x);
+                const int64_t e = t0 + i;
+                if (i >= n_valid) continue;
+                const bool has_cons = single_round || cyclic;
+                if (i + 4 <= n_valid) {
+                    *reinterpret_cast<int4*>(out_part + off + e) = make_int4(pid[q][0], pid[q][1], pid[q][2], pid[q][3]);
+                    if (has_cons) *reinterpret_cast<int4*>(out_cons + off + e) = make_int4(cons[q][0], cons[q][1], cons[q][2], cons[q][3]);
+                } else {
+    #pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        if (i + x < n_valid) {
+                            out_part[off + e + x] = pid[q][x];
+                            if (has_cons) out_cons[off + e + x] = cons[q][x];
+                        }
+                    }
+                }
+                if (out_total != nullptr) {
+    #pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const int64_t ex = e + x;
+                        if (i + x >= n_valid) continue;
+                        if (single_round) {
+                            out_total[tc_off[t] + ex] = sorted ? (int64_t)(key[q][x] ^ LAG_KEY_MASK) : lag[off + ex];
+                            out_count[tc_off[t] + ex] = 1;
+                        } else if (cyclic && ex < C) {
+                            const int64_t cnt = P / C + (ex < P % C ? 1 : 0);
+                            out_total[tc_off[t] + ex] = (int64_t)((uint64_t)cnt * (uint64_t)lag[off]);   // wraps like repeated addition
+                            out_count[tc_off[t] + ex] = (int32_t)cnt;
+                        }
                     }
                 }
             }
-#pragma unroll
-            for (int q = 0; q < FB; ++q) {
-                const int64_t e = t0 + i0 + q * 256 + (int)threadIdx.x;
-                if (e >= P) continue;
-                out_part[off + e] = pid[q];
-                if (single_round) {
-                    out_cons[off + e] = cons[q];
-                    if (out_total) {
-                        const int64_t lg = sorted ? (int64_t)(key[q] ^ LAG_KEY_MASK) : lag[off + e];
-                        out_total[tc_off[t] + e] = lg;
-                        out_count[tc_off[t] + e] = 1;
+        } else {
+            constexpr int FB = 8;                       // elements per thread and batch: all loads of a batch before its stores
+            // cyclic topics: position e goes to member e mod C. One 64-bit modulo per thread and tile; the elements of a
+            // thread are 256 apart, so the rest is additions (a 64-bit modulo per element made this kernel compute-bound:
+            // BASELINE config 5, 76 M elements, 0.26 ms)
+            const uint32_t cstep = cyclic ? (uint32_t)(256 % C) : 0u;
+            uint32_t cmod = cyclic ? (uint32_t)((t0 + (int64_t)threadIdx.x) % C) : 0u;
+            for (int i0 = 0; i0 < RT_TILE; i0 += FB * 256) {
+                if (t0 + i0 >= P) break;                // uniform over the CTA
+                // ONE round trip to memory per batch: everything that does not depend on loaded data is requested up front
+                // (own element, the consumer of the slot, and — lane 31 only — the successor element for the certificate)
+                uint32_t pay[FB], p1x[FB];
+                uint64_t key[FB], k1x[FB];
+                int32_t pid[FB], cons[FB];
+    #pragma unroll
+                for (int q = 0; q < FB; ++q) {
+                    const int64_t e = t0 + i0 + q * 256 + (int)threadIdx.x;
+                    pay[q] = (uint32_t)e; p1x[q] = (uint32_t)(e + 1);
+                    key[q] = 0; k1x[q] = 0;
+                    cons[q] = 0;
+                    if (e < P) {
+                        if (sorted) {
+                            pay[q] = fpay[e];
+                            if (need_key) key[q] = fkey[e];
+                            if (VERIFY && lane == 31 && e + 1 < P) { k1x[q] = fkey[e + 1]; p1x[q] = fpay[e + 1]; }
+                        }
+                        if (single_round) cons[q] = cset_rank[coff + e];
+                        else if (cyclic) cons[q] = cset_rank[coff + cmod];
                     }
-                } else if (cyclic) {
-                    out_cons[off + e] = cons[q];
-                    if (out_total && e < C) {
-                        const int64_t cnt = P / C + (e < P % C ? 1 : 0);
-                        out_total[tc_off[t] + e] = (int64_t)((uint64_t)cnt * (uint64_t)lag[off]);   // wraps like repeated addition
-                        out_count[tc_off[t] + e] = (int32_t)cnt;
+                    if (cyclic) {                       // (for every q, also past the end: keeps cmod = (t0 + i0 + q*256 + tid) mod C)
+                        cmod += cstep;
+                        if ((int64_t)cmod >= C) cmod -= (uint32_t)C;
+                    }
+                }
+    #pragma unroll
+                for (int q = 0; q < FB; ++q) {
+                    const int64_t e = t0 + i0 + q * 256 + (int)threadIdx.x;
+                    pid[q] = (int32_t)pay[q];
+                    if (e < P && part != nullptr) pid[q] = part[off + pay[q]];
+                }
+                if (VERIFY && sorted) {
+                    // strictly increasing in (key, id when the ids had to be ordered, position): the successor of an
+                    // element is the next lane's
+    #pragma unroll
+                    for (int q = 0; q < FB; ++q) {
+                        const int64_t e = t0 + i0 + q * 256 + (int)threadIdx.x;
+                        uint64_t k1 = __shfl_down_sync(0xffffffffu, key[q], 1);
+                        uint32_t p1 = __shfl_down_sync(0xffffffffu, pay[q], 1);
+                        int32_t i1 = __shfl_down_sync(0xffffffffu, pid[q], 1);
+                        if (lane == 31) {
+                            k1 = k1x[q];
+                            p1 = p1x[q];
+                            i1 = (part != nullptr && e + 1 < P) ? part[off + p1] : (int32_t)p1;
+                        }
+                        if (e + 1 < P) {
+                            bool ok = key[q] < k1;
+                            if (key[q] == k1) ok = tie ? (pid[q] < i1 || (pid[q] == i1 && pay[q] < p1)) : (pay[q] < p1);
+                            bad |= !ok;
+                        }
+                    }
+                }
+    #pragma unroll
+                for (int q = 0; q < FB; ++q) {
+                    const int64_t e = t0 + i0 + q * 256 + (int)threadIdx.x;
+                    if (e >= P) continue;
+                    out_part[off + e] = pid[q];
+                    if (single_round) {
+                        out_cons[off + e] = cons[q];
+                        if (out_total) {
+                            const int64_t lg = sorted ? (int64_t)(key[q] ^ LAG_KEY_MASK) : lag[off + e];
+                            out_total[tc_off[t] + e] = lg;
+                            out_count[tc_off[t] + e] = 1;
+                        }
+                    } else if (cyclic) {
+                        out_cons[off + e] = cons[q];
+                        if (out_total && e < C) {
+                            const int64_t cnt = P / C + (e < P % C ? 1 : 0);
+                            out_total[tc_off[t] + e] = (int64_t)((uint64_t)cnt * (uint64_t)lag[off]);   // wraps like repeated addition
+                            out_count[tc_off[t] + e] = (int32_t)cnt;
+                        }
                     }
                 }
             }

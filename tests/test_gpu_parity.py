@@ -767,3 +767,84 @@ def test_grouping_reference_vector(pkg):
         g = f.download_grouping()
     assert g["member_off"].tolist() == [0, 4, 6]
     assert list(zip(g["topic"].tolist(), g["partition"].tolist())) == [(0, 0), (0, 2), (1, 0), (1, 1), (0, 1), (0, 3)]
+
+
+# ---- consumersPerTopic + consumer-set de-duplication on the device --------------------------------
+
+def _invert_reference(n_topics, sub_off, sub_topic):
+    """Plain Python restatement of Main:410-426 on integers, then the de-duplication rule of include/lagassign.h:
+    per topic the ascending set of members, identical sets stored once, numbered by first appearance."""
+    per_topic = [set() for _ in range(n_topics)]
+    for m in range(len(sub_off) - 1):
+        for e in range(int(sub_off[m]), int(sub_off[m + 1])):
+            per_topic[int(sub_topic[e])].add(m)
+    ids, sets, topic_cset = {}, [], []
+    for t in range(n_topics):
+        key = tuple(sorted(per_topic[t]))
+        if key not in ids:
+            ids[key] = len(sets)
+            sets.append(key)
+        topic_cset.append(ids[key])
+    cset_off = np.concatenate([[0], np.cumsum([len(s) for s in sets])]).astype(np.int64)
+    cset_rank = np.array([m for s in sets for m in s], dtype=np.int32)
+    return np.array(topic_cset, np.int32), cset_off, cset_rank
+
+
+@pytest.mark.parametrize("case", ["few_sets", "all_distinct", "one_set", "empty_topics", "repeats", "wide"])
+def test_invert_subscriptions_on_device(pkg, case):
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(case.encode()))
+    if case == "few_sets":        # a handful of subscription patterns shared by many members' topics
+        M, T = 300, 5000
+        patterns = [np.sort(rng.choice(T, size=int(rng.integers(1, T)), replace=False)) for _ in range(4)]
+        subs = [patterns[int(rng.integers(0, 4))] for _ in range(M)]
+    elif case == "all_distinct":
+        M, T = 70, 900
+        subs = [np.sort(rng.choice(T, size=int(rng.integers(0, T)), replace=False)) for _ in range(M)]
+    elif case == "one_set":       # BASELINE config 4's shape: everybody subscribes to everything
+        M, T = 4096, 3000
+        subs = [np.arange(T)] * M
+    elif case == "empty_topics":
+        M, T = 40, 1000
+        subs = [np.sort(rng.choice(T // 2, size=int(rng.integers(0, 50)), replace=False)) for _ in range(M)]
+    elif case == "repeats":       # a topic listed twice by one member counts once; order inside a list is free
+        M, T = 33, 64
+        subs = [rng.integers(0, T, size=int(rng.integers(0, 200))) for _ in range(M)]
+    else:                         # more than one 32-member word per row, not a multiple of 32
+        M, T = 1000 + 7, 257
+        subs = [np.sort(rng.choice(T, size=int(rng.integers(0, T)), replace=False)) for _ in range(M)]
+    sub_off = np.concatenate([[0], np.cumsum([len(s) for s in subs])]).astype(np.int64)
+    sub_topic = np.concatenate(list(subs) + [np.zeros(0, np.int64)]).astype(np.int32)
+    got = pkg.invert_subscriptions(T, sub_off, sub_topic)
+    tc, co, cr = _invert_reference(T, sub_off, sub_topic)
+    assert np.array_equal(got["topic_cset"], tc)
+    assert np.array_equal(got["cset_off"], co)
+    assert np.array_equal(got["cset_rank"], cr)
+
+
+def test_invert_subscriptions_matches_host_flatten(pkg):
+    """The same consumer sets as LagBasedPartitionAssignor::flatten (host, strings) for a generated group."""
+    rng = np.random.default_rng(5)
+    members = [f"m{int(i)}" for i in rng.permutation(60)]
+    topics = [f"topic-{i}" for i in range(200)]
+    subs = {m: [topics[int(i)] for i in rng.permutation(200)[:int(rng.integers(1, 200))]] for m in members}
+    lags = {t: [(t, p, int(rng.integers(0, 1000))) for p in range(3)] for t in topics}
+    a = pkg.LagBasedPartitionAssignor()
+    flat, topic_order, by_rank = a.flatten(lags, subs)
+    rank = {m: r for r, m in enumerate(by_rank)}
+    tindex = {t: i for i, t in enumerate(topic_order)}
+    lists = [[] for _ in by_rank]
+    for m, ts in subs.items():
+        lists[rank[m]] = [tindex[t] for t in ts if t in tindex]
+    sub_off = np.concatenate([[0], np.cumsum([len(x) for x in lists])]).astype(np.int64)
+    sub_topic = np.array([t for x in lists for t in x], np.int32)
+    got = pkg.invert_subscriptions(len(topic_order), sub_off, sub_topic)
+    assert np.array_equal(got["topic_cset"], flat["topic_cset"])
+    assert np.array_equal(got["cset_off"], flat["cset_off"])
+    assert np.array_equal(got["cset_rank"], flat["cset_rank"])
+
+
+def test_invert_subscriptions_argument_errors(pkg):
+    with pytest.raises(pkg.LagAssignError) as e:
+        pkg.invert_subscriptions(4, [0, 2], [1, 9])            # topic index out of range
+    assert e.value.code == -1
