@@ -265,9 +265,12 @@ def main():
     for a, m, b_ in ev:
         flush()
         a.record(stream)
-        f.execute()
-        m.record(stream)
-        sh.gather()
+        if world == 1:
+            f.execute()
+            m.record(stream)
+        else:
+            sh.execute()          # kernels, narrowing, all-gather and widening, chunk-pipelined (distributed.py)
+            m.record(stream)
         b_.record(stream)
         torch.cuda.synchronize()
         for k, (ms, n) in f.profile().items():
@@ -284,24 +287,25 @@ def main():
     for a, b_ in ev_u:
         flush()
         a.record(stream)
-        f.execute()
-        sh.gather()
+        sh.execute()
         b_.record(stream)
         torch.cuda.synchronize()
     t_unprofiled_ms = sum(a.elapsed_time(b_) for a, b_ in ev_u) / len(ev_u)
     exchange_ms = None
-    if world > 1:          # where the exchange's time goes (not the headline: separate steps with four more events each)
-        acc = [0.0, 0.0, 0.0]
+    if world > 1:          # where the exchange's time goes (not the headline: separate steps with extra events)
+        acc = {}
         for _ in range(5):
             flush()
-            f.execute()
-            e4 = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            sh.gather(events=e4)
+            evs = []
+            sh.execute(events=evs)
             torch.cuda.synchronize()
-            for j in range(3):
-                acc[j] += e4[j].elapsed_time(e4[j + 1]) / 5
-        exchange_ms = {"narrow": acc[0], "all_gather": acc[1], "widen": acc[2]}
-    t_compute_ms = sum(a.elapsed_time(m) for a, m, b_ in ev)
+            for name, e0, e1 in evs:
+                acc[name] = acc.get(name, 0.0) + e0.elapsed_time(e1) / 5
+        exchange_ms = dict(acc, chunks=sh.n_chunks,
+                           note="per step, summed over the chunks; all_gather_wait = time the compute stream waits for a "
+                                "chunk's collective after its own work is done (the rest of the collective is hidden behind "
+                                "the next chunk's kernels)")
+    t_compute_ms = sum(a.elapsed_time(m) for a, m, b_ in ev) if world == 1 else sum(v[0] for v in prof_acc.values())
     launches_per_step = f.stats()["kernel_launches"]
     stats = f.stats()
 
@@ -444,7 +448,10 @@ def main():
             alg = None
             alg_note = "latency-bound kernel (sequential round fill): no bandwidth roofline, see time share"
         per_launch_ms = dom_ms / max(dom_n, 1)
-        achieved = (alg / (per_launch_ms * 1e-3) / 1e9) if alg else None
+        # `alg` is what ONE launch of the radix kernels moves, but what ALL launches of a step move together for the
+        # on-chip kernels (N > 1 runs them chunk by chunk)
+        alg_ms = dom_ms / args.steps if dom_name in ("k_warp_topics", "k_cta_topics") else per_launch_ms
+        achieved = (alg / (alg_ms * 1e-3) / 1e9) if alg else None
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if world == 1 and os.path.exists(tp):     # measured at N = 1 (ncu is never run on a multi-rank command)

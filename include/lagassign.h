@@ -211,6 +211,11 @@ int  lagassign_upload(lagassign_ctx *ctx, const lagassign_batch *in);
 int  lagassign_upload_offsets(lagassign_ctx *ctx, const lagassign_batch *in,
                               const lagassign_offsets *offs);
 int  lagassign_execute(lagassign_ctx *ctx);
+/* execute() for the topics [t_lo, t_hi) of the uploaded batch only (asynchronous). For callers that overlap the
+ * result exchange of one topic range with the kernels of the next (distributed.py). Batches whose topics all have at
+ * most 4096 partitions, without totals / grouping; LAGASSIGN_ERR_UNSUPPORTED otherwise (use execute()). The per-kernel
+ * profile accumulates over the ranges of one pass (it restarts at t_lo == 0). */
+int  lagassign_execute_range(lagassign_ctx *ctx, int64_t t_lo, int64_t t_hi);
 int  lagassign_sync(lagassign_ctx *ctx);
 int  lagassign_download(lagassign_ctx *ctx, const lagassign_result *out);
 
@@ -235,6 +240,15 @@ int  lagassign_bind_device_outputs(lagassign_ctx *ctx, int32_t *d_out_partition,
 int64_t lagassign_exchange_slot_bytes(int64_t n, int part_width, int cons_width);
 int  lagassign_exchange_pack(void *cuda_stream, int64_t n, const int32_t *d_part, const int32_t *d_cons,
                              int part_width, int cons_width, void *d_slot);
+/* unpack for ARBITRARY topic ranges per rank (a chunk of every rank's shard): rank r's slot holds the results of the
+ * topics [d_range_lo[r], d_range_hi[r]); skip_rank (or -1) names a rank whose range is already in place in the output
+ * arrays (the caller's own, written there by its kernels). */
+int  lagassign_exchange_unpack_ranges(void *cuda_stream, const int64_t *d_topic_off, const int32_t *d_topic_cset,
+                                      const int64_t *d_cset_off, const int32_t *d_cset_rank,
+                                      const int64_t *d_range_lo, const int64_t *d_range_hi, int world, int skip_rank,
+                                      int64_t max_topics_per_rank, const void *d_slots, int64_t slot_bytes,
+                                      int part_width, int cons_width,
+                                      int32_t *d_out_partition, int32_t *d_out_consumer_rank);
 int  lagassign_exchange_unpack(void *cuda_stream, int64_t n_topics, const int64_t *d_topic_off,
                                const int32_t *d_topic_cset, const int64_t *d_cset_off, const int32_t *d_cset_rank,
                                const int64_t *d_shard_first_topic, int world, const void *d_slots,

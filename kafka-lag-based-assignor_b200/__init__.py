@@ -119,6 +119,8 @@ def load_library() -> ctypes.CDLL:
     L.lagassign_upload.argtypes = [vp, ctypes.POINTER(_Batch)]
     L.lagassign_upload_offsets.argtypes = [vp, ctypes.POINTER(_Batch), ctypes.POINTER(_Offsets)]
     L.lagassign_execute.argtypes = [vp]
+    L.lagassign_execute_range.argtypes = [vp, i64, i64]
+    L.lagassign_exchange_unpack_ranges.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, vp, i64, i32, i32, vp, vp]
     L.lagassign_sync.argtypes = [vp]
     L.lagassign_download.argtypes = [vp, ctypes.POINTER(_Result)]
     L.lagassign_bind_device_outputs.argtypes = [vp, vp, vp]
@@ -140,7 +142,8 @@ def load_library() -> ctypes.CDLL:
     for name in ("lagassign_device_count", "lagassign_create", "lagassign_create_on_stream", "lagassign_create_multi",
                  "lagassign_shard_count",
                  "lagassign_set_option", "lagassign_assign_batch", "lagassign_assign_batch_narrow", "lagassign_upload",
-                 "lagassign_upload_offsets", "lagassign_execute", "lagassign_sync", "lagassign_download",
+                 "lagassign_upload_offsets", "lagassign_execute", "lagassign_execute_range", "lagassign_sync", "lagassign_download",
+                 "lagassign_exchange_unpack_ranges",
                  "lagassign_bind_device_outputs", "lagassign_download_lags", "lagassign_get_stats",
                  "lagassign_profile_count", "lagassign_profile_entry",
                  "lagassign_group_sizes", "lagassign_download_grouping",
@@ -307,6 +310,10 @@ class FlatAssignor:
 
     def execute(self):
         self._check(self._L.lagassign_execute(self._ctx))
+
+    def execute_range(self, t_lo: int, t_hi: int):
+        """lagassign_execute_range(): the kernels of the topics [t_lo, t_hi) of the uploaded batch only."""
+        self._check(self._L.lagassign_execute_range(self._ctx, t_lo, t_hi))
 
     def sync(self):
         self._check(self._L.lagassign_sync(self._ctx))

@@ -37,13 +37,15 @@ k_exchange_pack(int64_t n, const int32_t* __restrict__ part, const int32_t* __re
 }
 
 struct UnpackArgs {
-    int64_t n_topics;
+    int64_t max_topics;          // largest range of a rank (grid dimension x covers it, y = rank)
     const int64_t* topic_off;    // [T+1] of the WHOLE batch
     const int32_t* topic_cset;   // [T]
     const int64_t* cset_off;     // [S+1]
     const int32_t* cset_rank;
-    const int64_t* shard_first_topic;   // [world+1] topic ranges of the ranks
+    const int64_t* range_lo;     // [world] rank r's slot holds the topics [range_lo[r], range_hi[r])
+    const int64_t* range_hi;     // [world]
     int world;
+    int skip_rank;               // this rank's range is already in place (-1: none)
     int64_t slot_bytes;          // distance between the ranks' slots in `src`
     const uint8_t* src;          // gathered slots
     int32_t* out_part;           // [N]
@@ -55,16 +57,16 @@ __global__ void __launch_bounds__(256)
 k_exchange_unpack(UnpackArgs a) {
     using PT = typename Narrow<PW>::type;
     const int lane = threadIdx.x & 31;
+    const int r = (int)blockIdx.y;                                           // rank whose slot this CTA row widens
+    if (r == a.skip_rank) return;
+    const int64_t t_first = a.range_lo[r], t_end = a.range_hi[r];
+    const int64_t start = a.topic_off[t_first];                              // first partition in that slot
+    const int64_t n_r = a.topic_off[t_end] - start;
+    const uint8_t* slot = a.src + (int64_t)r * a.slot_bytes;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t t = warp0; t < a.n_topics; t += n_warps) {
-        // rank that computed topic t (world <= 8..64: a linear scan of a register-resident table is enough)
-        int r = 0;
-        while (r + 1 < a.world && t >= a.shard_first_topic[r + 1]) ++r;
+    for (int64_t t = t_first + warp0; t < t_end; t += n_warps) {
         const int64_t off = a.topic_off[t], P = a.topic_off[t + 1] - off;
-        const int64_t start = a.topic_off[a.shard_first_topic[r]];                 // first partition of that rank
-        const int64_t n_r = a.topic_off[a.shard_first_topic[r + 1]] - start;
-        const uint8_t* slot = a.src + (int64_t)r * a.slot_bytes;
         const PT* sp = reinterpret_cast<const PT*>(slot) + (off - start);
         const int s = a.topic_cset[t];
         const int64_t coff = a.cset_off[s], C = a.cset_off[s + 1] - coff;
@@ -155,23 +157,36 @@ int lagassign_exchange_pack(void* cuda_stream, int64_t n, const int32_t* d_part,
     return cudaGetLastError() == cudaSuccess ? LAGASSIGN_OK : LAGASSIGN_ERR_CUDA;
 }
 
-int lagassign_exchange_unpack(void* cuda_stream, int64_t n_topics, const int64_t* d_topic_off, const int32_t* d_topic_cset,
-                              const int64_t* d_cset_off, const int32_t* d_cset_rank, const int64_t* d_shard_first_topic,
-                              int world, const void* d_slots, int64_t slot_bytes, int part_width, int cons_width,
-                              int32_t* d_out_partition, int32_t* d_out_consumer_rank) {
-    if (n_topics < 0 || world < 1 || !d_topic_off || !d_cset_off || !d_shard_first_topic || !d_slots ||
-        !d_out_partition || !d_out_consumer_rank || (n_topics > 0 && !d_topic_cset))
+int lagassign_exchange_unpack_ranges(void* cuda_stream, const int64_t* d_topic_off, const int32_t* d_topic_cset,
+                                     const int64_t* d_cset_off, const int32_t* d_cset_rank, const int64_t* d_range_lo,
+                                     const int64_t* d_range_hi, int world, int skip_rank, int64_t max_topics_per_rank,
+                                     const void* d_slots, int64_t slot_bytes, int part_width, int cons_width,
+                                     int32_t* d_out_partition, int32_t* d_out_consumer_rank) {
+    if (world < 1 || world > 65535 || !d_topic_off || !d_cset_off || !d_range_lo || !d_range_hi || !d_slots ||
+        !d_out_partition || !d_out_consumer_rank || (max_topics_per_rank > 0 && !d_topic_cset))
         return exch_fail("NULL argument");
-    if (n_topics == 0) return LAGASSIGN_OK;
+    if (max_topics_per_rank <= 0) return LAGASSIGN_OK;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
-    UnpackArgs a{n_topics, d_topic_off, d_topic_cset, d_cset_off, d_cset_rank, d_shard_first_topic, world, slot_bytes,
-                 static_cast<const uint8_t*>(d_slots), d_out_partition, d_out_consumer_rank};
-    const int grid = (int)std::min<int64_t>((n_topics + 7) / 8, 148 * 16);
+    UnpackArgs a{max_topics_per_rank, d_topic_off, d_topic_cset, d_cset_off, d_cset_rank, d_range_lo, d_range_hi, world, skip_rank,
+                 slot_bytes, static_cast<const uint8_t*>(d_slots), d_out_partition, d_out_consumer_rank};
+    const dim3 grid((unsigned)std::min<int64_t>((max_topics_per_rank + 7) / 8, std::max(1, 148 * 16 / world)), (unsigned)world);
 #define UNPACK_CASE(PW, CW) if (part_width == PW && cons_width == CW) { k_exchange_unpack<PW, CW><<<grid, 256, 0, st>>>(a); } else
     UNPACK_CASE(1, 0) UNPACK_CASE(2, 0) UNPACK_CASE(4, 0) UNPACK_CASE(1, 2) UNPACK_CASE(2, 2) UNPACK_CASE(4, 2)
     UNPACK_CASE(1, 4) UNPACK_CASE(2, 4) UNPACK_CASE(4, 4) { return exch_fail("unsupported widths"); }
 #undef UNPACK_CASE
     return cudaGetLastError() == cudaSuccess ? LAGASSIGN_OK : LAGASSIGN_ERR_CUDA;
+}
+
+// contiguous shards: rank r holds the topics [d_shard_first_topic[r], d_shard_first_topic[r + 1])
+int lagassign_exchange_unpack(void* cuda_stream, int64_t n_topics, const int64_t* d_topic_off, const int32_t* d_topic_cset,
+                              const int64_t* d_cset_off, const int32_t* d_cset_rank, const int64_t* d_shard_first_topic,
+                              int world, const void* d_slots, int64_t slot_bytes, int part_width, int cons_width,
+                              int32_t* d_out_partition, int32_t* d_out_consumer_rank) {
+    if (n_topics < 0 || !d_shard_first_topic) return exch_fail("NULL argument");
+    if (n_topics == 0) return LAGASSIGN_OK;
+    return lagassign_exchange_unpack_ranges(cuda_stream, d_topic_off, d_topic_cset, d_cset_off, d_cset_rank, d_shard_first_topic,
+                                            d_shard_first_topic + 1, world, -1, n_topics, d_slots, slot_bytes, part_width,
+                                            cons_width, d_out_partition, d_out_consumer_rank);
 }
 
 }  // extern "C"

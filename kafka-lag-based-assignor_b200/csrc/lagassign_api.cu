@@ -218,13 +218,13 @@ cudaEvent_t prof_event(lagassign_ctx* ctx) {
 struct ProfScope {   // records an event pair around one launch when profiling is on
     lagassign_ctx* ctx;
     ProfRec rec;
-    ProfScope(lagassign_ctx* c, int kind) : ctx(c) {
-        if (!ctx->profile) return;
+    ProfScope(lagassign_ctx* c, int kind) : ctx(c) {        // c == nullptr: never records
+        if (!ctx || !ctx->profile) return;
         rec.kind = kind; rec.a = prof_event(ctx); rec.b = prof_event(ctx);
         cudaEventRecord(rec.a, ctx->stream);
     }
     ~ProfScope() {
-        if (!ctx->profile) return;
+        if (!ctx || !ctx->profile) return;
         cudaEventRecord(rec.b, ctx->stream);
         ctx->prof.push_back(rec);
     }
@@ -585,6 +585,34 @@ int upload_data_now(lagassign_ctx* ctx, const lagassign_batch* in) {
     return LAGASSIGN_OK;
 }
 
+// Kernels of the on-chip topics with index in [t_lo, t_hi) (the per-bin topic lists are ascending, so a topic range is
+// a slice of each); returns the number of launches. Used by the copy/compute pipeline and by lagassign_execute_range.
+int launch_topic_range(lagassign_ctx* ctx, const DevBatch& b, int64_t t_lo, int64_t t_hi, bool profile) {
+    auto slice = [&](const std::vector<int32_t>& v, int& lo, int& hi) {
+        lo = (int)(std::lower_bound(v.begin(), v.end(), (int32_t)t_lo) - v.begin());
+        hi = (int)(std::lower_bound(v.begin(), v.end(), (int32_t)t_hi) - v.begin());
+    };
+    int lo, hi, launches = 0;
+    slice(ctx->h_list_none, lo, hi);
+    if (hi > lo) {
+        ProfScope ps(profile ? ctx : nullptr, K_UNASSIGNED);
+        launch_unassigned_topics(b, ctx->d_list_none.as<int32_t>() + lo, hi - lo, ctx->stream); ++launches;
+    }
+    slice(ctx->h_list_warp, lo, hi);
+    if (hi > lo) {
+        ProfScope ps(profile ? ctx : nullptr, K_WARP);
+        launch_warp_topics(b, ctx->d_list_warp.as<int32_t>() + lo, hi - lo, ctx->stream); ++launches;
+    }
+    for (int c2 = 0; c2 < N_CTA_CLASSES; ++c2) {
+        slice(ctx->h_list_cta[c2], lo, hi);
+        if (hi > lo) {
+            ProfScope ps(profile ? ctx : nullptr, K_CTA);
+            launch_cta_topics(b, ctx->d_list_cta[c2].as<int32_t>() + lo, hi - lo, c2, ctx->sm_count, ctx->stream); ++launches;
+        }
+    }
+    return launches;
+}
+
 constexpr int64_t PIPE_MIN_ELEMS = 1 << 21;      // below this one copy each way is as good
 constexpr int64_t PIPE_CHUNK_ELEMS = 3 << 20;    // ~24 MB of lags per chunk
 
@@ -659,19 +687,7 @@ int assign_batch_pipelined_impl(lagassign_ctx* ctx, const lagassign_batch* in, c
         CUDA_TRY(ctx, cudaEventRecord(ev_in, ctx->stream_in));
         if (ctx->trace) CUDA_TRY(ctx, cudaEventRecord(tev[1 + 3 * c], ctx->stream_in));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ev_in, 0));
-        auto slice = [&](const std::vector<int32_t>& v, int& lo, int& hi) {
-            lo = (int)(std::lower_bound(v.begin(), v.end(), (int32_t)t_lo) - v.begin());
-            hi = (int)(std::lower_bound(v.begin(), v.end(), (int32_t)t_hi) - v.begin());
-        };
-        int lo, hi;
-        slice(ctx->h_list_none, lo, hi);
-        if (hi > lo) { launch_unassigned_topics(b, ctx->d_list_none.as<int32_t>() + lo, hi - lo, ctx->stream); ++launches; }
-        slice(ctx->h_list_warp, lo, hi);
-        if (hi > lo) { launch_warp_topics(b, ctx->d_list_warp.as<int32_t>() + lo, hi - lo, ctx->stream); ++launches; }
-        for (int c2 = 0; c2 < N_CTA_CLASSES; ++c2) {
-            slice(ctx->h_list_cta[c2], lo, hi);
-            if (hi > lo) { launch_cta_topics(b, ctx->d_list_cta[c2].as<int32_t>() + lo, hi - lo, c2, ctx->sm_count, ctx->stream); ++launches; }
-        }
+        launches += launch_topic_range(ctx, b, t_lo, t_hi, /*profile=*/false);
         const uint8_t* d2h_part = reinterpret_cast<const uint8_t*>(src_part + e0);
         const uint8_t* d2h_cons = reinterpret_cast<const uint8_t*>(src_cons + e0);
         if (n && out.narrow) {
@@ -1065,6 +1081,27 @@ int lagassign_execute(lagassign_ctx* ctx) {
         }
     }
     ctx->executed = true;
+    return LAGASSIGN_OK;
+}
+
+int lagassign_execute_range(lagassign_ctx* ctx, int64_t t_lo, int64_t t_hi) {
+    if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
+    if (!ctx->shards.empty()) return fail(ctx, LAGASSIGN_ERR_UNSUPPORTED, "not available on a multi-device context");
+    if (!ctx->uploaded) return fail(ctx, LAGASSIGN_ERR_STATE, "execute_range() before a successful upload()");
+    if (t_lo < 0 || t_hi < t_lo || t_hi > ctx->T) return fail(ctx, LAGASSIGN_ERR_ARG, "topic range outside the batch");
+    if (ctx->n_big > 0 || ctx->want_group || ctx->want_totals)
+        return fail(ctx, LAGASSIGN_ERR_UNSUPPORTED, "execute_range covers batches of topics with at most 4096 partitions, without totals / grouping");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (t_lo == 0) {                       // a new pass over the batch: start a fresh per-kernel profile
+        ctx->prof.clear();
+        ctx->ev_used = 0;
+        ctx->prof_resolved = false;
+        ctx->stats.kernel_launches = 0;
+    }
+    DevBatch b = make_dev_batch(ctx);
+    ctx->stats.kernel_launches += launch_topic_range(ctx, b, t_lo, t_hi, ctx->profile);
+    CUDA_TRY(ctx, cudaGetLastError());
+    if (t_hi == ctx->T) ctx->executed = true;
     return LAGASSIGN_OK;
 }
 

@@ -114,17 +114,32 @@ def all_gather_results(local_part, local_cons, counts: Sequence[int], group=None
     return full_p, full_c
 
 
-class ShardedAssignor:
-    """One rank's view of a topic-sharded assign(): upload this rank's contiguous
-    shard, run the kernels, narrow the results into this rank's slot of the gather
-    buffer, all-gather the slots, widen them into the full int32 arrays.
-    torch (CUDA + NCCL) is plumbing only."""
+def chunk_ranges(bounds: Sequence[Tuple[int, int]], n_chunks: int) -> List[List[Tuple[int, int]]]:
+    """Every rank's contiguous topic range cut into n_chunks contiguous pieces: [[(lo, hi) per rank] per chunk]."""
+    return [[(lo + (hi - lo) * c // n_chunks, lo + (hi - lo) * (c + 1) // n_chunks) for lo, hi in bounds]
+            for c in range(n_chunks)]
 
-    def __init__(self, flat_assignor, rank: int, world_size: int, group=None):
+
+def pick_chunks(local_partitions: int, has_radix_topics: bool) -> int:
+    """Chunks of the exchange pipeline. A chunk's all-gather runs while the next chunk's kernels do, so chunks pay off
+    while a shard's kernels take longer than a collective's latency (~20 us): about 3 M partitions per chunk."""
+    if has_radix_topics:
+        return 1                      # the radix path is one chain of device-wide kernels: lagassign_execute()
+    return int(min(4, max(1, round(local_partitions / 3.2e6))))
+
+
+class ShardedAssignor:
+    """One rank's view of a topic-sharded assign(): upload this rank's contiguous shard; then, chunk by chunk of the
+    shard, run the kernels (they write this rank's int32 results straight into its place in the full arrays), narrow
+    the chunk into this rank's slot and start its all-gather, which proceeds on NCCL's stream while the next chunk's
+    kernels run; finally widen the other ranks' slots into the full arrays. torch (CUDA + NCCL) is plumbing only."""
+
+    def __init__(self, flat_assignor, rank: int, world_size: int, group=None, n_chunks: int = 0):
         self.f = flat_assignor
         self.rank, self.world, self.group = rank, world_size, group
         self.counts = None
         self.full_part = self.full_cons = None
+        self.force_chunks = n_chunks
 
     def upload(self, batch: dict):
         import torch
@@ -139,58 +154,89 @@ class ShardedAssignor:
         total = int(sum(self.counts))
         dev = torch.device("cuda", torch.cuda.current_device())
         self.start = int(sum(self.counts[:self.rank]))
-        n = self.counts[self.rank]
-        self.full_part = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-        self.full_cons = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        self.full_part = torch.empty(max(total, 1) + 4, dtype=torch.int32, device=dev)
+        self.full_cons = torch.empty(max(total, 1) + 4, dtype=torch.int32, device=dev)
+        # this rank's kernels write their results where they belong in the full arrays
+        self.f.bind_device_outputs(self.full_part.data_ptr() + 4 * self.start, self.full_cons.data_ptr() + 4 * self.start)
         if self.world == 1:
-            self.f.bind_device_outputs(self.full_part.data_ptr(), self.full_cons.data_ptr())
             return
-        self.n_topics = len(batch["topic_off"]) - 1
+        off = np.asarray(batch["topic_off"], dtype=np.int64)
+        self.n_topics = len(off) - 1
         self.pw, self.cw = exchange_format(batch)
-        self.slot_bytes = int(self.L.lagassign_exchange_slot_bytes(max(self.counts), self.pw, self.cw))
-        self.slots = torch.empty(self.world * max(self.slot_bytes, 16), dtype=torch.uint8, device=dev)
-        self.loc_part = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-        self.loc_cons = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-        self.f.bind_device_outputs(self.loc_part.data_ptr(), self.loc_cons.data_ptr())
-        # the whole batch's shape, for the widening kernel (small: 12 B per topic + the consumer sets)
+        has_radix = bool(self.f.stats()["topics_device"] > 0)
+        # the same chunking on every rank: decided from the largest shard
+        self.n_chunks = self.force_chunks or pick_chunks(max(self.counts), False)
+        if self.world > 1:
+            import torch.distributed as dist
+            flag = torch.tensor([1 if has_radix else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)      # any rank with radix-path topics: one chunk everywhere
+            if int(flag.item()):
+                self.n_chunks = 1
+        self.use_ranges = not bool(int(flag.item()))
         t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
-        self.d_topic_off = t(batch["topic_off"], np.int64)
+        self.chunks = []
+        for ranges in chunk_ranges(self.bounds, self.n_chunks):
+            n_rc = [int(off[h] - off[l]) for l, h in ranges]
+            sb = int(self.L.lagassign_exchange_slot_bytes(max(n_rc), self.pw, self.cw))
+            my_lo, my_hi = ranges[self.rank]
+            self.chunks.append(dict(
+                local=(my_lo - lo, my_hi - lo), e0=int(off[my_lo]), n=n_rc[self.rank], slot_bytes=sb,
+                slots=torch.empty(self.world * max(sb, 16), dtype=torch.uint8, device=dev),
+                d_lo=t([l for l, _ in ranges], np.int64), d_hi=t([h for _, h in ranges], np.int64),
+                max_topics=max(h - l for l, h in ranges)))
+        # the whole batch's shape, for the widening kernel (small: 12 B per topic + the consumer sets)
+        self.d_topic_off = t(off, np.int64)
         self.d_topic_cset = t(batch["topic_cset"], np.int32)
         self.d_cset_off = t(batch["cset_off"], np.int64)
         self.d_cset_rank = t(batch["cset_rank"], np.int32) if len(batch["cset_rank"]) else torch.zeros(1, dtype=torch.int32, device=dev)
-        self.d_first = t([lo_ for lo_, _ in self.bounds] + [self.n_topics], np.int64)
 
-    def execute(self, gather: bool = True):
-        self.f.execute()
-        if gather:
-            self.gather()
-
-    def gather(self, events=None):
-        """Narrow, all-gather, widen (no-op on one rank). `events`: four torch.cuda.Event recorded before the narrowing,
-        before and after the collective and after the widening (bench.py's breakdown of the exchange)."""
+    def execute(self, gather: bool = True, events=None):
+        """One step. `events` (bench.py): a list that receives (name, start event, end event) triples of the exchange legs."""
         import ctypes
         import torch
         import torch.distributed as dist
-        if self.world == 1:
+        if self.world == 1 or not gather:
+            self.f.execute()
             return
         cur = torch.cuda.current_stream()
         st = ctypes.c_void_p(cur.cuda_stream)
-        if events: events[0].record(cur)
         vp = ctypes.c_void_p
-        my = self.slots[self.rank * self.slot_bytes:(self.rank + 1) * self.slot_bytes]
-        rc = self.L.lagassign_exchange_pack(st, self.counts[self.rank], vp(self.loc_part.data_ptr()), vp(self.loc_cons.data_ptr()),
-                                            self.pw, self.cw, vp(my.data_ptr()))
-        assert rc == 0, rc
-        if events: events[1].record(cur)
-        dist.all_gather_into_tensor(self.slots[:self.world * self.slot_bytes], my, group=self.group)
-        if events: events[2].record(cur)
-        rc = self.L.lagassign_exchange_unpack(st, self.n_topics, vp(self.d_topic_off.data_ptr()), vp(self.d_topic_cset.data_ptr()),
-                                              vp(self.d_cset_off.data_ptr()), vp(self.d_cset_rank.data_ptr()),
-                                              vp(self.d_first.data_ptr()), self.world, vp(self.slots.data_ptr()),
-                                              self.slot_bytes, self.pw, self.cw,
-                                              vp(self.full_part.data_ptr()), vp(self.full_cons.data_ptr()))
-        assert rc == 0, rc
-        if events: events[3].record(cur)
+
+        def mark():
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(cur)
+            return e
+        works = []
+        for ch in self.chunks:
+            if self.use_ranges:
+                self.f.execute_range(*ch["local"])
+            else:
+                self.f.execute()
+            e0 = mark() if events is not None else None
+            my = ch["slots"][self.rank * ch["slot_bytes"]:(self.rank + 1) * ch["slot_bytes"]]
+            rc = self.L.lagassign_exchange_pack(st, ch["n"], vp(self.full_part.data_ptr() + 4 * ch["e0"]),
+                                                vp(self.full_cons.data_ptr() + 4 * ch["e0"]), self.pw, self.cw, vp(my.data_ptr()))
+            assert rc == 0, rc
+            e1 = mark() if events is not None else None
+            works.append(dist.all_gather_into_tensor(ch["slots"][:self.world * ch["slot_bytes"]], my, group=self.group, async_op=True)
+                         if ch["slot_bytes"] > 0 else None)      # (a chunk without partitions on any rank)
+            if events is not None:
+                events.append(("narrow", e0, e1))
+        for ch, w in zip(self.chunks, works):
+            e0 = mark() if events is not None else None
+            if w is None:
+                continue
+            w.wait()                                   # the current stream waits for this chunk's collective
+            e1 = mark() if events is not None else None
+            rc = self.L.lagassign_exchange_unpack_ranges(
+                st, vp(self.d_topic_off.data_ptr()), vp(self.d_topic_cset.data_ptr()), vp(self.d_cset_off.data_ptr()),
+                vp(self.d_cset_rank.data_ptr()), vp(ch["d_lo"].data_ptr()), vp(ch["d_hi"].data_ptr()), self.world, self.rank,
+                ch["max_topics"], vp(ch["slots"].data_ptr()), ch["slot_bytes"], self.pw, self.cw,
+                vp(self.full_part.data_ptr()), vp(self.full_cons.data_ptr()))
+            assert rc == 0, rc
+            if events is not None:
+                events.append(("all_gather_wait", e0, e1))
+                events.append(("widen", e1, mark()))
 
     def results(self):
         """(out_partition, out_consumer_rank) of the whole batch as contiguous 1-D tensors."""

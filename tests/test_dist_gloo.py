@@ -107,3 +107,25 @@ def test_exchange_format_choices():
     assert D.exchange_format(neg) == (4, 0)
     unsub = uniform_batch(2, 5, 0, np.zeros(10, np.int64))    # nobody subscribed: nothing to send for consumers
     assert D.exchange_format(unsub) == (1, 0)
+
+
+def test_chunk_ranges_cover_every_shard_once():
+    """The exchange pipeline cuts every rank's topic range into the same number of contiguous chunks."""
+    from kafka_lag_based_assignor_b200 import distributed as D
+    rng = np.random.default_rng(4)
+    for _ in range(30):
+        T = int(rng.integers(0, 60))
+        P = rng.integers(0, 500, size=T)
+        off = np.concatenate([[0], np.cumsum(P)]).astype(np.int64)
+        for world in (1, 2, 3, 8):
+            bounds = D.shard_bounds(off, world)
+            for k in (1, 2, 4):
+                chunks = D.chunk_ranges(bounds, k)
+                assert len(chunks) == k and all(len(c) == world for c in chunks)
+                for r, (lo, hi) in enumerate(bounds):
+                    pieces = [chunks[c][r] for c in range(k)]
+                    assert pieces[0][0] == lo and pieces[-1][1] == hi
+                    assert all(pieces[i][1] == pieces[i + 1][0] for i in range(k - 1))
+                    assert all(a <= b for a, b in pieces)
+    assert D.pick_chunks(12_800_000, False) == 4 and D.pick_chunks(3_200_000, False) == 1
+    assert D.pick_chunks(6_400_000, False) == 2 and D.pick_chunks(50_000_000, True) == 1
