@@ -254,45 +254,43 @@ def main():
         sh.execute()
     barrier()
 
-    # ---- timed: K steps, device events around each step on the launching stream -----------
+    # ---- timed: K steps as a caller runs them, device events around each step on the launching stream ---------
+    # (N > 1: kernels, narrowing, all-gather and widening: distributed.py)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    f.set_option(pkg.OPT_PROFILE, 1)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
-           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    prof_acc = {}
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    for a, m, b_ in ev:
-        flush()
-        a.record(stream)
-        if world == 1:
-            f.execute()
-            m.record(stream)
-        else:
-            sh.execute()          # kernels, narrowing, all-gather and widening, chunk-pipelined (distributed.py)
-            m.record(stream)
-        b_.record(stream)
-        torch.cuda.synchronize()
-        for k, (ms, n) in f.profile().items():
-            acc = prof_acc.setdefault(k, [0.0, 0])
-            acc[0] += ms; acc[1] += n
-    barrier()
-    clocks = sampler.stop()
-    f.set_option(pkg.OPT_PROFILE, 0)
-    t_total_ms = sum(a.elapsed_time(b_) for a, m, b_ in ev)
-    # Not the headline: the same step without the per-kernel events. Only then do the size bins
-    # of a mixed batch run on concurrent streams (lagassign_execute), so this is what a caller
-    # who does not profile gets; identical for single-bin workloads such as config 4.
-    ev_u = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 10))]
-    for a, b_ in ev_u:
+    for a, b_ in ev:
         flush()
         a.record(stream)
         sh.execute()
         b_.record(stream)
         torch.cuda.synchronize()
-    t_unprofiled_ms = sum(a.elapsed_time(b_) for a, b_ in ev_u) / len(ev_u)
+    barrier()
+    clocks = sampler.stop()
+    t_total_ms = sum(a.elapsed_time(b_) for a, b_ in ev)
+    t_unprofiled_ms = t_total_ms / args.steps
+    # ---- the same steps with CUDA events around every kernel launch (LAGASSIGN_OPT_PROFILE): the per-kernel times
+    # behind `roofline` and `kernel_ms_per_step`. Not the headline: the events serialise the size bins of a mixed
+    # batch, which otherwise run on concurrent streams.
+    f.set_option(pkg.OPT_PROFILE, 1)
+    n_prof = max(3, min(args.steps, 10))
+    prof_acc = {}
+    t_profiled_ms = 0.0
+    for _ in range(n_prof):
+        flush()
+        a = torch.cuda.Event(enable_timing=True); b_ = torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        sh.execute()
+        b_.record(stream)
+        torch.cuda.synchronize()
+        t_profiled_ms += a.elapsed_time(b_) / n_prof
+        for k, (ms, n) in f.profile().items():
+            acc = prof_acc.setdefault(k, [0.0, 0])
+            acc[0] += ms; acc[1] += n
+    f.set_option(pkg.OPT_PROFILE, 0)
     exchange_ms = None
-    if world > 1:          # where the exchange's time goes (not the headline: separate steps with extra events)
+    if world > 1:          # where the exchange's time goes (eager steps with extra events)
         acc = {}
         for _ in range(5):
             flush()
@@ -302,10 +300,11 @@ def main():
             for name, e0, e1 in evs:
                 acc[name] = acc.get(name, 0.0) + e0.elapsed_time(e1) / 5
         exchange_ms = dict(acc, chunks=sh.n_chunks,
-                           note="per step, summed over the chunks; all_gather_wait = time the compute stream waits for a "
-                                "chunk's collective after its own work is done (the rest of the collective is hidden behind "
+                           note="per eager step, summed over the chunks; all_gather_wait = time the compute stream waits for "
+                                "a chunk's collective after its own work is done (the rest of the collective is hidden behind "
                                 "the next chunk's kernels)")
-    t_compute_ms = sum(a.elapsed_time(m) for a, m, b_ in ev) if world == 1 else sum(v[0] for v in prof_acc.values())
+    kernel_ms_step = sum(v[0] for v in prof_acc.values()) / n_prof
+    t_compute_ms = kernel_ms_step * args.steps
     launches_per_step = f.stats()["kernel_launches"]
     stats = f.stats()
 
@@ -395,6 +394,7 @@ def main():
                 a.record(stream); fa.execute(); z.record(stream); torch.cuda.synchronize()
                 tot += a.elapsed_time(z)
             return tot / steps
+        ms_plain = timed(f)
         fg = pkg.FlatAssignor(local_rank, stream=stream.cuda_stream)
         fg.set_option(pkg.OPT_GROUP, 1)
         fg.upload(*args_of(batch))
@@ -410,11 +410,11 @@ def main():
                           batch["topic_cset"], batch["cset_off"], batch["cset_rank"])
         ms_off = timed(fo)
         fo.close()
-        next_rows = {"grouping_by_member": {"ms_per_step_with_grouping": ms_group, "ms_per_step_without": t_compute_ms / args.steps,
+        next_rows = {"grouping_by_member": {"ms_per_step_with_grouping": ms_group, "ms_per_step_without": ms_plain,
                                             "check": "ok" if grouped_ok else "MISMATCH",
                                             "note": "SURVEY 8f row 2: stable partition of the flat result by member rank on the device"},
                      "device_lag_computation": {"ms_per_step_with_offsets": ms_off,
-                                                "ratio_to_plain_step": ms_off / (t_compute_ms / args.steps),
+                                                "ratio_to_plain_step": ms_off / ms_plain,
                                                 "note": "SURVEY 8f row 1: computePartitionLag (Main:376-404) evaluated inside the sort kernels as "
                                                         "they build their keys (no lag array, no extra launch): the step reads 25 B/partition of "
                                                         "raw offsets instead of 8 B of lags"}}
@@ -432,7 +432,7 @@ def main():
         # dominant kernel of this rank's step
         dom = max(prof_acc.items(), key=lambda kv: kv[1][0]) if prof_acc else ("none", [1e-9, 1])
         dom_name, (dom_ms, dom_n) = dom[0], dom[1]
-        step_ms = t_compute_ms / args.steps
+        step_ms = kernel_ms_step
         share = dom_ms / max(sum(v[0] for v in prof_acc.values()), 1e-12)
         if dom_name == "k_big_scatter":
             # 64-bit key + 32-bit payload read and written once per executed digit pass
@@ -450,7 +450,7 @@ def main():
         per_launch_ms = dom_ms / max(dom_n, 1)
         # `alg` is what ONE launch of the radix kernels moves, but what ALL launches of a step move together for the
         # on-chip kernels (N > 1 runs them chunk by chunk)
-        alg_ms = dom_ms / args.steps if dom_name in ("k_warp_topics", "k_cta_topics") else per_launch_ms
+        alg_ms = dom_ms / n_prof if dom_name in ("k_warp_topics", "k_cta_topics") else per_launch_ms
         achieved = (alg / (alg_ms * 1e-3) / 1e9) if alg else None
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -480,15 +480,16 @@ def main():
                     "d2h_bytes_per_step_int32": st2["d2h_bytes"],
                     "value_int32_replanned": N_total * e2e_steps / (t_e2e_replan_ms * 1e-3),
                     "h2d_bytes_per_step_replanned": st2_replan["h2d_bytes"]},
-            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches": (launches_per_step + (2 * sh.n_chunks if world > 1 else 0)) * args.steps,   # + narrow / widen kernels
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "bytes_model": alg_note,
                          "launch_ms": per_launch_ms, "share_of_step": share},
-            "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof_acc.items()},
+            "kernel_ms_per_step": {k: v[0] / n_prof for k, v in prof_acc.items()},
             "ms_per_step_unprofiled": t_unprofiled_ms,
+            "ms_per_step_profiled": t_profiled_ms,
             "compute_ms_per_step": step_ms,
-            "gather_ms_per_step": (t_total_ms - t_compute_ms) / args.steps,
+            "gather_ms_per_step": max(t_total_ms / args.steps - step_ms, 0.0),
             "exchange_ms": exchange_ms,
             "parity_spot_check": "ok" if bad == 0.0 else "MISMATCH",
             "next_rows": next_rows,

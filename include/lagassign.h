@@ -156,6 +156,10 @@ int  lagassign_create(lagassign_ctx **ctx, int device);
  * sees the kernels. */
 int  lagassign_create_on_stream(lagassign_ctx **ctx, int device, void *cuda_stream);
 
+/* Move a context created with lagassign_create_on_stream to another stream of the caller (for example the stream a
+ * CUDA graph is being captured on: lagassign_execute_range enqueues kernels only, so a caller may capture its steps). */
+int  lagassign_set_stream(lagassign_ctx *ctx, void *cuda_stream);
+
 /* One context over SEVERAL devices of this process ("topics shard naturally across the 8 GPUs"):
  * the batch of lagassign_assign_batch / upload is cut into contiguous topic ranges balanced by partition count,
  * one per device; every device runs the whole path on its range concurrently (its own stream and PCIe link) and

@@ -107,6 +107,7 @@ def load_library() -> ctypes.CDLL:
     L.lagassign_device_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
     L.lagassign_create.argtypes = [ctypes.POINTER(vp), i32]
     L.lagassign_create_on_stream.argtypes = [ctypes.POINTER(vp), i32, vp]
+    L.lagassign_set_stream.argtypes = [vp, vp]
     L.lagassign_create_multi.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int), i32]
     L.lagassign_shard_count.argtypes = [vp, ctypes.POINTER(ctypes.c_int)]
     L.lagassign_destroy.argtypes = [vp]
@@ -139,7 +140,7 @@ def load_library() -> ctypes.CDLL:
     L.lagassign_subscriptions_last_error.restype = ctypes.c_char_p
     L.lagassign_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
     L.lagassign_host_free.argtypes = [vp]
-    for name in ("lagassign_device_count", "lagassign_create", "lagassign_create_on_stream", "lagassign_create_multi",
+    for name in ("lagassign_device_count", "lagassign_create", "lagassign_create_on_stream", "lagassign_set_stream", "lagassign_create_multi",
                  "lagassign_shard_count",
                  "lagassign_set_option", "lagassign_assign_batch", "lagassign_assign_batch_narrow", "lagassign_upload",
                  "lagassign_upload_offsets", "lagassign_execute", "lagassign_execute_range", "lagassign_sync", "lagassign_download",
@@ -237,6 +238,7 @@ class FlatAssignor:
         if want_totals:
             self.set_option(OPT_TOTALS, 1)
         self.want_totals = want_totals
+        self.profiling = False
 
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
@@ -261,6 +263,8 @@ class FlatAssignor:
 
     def set_option(self, option: int, value: int):
         self._check(self._L.lagassign_set_option(self._ctx, option, value))
+        if option == OPT_PROFILE:
+            self.profiling = bool(value)
 
     def _batch(self, topic_off, lag, partition, topic_cset, cset_off, cset_rank):
         topic_off = _arr(topic_off, np.int64, "topic_off")
@@ -310,6 +314,10 @@ class FlatAssignor:
 
     def execute(self):
         self._check(self._L.lagassign_execute(self._ctx))
+
+    def set_stream(self, cuda_stream: int):
+        """lagassign_set_stream(): later work is enqueued on this stream (contexts created on a caller's stream only)."""
+        self._check(self._L.lagassign_set_stream(self._ctx, ctypes.c_void_p(cuda_stream)))
 
     def execute_range(self, t_lo: int, t_hi: int):
         """lagassign_execute_range(): the kernels of the topics [t_lo, t_hi) of the uploaded batch only."""

@@ -832,6 +832,15 @@ int lagassign_create_on_stream(lagassign_ctx** ctx, int device, void* cuda_strea
     return create_common(ctx, device, cuda_stream, false);
 }
 
+int lagassign_set_stream(lagassign_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return fail(nullptr, LAGASSIGN_ERR_ARG, "ctx is NULL");
+    if (!ctx->shards.empty()) return fail(ctx, LAGASSIGN_ERR_UNSUPPORTED, "not available on a multi-device context");
+    if (ctx->own_stream) return fail(ctx, LAGASSIGN_ERR_STATE, "the context owns its stream (created with lagassign_create)");
+    ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    if (ctx->grp) ctx->grp->stream = ctx->stream;
+    return LAGASSIGN_OK;
+}
+
 void lagassign_destroy(lagassign_ctx* ctx) {
     if (!ctx) return;
     if (!ctx->shards.empty()) {

@@ -121,11 +121,11 @@ def chunk_ranges(bounds: Sequence[Tuple[int, int]], n_chunks: int) -> List[List[
 
 
 def pick_chunks(local_partitions: int, has_radix_topics: bool) -> int:
-    """Chunks of the exchange pipeline. A chunk's all-gather runs while the next chunk's kernels do, so chunks pay off
-    while a shard's kernels take longer than a collective's latency (~20 us): about 3 M partitions per chunk."""
-    if has_radix_topics:
-        return 1                      # the radix path is one chain of device-wide kernels: lagassign_execute()
-    return int(min(4, max(1, round(local_partitions / 3.2e6))))
+    """Chunks of the exchange pipeline (a chunk's all-gather runs while the next chunk's kernels do). Measured at
+    BASELINE config 4 on 2 x B200 with the steps driven from Python: 4 chunks 0.227 ms per step, 1 chunk 0.191 ms — the
+    collective does hide behind the kernels (the compute stream waits 16 us for it instead of 62), but four small kernel,
+    narrow and widen launches each cost more than they hide. So: one chunk unless the caller asks (n_chunks)."""
+    return 1
 
 
 class ShardedAssignor:
@@ -172,7 +172,7 @@ class ShardedAssignor:
             dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)      # any rank with radix-path topics: one chunk everywhere
             if int(flag.item()):
                 self.n_chunks = 1
-        self.use_ranges = not bool(int(flag.item()))
+        self.use_ranges = self.n_chunks > 1          # one chunk: lagassign_execute() (all size bins, concurrent streams)
         t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
         self.chunks = []
         for ranges in chunk_ranges(self.bounds, self.n_chunks):
@@ -192,12 +192,15 @@ class ShardedAssignor:
 
     def execute(self, gather: bool = True, events=None):
         """One step. `events` (bench.py): a list that receives (name, start event, end event) triples of the exchange legs."""
-        import ctypes
-        import torch
-        import torch.distributed as dist
         if self.world == 1 or not gather:
             self.f.execute()
             return
+        self._step(events)
+
+    def _step(self, events=None):
+        import ctypes
+        import torch
+        import torch.distributed as dist
         cur = torch.cuda.current_stream()
         st = ctypes.c_void_p(cur.cuda_stream)
         vp = ctypes.c_void_p

@@ -2,7 +2,7 @@
 # N-GPU run of the default bench (config 4, topic-sharded, all-gather inside the step):
 #   gpurun --gpus N --timeout 900 -- 'bash scripts/scale_run.sh N'
 N=${1:-2}
-timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
+timeout -s KILL 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
   --master-port 29533 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline 2>&1 | grep '^{' | tail -1 > gpurun_out/scale_n$N.json
 python - <<PY
 import json
