@@ -1,10 +1,10 @@
 #!/bin/bash
 # one-GPU check of the current tree: the whole GPU suite, then the headline configs (short form)
 #   gpurun --timeout 1200 -- 'bash scripts/quick_check.sh [configs...]'
-timeout -s KILL 700 python -m pytest tests -m gpu -q -x --timeout=600 2>&1 | tail -4
+timeout -s KILL 400 python -m pytest tests -m gpu -q -x --timeout=300 2>&1 | tail -4
 mkdir -p gpurun_out
 for c in ${@:-4 6 5 2}; do
-  timeout -s KILL 300 python bench.py --config $c --steps 10 --no-cpu-baseline 2>gpurun_out/err_c$c.txt | tail -1 > gpurun_out/quick_c$c.json
+  timeout -s KILL 150 python bench.py --config $c --steps 10 --no-cpu-baseline 2>gpurun_out/err_c$c.txt | tail -1 > gpurun_out/quick_c$c.json
   python - <<PY || tail -5 gpurun_out/err_c$c.txt
 import json
 d=json.load(open("gpurun_out/quick_c$c.json"))
