@@ -1121,9 +1121,14 @@ k_group_finalize(BigTopics bt, const int64_t* __restrict__ glag, int64_t n_membe
     const int64_t n = bt.P[0];
     const int sel = bt.sel_final[0];
     const uint32_t* fpay = (sel == SEL_A) ? bt.payA : bt.payB;
+    const uint64_t* fkey = (sel == SEL_A) ? bt.keyA : bt.keyB;
+    // the member rank of sorted position i comes from the SORTED key (a sequential read), not from glag[e] (a random one)
+    auto rank_at = [&](int64_t i) -> int64_t {
+        return n_members - ((sel == SEL_RAW) ? glag[i] : (int64_t)(fkey[i] ^ LAG_KEY_MASK));
+    };
     for (int64_t i = n_unassigned + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t e = (sel == SEL_RAW) ? i : (int64_t)fpay[i];
-        const int64_t rank = n_members - glag[e];
+        const int64_t rank = rank_at(i);
         const int64_t o = i - n_unassigned;
         int clo = 0, chi = n_coarse;                                               // last c with coarse[c] <= e
         while (chi - clo > 1) {
@@ -1137,11 +1142,7 @@ k_group_finalize(BigTopics bt, const int64_t* __restrict__ glag, int64_t n_membe
         }
         grp_topic[o] = (int32_t)lo;
         grp_part[o] = out_part[e];
-        bool first = (i == n_unassigned);
-        if (!first) {
-            const int64_t ep = (sel == SEL_RAW) ? i - 1 : (int64_t)fpay[i - 1];
-            first = (n_members - glag[ep]) != rank;
-        }
+        const bool first = (i == n_unassigned) || rank_at(i - 1) != rank;
         if (first) member_start[rank] = o;
     }
 }
