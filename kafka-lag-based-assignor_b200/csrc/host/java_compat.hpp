@@ -54,58 +54,6 @@ inline uint32_t java_string_hash(const std::string& s) {
     return h;
 }
 
-// Iteration order of a java.util.HashMap<String, ?> (OpenJDK 8+) that only sees
-// put() of new keys — what consumersPerTopic builds (:412-424) and :177 iterates.
-// Default capacity 16, load factor 0.75, doubling with order-preserving bucket
-// splits, index (h ^ h>>>16) & (n-1), new keys appended at the chain tail.
-// A bin that would be treeified (9th key in one bucket of a >=64-slot table)
-// reorders its chain in ways not modelled here: that case throws.
-class JavaHashMapOrder {
- public:
-    JavaHashMapOrder() : cap_(16), buckets_(16) {}
-
-    // returns the key's index (insertion number); inserts it if new
-    int put_if_absent(const std::string& key) {
-        auto it = index_.find(key);
-        if (it != index_.end()) return it->second;
-        const int id = static_cast<int>(keys_.size());
-        keys_.push_back(key);
-        hashes_.push_back(spread(java_string_hash(key)));
-        index_.emplace(key, id);
-        std::vector<int>& chain = buckets_[hashes_[id] & (cap_ - 1)];
-        chain.push_back(id);
-        if (chain.size() >= 9) {
-            if (cap_ < 64) resize();
-            else throw std::runtime_error(
-                "topic names collide into a treeified java.util.HashMap bin; its iteration order is not modelled");
-        }
-        if (keys_.size() > static_cast<size_t>(cap_) * 3 / 4) resize();
-        return id;
-    }
-
-    std::vector<int> order() const {
-        std::vector<int> o;
-        o.reserve(keys_.size());
-        for (const auto& chain : buckets_) for (int id : chain) o.push_back(id);
-        return o;
-    }
-    const std::string& key(int id) const { return keys_[id]; }
-    size_t size() const { return keys_.size(); }
-
- private:
-    static uint32_t spread(uint32_t h) { return h ^ (h >> 16); }
-    void resize() {
-        std::vector<std::vector<int>> old;
-        old.swap(buckets_);
-        cap_ *= 2;
-        buckets_.assign(cap_, {});
-        for (const auto& chain : old) for (int id : chain) buckets_[hashes_[id] & (cap_ - 1)].push_back(id);
-    }
-    uint32_t cap_;
-    std::vector<std::vector<int>> buckets_;
-    std::vector<std::string> keys_;
-    std::vector<uint32_t> hashes_;
-    std::unordered_map<std::string, int> index_;
-};
-
 }  // namespace lagassign_host
+
+#include "java_hashmap_order.hpp"   // JavaHashMapOrder: iteration order of the HashMap built by consumersPerTopic, tree bins included

@@ -136,3 +136,89 @@ def test_unflatten_argument_errors(pkg):
     with pytest.raises(pkg.LagAssignError):           # a rank that names no member
         a.unflatten(np.array([0, 1], np.int32), np.array([0, 7], np.int32))
     assert a.unflatten(np.array([1, 0], np.int32), np.array([0, -1], np.int32)) == {"m": [("t", 1)]}
+
+
+# ---- topic order = iteration order of the java.util.HashMap built by consumersPerTopic, tree bins included ---------
+
+def _topic_order_cpp(pkg, topics):
+    """Topics in the order the C++ mirror visits them (JavaHashMapOrder) when one member subscribes to `topics`."""
+    a = pkg.LagBasedPartitionAssignor()
+    lags = {t: [(t, 0, 1)] for t in topics}
+    _, order, _ = a.flatten(lags, {"m": list(topics)})
+    return order
+
+
+def _colliding_names(rng, n, low_bits):
+    """n distinct names whose spread String.hashCode agrees in its `low_bits` lowest bits (they share a bucket until the
+    table has more than 2^low_bits slots, then split both ways)."""
+    from java_hashmap_model import string_hash
+    out, target = [], None
+    i = 0
+    while len(out) < n:
+        s = "topic-%d-%d" % (int(rng.integers(0, 1 << 30)), i)
+        i += 1
+        h = string_hash(s)
+        h = (h ^ (h >> 16)) & ((1 << low_bits) - 1)
+        if target is None:
+            target = h
+        if h == target:
+            out.append(s)
+    return out
+
+
+@pytest.mark.parametrize("case", ["plain", "equal_hashes", "shared_low_bits", "two_tree_bins", "big"])
+def test_topic_order_matches_the_python_hashmap_model(pkg, case):
+    import itertools
+    from java_hashmap_model import JavaHashMapModel
+    rng = np.random.default_rng({"plain": 1, "equal_hashes": 2, "shared_low_bits": 3, "two_tree_bins": 4, "big": 5}[case])
+    filler = ["f%d" % i for i in range(200)]
+    if case == "plain":
+        topics = ["t%05d" % int(i) for i in rng.permutation(3000)]      # (such regular names do fill a bin now and then)
+        expect_tree = None
+    elif case == "equal_hashes":
+        # "Aa" and "BB" have the same hashCode, so do all concatenations: one bucket for ever; 9th key -> resize (table
+        # below 64 slots), ... then a tree; later keys are linked after their tree parents
+        fam = ["".join(p) for p in itertools.product(["Aa", "BB"], repeat=5)]
+        order = [int(i) for i in rng.permutation(len(fam))]
+        topics = [fam[i] for i in order[:12]] + filler[:70] + [fam[i] for i in order[12:]] + filler[70:]
+        expect_tree = True
+    elif case == "shared_low_bits":
+        col = _colliding_names(rng, 40, 9)         # share a bucket up to 512 slots; the 1024-slot table splits the tree
+        topics = filler[:50] + col[:25] + ["g%d" % i for i in range(600)] + col[25:] + ["h%d" % i for i in range(400)]
+        expect_tree = True
+    elif case == "two_tree_bins":
+        a, b = _colliding_names(rng, 14, 8), _colliding_names(rng, 11, 8)
+        topics = filler[:60]
+        for i in range(14):
+            topics.append(a[i])
+            if i < 11:
+                topics.append(b[i])
+        topics += ["z%d" % i for i in range(300)]   # growth past 256 slots: both trees split, short halves untreeify
+        expect_tree = True
+    else:
+        topics = ["events.v1.tenant%d.stream" % int(i) for i in rng.permutation(60000)]
+        expect_tree = None
+    model = JavaHashMapModel()
+    for t in topics:
+        model.put(t)
+    if expect_tree is not None:
+        assert model.treeified == expect_tree
+    got = _topic_order_cpp(pkg, topics)
+    assert got == model.order()
+    assert sorted(got) == sorted(set(topics))
+
+
+def test_topic_order_without_tree_bins_is_the_plain_chain_order(pkg):
+    """Where no bin is treeified the order is: buckets by index, keys of a bucket in insertion order (round 1's model)."""
+    from java_hashmap_model import string_hash
+    rng = np.random.default_rng(9)
+    topics = ["n%d" % int(i) for i in rng.permutation(500)]
+    cap = 16
+    while len(topics) > cap * 3 // 4:
+        cap *= 2
+    buckets = {}
+    for t in topics:
+        h = string_hash(t)
+        buckets.setdefault((h ^ (h >> 16)) & (cap - 1), []).append(t)
+    expect = [t for i in sorted(buckets) for t in buckets[i]]
+    assert _topic_order_cpp(pkg, topics) == expect
