@@ -33,7 +33,7 @@ for r in rows[hi+1:]:
 tot=sum(v[1] for v in agg.values())
 with open("profiles/${R}_launches_config$c.txt","w") as f:
     f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py --config $c --steps 2 --warmup 3 --no-cpu-baseline --hot-path-only\n")
-    f.write("# --hot-path-only: the process launches nothing but the execute() steps (3 warm-up + 2 timed + 2 without per-kernel events);\n")
+    f.write("# --hot-path-only: the process launches nothing but the execute() steps (3 warm-up + 2 timed + 3 with per-kernel events);\n")
     f.write("# no e2e calls, no next-rows section. Cold-cache serialised times: compare SHARES with bench.py's share_of_step, not absolutes.\n")
     f.write("%-60s %8s %14s %7s\n"%("kernel","launches","total ns","share"))
     for k,(n,t) in agg.items(): f.write("%-60s %8d %14.0f %6.1f%%\n"%(k[:60],n,t,100*t/tot))
