@@ -62,6 +62,16 @@ int  lagassign_group_add_subscription(lagassign_group *g, const char *member_id,
 int  lagassign_group_add_topic_lags(lagassign_group *g, const char *topic,
                                     const int32_t *partitions, const int64_t *lags, int64_t n);
 
+/* Raw offsets of a topic instead of its lags: what readTopicPartitionLags gathers per partition (Main:338-356).
+ * begin / end: topicBeginOffsets / topicEndOffsets.getOrDefault(p, 0); committed + has_committed: the
+ * OffsetAndMetadata of the partition, if any. lagassign_group_assign() then lets the DEVICE compute every lag
+ * (computePartitionLag, Main:376-404, inside the sort kernels: lagassign_upload_offsets). A group is filled either
+ * with lags or with offsets. auto.offset.reset: "latest" (the default, Main:346-347), anything else = earliest. */
+int  lagassign_group_add_topic_offsets(lagassign_group *g, const char *topic, const int32_t *partitions,
+                                       const int64_t *begin_offset, const int64_t *end_offset,
+                                       const int64_t *committed, const uint8_t *has_committed, int64_t n);
+int  lagassign_group_set_auto_offset_reset(lagassign_group *g, const char *mode);
+
 /* assign(partitionLagPerTopic, subscriptions) (Main:166-188) on the GPU. */
 int  lagassign_group_assign(lagassign_group *g);
 

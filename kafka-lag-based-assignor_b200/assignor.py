@@ -48,6 +48,8 @@ def _load_host():
     H.lagassign_group_clear.argtypes = [vp]
     H.lagassign_group_add_subscription.argtypes = [vp, cp, ctypes.POINTER(cp), i32]
     H.lagassign_group_add_topic_lags.argtypes = [vp, cp, vp, vp, i64]
+    H.lagassign_group_add_topic_offsets.argtypes = [vp, cp, vp, vp, vp, vp, vp, i64]
+    H.lagassign_group_set_auto_offset_reset.argtypes = [vp, cp]
     H.lagassign_group_assign.argtypes = [vp]
     H.lagassign_group_flatten.argtypes = [vp, vp]
     H.lagassign_group_unflatten.argtypes = [vp, vp, vp]
@@ -150,6 +152,25 @@ class LagBasedPartitionAssignor:
                subscriptions: Mapping[str, Sequence[str]]) -> Dict[str, List[TopicPartition]]:
         H = self._H
         members = self._load_maps(partition_lag_per_topic, subscriptions)
+        self._check(H.lagassign_group_assign(self._g))
+        return self._collect(members)
+
+    def assign_from_offsets(self, offsets_per_topic, subscriptions, auto_offset_reset: str = "latest"):
+        """The same assignment from raw offsets: {topic: [(partition, begin, end, committed or None), ...]}.
+        computePartitionLag (Main:376-404) runs on the device (lagassign_group_add_topic_offsets)."""
+        H = self._H
+        members = self._load_maps({}, subscriptions)
+        self._check(H.lagassign_group_set_auto_offset_reset(self._g, _enc(auto_offset_reset)))
+        for topic, entries in offsets_per_topic.items():
+            n = len(entries)
+            parts = np.array([e[0] for e in entries], dtype=np.int32)
+            begin = np.array([e[1] for e in entries], dtype=np.int64)
+            end = np.array([e[2] for e in entries], dtype=np.int64)
+            com = np.array([0 if e[3] is None else e[3] for e in entries], dtype=np.int64)
+            has = np.array([0 if e[3] is None else 1 for e in entries], dtype=np.uint8)
+            ptr = lambda a: a.ctypes.data if n else None
+            self._check(H.lagassign_group_add_topic_offsets(self._g, _enc(topic), ptr(parts), ptr(begin), ptr(end),
+                                                            ptr(com), ptr(has), n))
         self._check(H.lagassign_group_assign(self._g))
         return self._collect(members)
 

@@ -16,6 +16,8 @@ struct lagassign_group {
     std::unique_ptr<LagBasedPartitionAssignor> assignor;
     Subscriptions subscriptions;
     PartitionLagPerTopic lags;
+    PartitionOffsetsPerTopic offsets;
+    std::string auto_offset_reset = "latest";       // ConsumerConfig default, Main:346-347
     Assignment result;
     FlatBatch flat;
     bool flat_valid = false;
@@ -78,7 +80,7 @@ const char* lagassign_group_name(const lagassign_group* g) { return g ? g->name.
 
 int lagassign_group_clear(lagassign_group* g) {
     if (!g) return fail(nullptr, LAGASSIGN_ERR_ARG, "group is NULL");
-    g->subscriptions.clear(); g->lags.clear(); g->result.clear(); g->result_index.clear(); g->topic_order.clear();
+    g->subscriptions.clear(); g->lags.clear(); g->offsets.clear(); g->result.clear(); g->result_index.clear(); g->topic_order.clear();
     g->flat = FlatBatch(); g->flat_valid = false;
     return LAGASSIGN_OK;
 }
@@ -101,9 +103,33 @@ int lagassign_group_add_topic_lags(lagassign_group* g, const char* topic, const 
     return LAGASSIGN_OK;
 }
 
+int lagassign_group_add_topic_offsets(lagassign_group* g, const char* topic, const int32_t* partitions,
+                                      const int64_t* begin_offset, const int64_t* end_offset, const int64_t* committed,
+                                      const uint8_t* has_committed, int64_t n) {
+    if (!g || !topic || (n > 0 && (!begin_offset || !end_offset || !committed || !has_committed)))
+        return fail(g, LAGASSIGN_ERR_ARG, "group, topic or an offset array is NULL");
+    std::vector<TopicPartitionOffsets> v;
+    v.reserve((size_t)n);
+    for (int64_t i = 0; i < n; ++i)
+        v.push_back({topic, partitions ? partitions[i] : (int32_t)i, begin_offset[i], end_offset[i], committed[i], has_committed[i] != 0});
+    g->offsets[topic] = std::move(v);
+    return LAGASSIGN_OK;
+}
+
+int lagassign_group_set_auto_offset_reset(lagassign_group* g, const char* mode) {
+    if (!g || !mode) return fail(g, LAGASSIGN_ERR_ARG, "group or mode is NULL");
+    g->auto_offset_reset = mode;
+    return LAGASSIGN_OK;
+}
+
 int lagassign_group_assign(lagassign_group* g) {
     if (!g) return fail(nullptr, LAGASSIGN_ERR_ARG, "group is NULL");
+    if (!g->offsets.empty() && !g->lags.empty())
+        return fail(g, LAGASSIGN_ERR_ARG, "a group takes either lags or raw offsets, not both");
     try {
+        if (!g->offsets.empty())
+            g->result = g->assignor->assignFromOffsets(g->offsets, g->auto_offset_reset, g->subscriptions, &g->topic_order);
+        else
         g->result = g->assignor->assign(g->lags, g->subscriptions, &g->topic_order);
     } catch (const std::exception& e) {
         return fail(g, LAGASSIGN_ERR_CUDA, e.what());

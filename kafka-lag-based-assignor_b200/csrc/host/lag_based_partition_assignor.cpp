@@ -185,4 +185,68 @@ Assignment LagBasedPartitionAssignor::assign(const PartitionLagPerTopic& lags, c
     return unflatten(fb, out_part.data(), out_cons.data());
 }
 
+Assignment LagBasedPartitionAssignor::assignFromOffsets(const PartitionOffsetsPerTopic& offsets, const std::string& autoOffsetReset,
+                                                        const Subscriptions& subscriptions, std::vector<std::string>* topicOrderOut) {
+    // layout (member ranks, topic order, consumer sets, partition ids) exactly as for lags; the lag column stays empty
+    PartitionLagPerTopic shape;
+    for (const auto& kv : offsets) {
+        std::vector<TopicPartitionLag>& v = shape[kv.first];
+        v.reserve(kv.second.size());
+        for (const TopicPartitionOffsets& e : kv.second) v.push_back({e.topic, e.partition, 0});
+    }
+    const FlatBatch fb = flatten(shape, subscriptions);
+    if (topicOrderOut) *topicOrderOut = fb.topics;
+    const int64_t T = (int64_t)fb.topics.size();
+    const int64_t N = fb.topic_off[(size_t)T];
+    if (T == 0 || N == 0) return unflatten(fb, nullptr, nullptr);
+    std::vector<int64_t> begin((size_t)N), end((size_t)N), committed((size_t)N);
+    std::vector<uint8_t> has((size_t)N);
+    for (int64_t k = 0; k < T; ++k) {
+        auto it = offsets.find(fb.topics[(size_t)k]);
+        if (it == offsets.end()) continue;
+        int64_t o = fb.topic_off[(size_t)k];
+        for (const TopicPartitionOffsets& e : it->second) {
+            begin[(size_t)o] = e.beginOffset;
+            end[(size_t)o] = e.endOffset;
+            committed[(size_t)o] = e.hasCommitted ? e.committedOffset : 0;
+            has[(size_t)o] = e.hasCommitted ? 1 : 0;
+            ++o;
+        }
+    }
+    if (!ctx_) {
+        int rc = lagassign_create(&ctx_, device_);
+        if (rc != LAGASSIGN_OK) {
+            ctx_ = nullptr;
+            throw std::runtime_error(std::string("lagassign_create failed: ") + lagassign_last_error(nullptr));
+        }
+    }
+    std::vector<int32_t> out_part((size_t)N), out_cons((size_t)N);
+    lagassign_batch in{};
+    in.n_topics = T;
+    in.topic_off = fb.topic_off.data();
+    in.lag = nullptr;
+    in.partition = fb.implicit_ids ? nullptr : fb.partition.data();
+    in.topic_cset = fb.topic_cset.data();
+    in.n_csets = (int64_t)fb.cset_off.size() - 1;
+    in.cset_off = fb.cset_off.data();
+    in.cset_rank = fb.cset_rank.data();
+    lagassign_offsets offs{};
+    offs.begin_offset = begin.data();
+    offs.end_offset = end.data();
+    offs.committed = committed.data();
+    offs.has_committed = has.data();
+    std::string mode = autoOffsetReset;
+    for (char& c : mode) c = (char)std::tolower((unsigned char)c);
+    offs.reset_latest = mode == "latest" ? 1 : 0;                     // Main:391 equalsIgnoreCase("latest"), else "assume earliest"
+    lagassign_result out{};
+    out.out_partition = out_part.data();
+    out.out_consumer_rank = out_cons.data();
+    int rc = lagassign_upload_offsets(ctx_, &in, &offs);
+    if (rc == LAGASSIGN_OK) rc = lagassign_execute(ctx_);
+    if (rc == LAGASSIGN_OK) rc = lagassign_download(ctx_, &out);
+    if (rc != LAGASSIGN_OK)
+        throw std::runtime_error(std::string("assignment from offsets failed: ") + lagassign_last_error(ctx_));
+    return unflatten(fb, out_part.data(), out_cons.data());
+}
+
 }  // namespace lagassign_host

@@ -26,6 +26,16 @@ struct TopicPartitionLag {         // Main:431-455
     int64_t lag;
 };
 
+// What readTopicPartitionLags gathers per partition before it calls computePartitionLag (Main:338-356): the begin
+// and end offsets (0 when the broker did not report them, Main:350-351) and the committed offset if there is one.
+struct TopicPartitionOffsets {
+    std::string topic;
+    int32_t partition;
+    int64_t beginOffset, endOffset, committedOffset;
+    bool hasCommitted;              // partitionMetadata != null (Main:384)
+};
+using PartitionOffsetsPerTopic = std::unordered_map<std::string, std::vector<TopicPartitionOffsets>>;
+
 // Map<String, List<String>> member -> topics, as its entries in ITERATION ORDER
 // (Main:168; the order matters through consumersPerTopic, Main:413).
 using Subscriptions = std::vector<std::pair<std::string, std::vector<std::string>>>;
@@ -70,6 +80,12 @@ class LagBasedPartitionAssignor {
     // topics in the order they were assigned.
     Assignment assign(const PartitionLagPerTopic& partitionLagPerTopic, const Subscriptions& subscriptions,
                       std::vector<std::string>* topicOrderOut = nullptr);
+
+    // The same assignment from RAW OFFSETS: readTopicPartitionLags' loop body (Main:344-356) moves to the device —
+    // every partition's lag is computePartitionLag(committed?, begin, end, autoOffsetReset) (Main:376-404), evaluated
+    // by the sort kernels as they build their keys (lagassign_upload_offsets); no lag exists on the host.
+    Assignment assignFromOffsets(const PartitionOffsetsPerTopic& offsetsPerTopic, const std::string& autoOffsetReset,
+                                 const Subscriptions& subscriptions, std::vector<std::string>* topicOrderOut = nullptr);
 
     // The two host-side halves of assign(): everything before and after the device call.
     // flatten: member ranks (Main:258-259), consumersPerTopic and its iteration order

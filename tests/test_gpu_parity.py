@@ -848,3 +848,30 @@ def test_invert_subscriptions_argument_errors(pkg):
     with pytest.raises(pkg.LagAssignError) as e:
         pkg.invert_subscriptions(4, [0, 2], [1, 9])            # topic index out of range
     assert e.value.code == -1
+
+
+def test_host_mirror_assign_from_offsets(pkg):
+    """lagassign_group_add_topic_offsets: the plugin-shaped mirror fed with raw offsets (what readTopicPartitionLags
+    gathers, Main:338-356) gives the assignment of the same group fed with computePartitionLag's lags (Main:376-404)."""
+    rng = np.random.default_rng(31)
+    members = [f"consumer-{int(i)}" for i in rng.permutation(9)]
+    topics = [f"orders.{i}" for i in range(25)]
+    subs = {m: [topics[int(i)] for i in rng.permutation(25)[:int(rng.integers(1, 25))]] for m in members}
+    for mode in ("latest", "earliest", "LATEST", "none"):
+        offsets, lags = {}, {}
+        for t in topics:
+            P = int(rng.integers(0, 40))
+            ids = [int(x) for x in (range(P) if rng.random() < 0.5 else rng.permutation(P + 5)[:P])]
+            rows, lrows = [], []
+            for pid in ids:
+                end = int(rng.integers(0, 1 << 40))
+                begin = int(end * rng.random())
+                com = None if rng.random() < 0.3 else int(rng.integers(0, 1 << 40))
+                rows.append((pid, begin, end, com))
+                lrows.append((t, pid, oracle.compute_partition_lag(com, begin, end, mode)))
+            offsets[t], lags[t] = rows, lrows
+        a = pkg.LagBasedPartitionAssignor(0)
+        got = a.assign_from_offsets(offsets, subs, auto_offset_reset=mode)
+        exp = a.assign(lags, subs)
+        assert got == exp
+        a.close()
