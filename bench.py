@@ -484,7 +484,10 @@ def main():
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "bytes_model": alg_note,
-                         "launch_ms": per_launch_ms, "share_of_step": share},
+                         "launch_ms": per_launch_ms, "share_of_step": share,
+                         "note": ("launch-bound step: a kernel of %.0f us is about the cost of launching and draining it on 148 "
+                                  "SMs, so the HBM fraction says little here" % (per_launch_ms * 1e3))
+                                 if (alg and per_launch_ms < 0.03) else None},
             "kernel_ms_per_step": {k: v[0] / n_prof for k, v in prof_acc.items()},
             "ms_per_step_unprofiled": t_unprofiled_ms,
             "ms_per_step_profiled": t_profiled_ms,
